@@ -1,0 +1,1068 @@
+// aps_abi.cu -- the extern "C" surface declared in include/apsmatch.h: argument checks with the
+// reference's error identifiers, host<->device staging, and the kernel pipelines.
+// No CPU compute path exists here: without a CUDA device every entry fails with APS_ERR_NOGPU.
+#include <cmath>
+#include <limits>
+#include <new>
+#include <string>
+
+#include "aps_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+static thread_local std::string g_err_msg;
+static thread_local std::string g_err_id;
+
+void aps_set_error(int code, const char* id, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err_msg = buf;
+  g_err_id = id ? id : "";
+  (void)code;
+}
+
+extern "C" const char* aps_last_error(void) { return g_err_msg.c_str(); }
+extern "C" const char* aps_error_id(void) { return g_err_id.c_str(); }
+extern "C" int aps_abi_version(void) { return APS_ABI_VERSION; }
+
+#define APS_FAIL(code, id, ...)            \
+  do {                                     \
+    aps_set_error(code, id, __VA_ARGS__);  \
+    return code;                           \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+extern "C" int aps_ctx_create(int device, aps_ctx** out) {
+  if (!out) APS_FAIL(APS_ERR_ARGS, "", "aps_ctx_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    APS_FAIL(APS_ERR_NOGPU, "apsmatch:nogpu",
+             "no CUDA device available (%s); libapsmatch has no CPU fallback",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev) APS_FAIL(APS_ERR_ARGS, "", "device %d out of range (0..%d)", device, ndev - 1);
+  APS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  APS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    APS_FAIL(APS_ERR_NOGPU, "apsmatch:nogpu", "device %d is sm_%d%d; libapsmatch is built for sm_100a (B200) only",
+             device, prop.major, prop.minor);
+  aps_ctx* c = new (std::nothrow) aps_ctx();
+  if (!c) APS_FAIL(APS_ERR_ALLOC, "", "out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  APS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  cudaMemPool_t pool;
+  APS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  APS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  APS_CUDA(cudaMalloc((void**)&c->d_scratch_flags, 64 * sizeof(int32_t)));
+  APS_CUDA(cudaMallocHost((void**)&c->h_flags, 64 * sizeof(int32_t)));
+  *out = c;
+  return APS_OK;
+}
+
+extern "C" void aps_ctx_destroy(aps_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->d_scratch_flags) cudaFree(c->d_scratch_flags);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int aps_ctx_set_stream(aps_ctx* c, void* cuda_stream) {
+  if (!c) APS_FAIL(APS_ERR_ARGS, "", "ctx is NULL");
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)cuda_stream;
+  c->own_stream = false;
+  return APS_OK;
+}
+
+extern "C" int aps_ctx_synchronize(aps_ctx* c) {
+  if (!c) APS_FAIL(APS_ERR_ARGS, "", "ctx is NULL");
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  return APS_OK;
+}
+
+extern "C" int aps_ctx_set_float_engine(aps_ctx* c, int engine) {
+  if (!c || engine < 0 || engine > 2) APS_FAIL(APS_ERR_ARGS, "", "bad engine");
+  c->float_engine = engine;
+  return APS_OK;
+}
+
+extern "C" int aps_ctx_last_stats(aps_ctx* c, int64_t stats[4]) {
+  if (!c || !stats) APS_FAIL(APS_ERR_ARGS, "", "bad args");
+  for (int i = 0; i < 4; ++i) stats[i] = c->stats[i];
+  return APS_OK;
+}
+
+extern "C" void* aps_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void aps_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+#define APS_CTX(c)                                                        \
+  do {                                                                    \
+    if (!(c)) APS_FAIL(APS_ERR_NOGPU, "apsmatch:nogpu", "context is NULL (no GPU context; there is no CPU path)"); \
+    APS_CUDA(cudaSetDevice((c)->device));                                 \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// staging helpers
+static int stage_matrix(aps_ctx* c, const void* host, int64_t N, int D, int esz, int layout, void* dst_rm,
+                        DevBuf<uint8_t>& tmp) {
+  if (N == 0 || D == 0) return APS_OK;
+  size_t bytes = (size_t)N * D * esz;
+  if (layout == APS_ROW_MAJOR) {
+    APS_CUDA(cudaMemcpyAsync(dst_rm, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    APS_TRY(tmp.alloc(bytes, c->stream));
+    APS_CUDA(cudaMemcpyAsync(tmp.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    APS_TRY(aps_k_transpose_in(c->stream, tmp.p, N, D, esz, dst_rm));
+  }
+  return APS_OK;
+}
+
+__global__ void k_pad_rows_u8(const uint8_t* __restrict__ src, int64_t N, int nb, int nb16, uint8_t* __restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * nb16) return;
+  int64_t r = i / nb16;
+  int c = (int)(i - r * nb16);
+  dst[i] = c < nb ? src[r * nb + c] : (uint8_t)0;
+}
+static int pad_rows(cudaStream_t s, const uint8_t* src, int64_t N, int nb, int nb16, uint8_t* dst) {
+  if (N == 0) return APS_OK;
+  k_pad_rows_u8<<<(unsigned)aps_ceil_div(N * nb16, 256), 256, 0, s>>>(src, N, nb, nb16, dst);
+  APS_CUDA(cudaGetLastError());
+  return APS_OK;
+}
+
+__global__ void k_add_offset_u32(uint32_t* idx, int64_t n, uint32_t off) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && idx[i] != 0u) idx[i] += off;
+}
+
+static int copy_out_matrix(aps_ctx* c, const uint32_t* idx_rm, const float* dist_rm, int64_t N, int k, int layout,
+                           uint32_t* h_idx, float* h_dist) {
+  if (N == 0) return APS_OK;
+  if (layout == APS_ROW_MAJOR) {
+    APS_CUDA(cudaMemcpyAsync(h_idx, idx_rm, (size_t)N * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    APS_CUDA(cudaMemcpyAsync(h_dist, dist_rm, (size_t)N * k * 4, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    DevBuf<uint32_t> ic;
+    DevBuf<float> dc;
+    APS_TRY(ic.alloc((size_t)N * k, c->stream));
+    APS_TRY(dc.alloc((size_t)N * k, c->stream));
+    APS_TRY(aps_k_transpose_out_u32f32(c->stream, idx_rm, dist_rm, N, k, ic.p, dc.p));
+    APS_CUDA(cudaMemcpyAsync(h_idx, ic.p, (size_t)N * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    APS_CUDA(cudaMemcpyAsync(h_dist, dc.p, (size_t)N * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    APS_CUDA(cudaStreamSynchronize(c->stream));
+    return APS_OK;
+  }
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  return APS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// float search driver: tcgen05 candidates + exact re-rank (+ exact fallback rows), or exact only.
+struct FloatSide {          // one prepared descriptor set
+  const float* raw = nullptr;  // [N x D]
+  const float* xn = nullptr;   // normalised (or == raw)
+  const float* sq = nullptr;   // sum(xn^2)
+  const float* invn = nullptr;
+  const __nv_bfloat16* xb = nullptr;  // [N x Dp] or nullptr when the tensor path is not prepared
+  const float2* colsb = nullptr;
+  int64_t N = 0;
+};
+
+static bool tc_wanted(const aps_ctx* c, int D, int64_t nq, int64_t nt) {
+  if (c->float_engine == 1) return false;
+  int Dp = (D + 63) / 64 * 64;
+  if (!aps_k_knn_tc_supported(Dp)) return false;
+  if (c->float_engine == 2) return true;
+  return nq * nt >= (int64_t)1 << 22;  // tiny problems: launch-bound either way, stay exact
+}
+
+// metric 0: FLANN-order squared L2 (global path) ; metric 1: SSD (pairwise path)
+static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, const FloatSide& T, int64_t t0,
+                     int64_t t1, int D, int k, int metric, int bias_mode, const int32_t* flags_dev,
+                     int64_t out_row0, uint32_t* idx, float* dist, bool use_tc) {
+  const int64_t nq = q1 - q0;
+  if (nq <= 0) return APS_OK;
+  c->stats[0] += nq;
+  if (!use_tc || t1 - t0 < k + 1) {
+    c->stats[2] = 1;
+    return aps_k_knn_exact(c->stream, Q.xn, Q.sq, nullptr, nullptr, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
+                           out_row0, idx, dist);
+  }
+  c->stats[2] = 2;
+  const int Dp = (D + 63) / 64 * 64;
+  const int kcand = 8;
+  // column segments: enough (row block, segment) units to balance the persistent grid
+  const int64_t row_blocks = aps_ceil_div(nq, 128);
+  int nseg = 1;
+  const int64_t tiles = aps_ceil_div(t1 - t0, 256);
+  while (row_blocks * nseg < 4 * (int64_t)c->sm_count && nseg * 2 <= tiles && nseg < 4) nseg *= 2;
+  DevBuf<uint32_t> cidx;
+  DevBuf<float> cscore;
+  DevBuf<int32_t> fb;
+  APS_TRY(cidx.alloc((size_t)nq * nseg * kcand, c->stream));
+  APS_TRY(cscore.alloc((size_t)nq * nseg * kcand, c->stream));
+  APS_TRY(fb.alloc((size_t)nq + 1, c->stream));
+  APS_CUDA(cudaMemsetAsync(fb.p + nq, 0, sizeof(int32_t), c->stream));
+  aps_tc_problem p;
+  p.Qb = Q.xb;
+  p.Tb = T.xb;
+  p.colsb = T.colsb;
+  p.Fq_total = Q.N;
+  p.Ft_total = T.N;
+  p.Dp = Dp;
+  p.q0 = q0;
+  p.q1 = q1;
+  p.t0 = t0;
+  p.t1 = t1;
+  p.nseg = nseg;
+  p.kcand = kcand;
+  p.cand_idx = cidx.p;
+  p.cand_score = cscore.p;
+  p.dump = nullptr;
+  APS_TRY(aps_k_knn_tc(c->stream, c->sm_count, p));
+  APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nseg, kcand, cidx.p,
+                       cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq));
+  // rows that could not be proven complete: exact search (device-side count, no host round trip)
+  APS_TRY(aps_k_knn_exact(c->stream, Q.xn, Q.sq, fb.p, fb.p + nq, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
+                          out_row0, idx, dist));
+  APS_CUDA(cudaMemcpyAsync(c->h_flags + 32, fb.p + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  return APS_OK;
+}
+
+// Prepared float set owning its buffers
+struct FloatSet {
+  DevBuf<float> raw, xn, sq, invn;
+  DevBuf<__nv_bfloat16> xb;
+  DevBuf<float2> colsb;
+  DevBuf<int32_t> flags;  // [8]: exact, maxdev bits, maxsq bits, maxabs bits
+  int64_t N = 0;
+  int D = 0;
+  FloatSide side() const {
+    FloatSide s;
+    s.raw = raw.p;
+    s.xn = xn.p ? xn.p : raw.p;
+    s.sq = sq.p;
+    s.invn = invn.p;
+    s.xb = xb.p;
+    s.colsb = colsb.p;
+    s.N = N;
+    return s;
+  }
+};
+
+static int floatset_alloc(aps_ctx* c, FloatSet& fs, int64_t N, int D) {
+  fs.N = N;
+  fs.D = D;
+  APS_TRY(fs.raw.alloc((size_t)N * D, c->stream));
+  APS_TRY(fs.sq.alloc((size_t)N, c->stream));
+  APS_TRY(fs.invn.alloc((size_t)N, c->stream));
+  APS_TRY(fs.flags.alloc(8, c->stream));
+  return APS_OK;
+}
+
+static int floatset_reset_flags(aps_ctx* c, FloatSet& fs) {
+  static const int32_t init[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  APS_CUDA(cudaMemcpyAsync(fs.flags.p, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  return APS_OK;
+}
+
+// normalise + (optionally) build tensor operands
+static int floatset_prepare(aps_ctx* c, FloatSet& fs, int norm_mode, bool tensor, int bias_mode) {
+  if (fs.N == 0) return APS_OK;
+  if (norm_mode != APS_NORM_NONE && !fs.xn.p) APS_TRY(fs.xn.alloc((size_t)fs.N * fs.D, c->stream));
+  float* xn = (norm_mode != APS_NORM_NONE) ? fs.xn.p : fs.raw.p;
+  APS_TRY(aps_k_prepare_norm(c->stream, fs.raw.p, fs.N, fs.D, norm_mode, xn, fs.sq.p, fs.invn.p, fs.flags.p));
+  if (tensor) {
+    const int Dp = (fs.D + 63) / 64 * 64;
+    APS_TRY(fs.xb.alloc((size_t)fs.N * Dp, c->stream));
+    APS_TRY(fs.colsb.alloc((size_t)fs.N, c->stream));
+    APS_TRY(aps_k_prepare_operands(c->stream, fs.raw.p, xn, fs.sq.p, fs.invn.p, fs.N, fs.D, Dp, fs.flags.p,
+                                   bias_mode, fs.xb.p, fs.colsb.p));
+  }
+  return APS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flann_knn_win
+extern "C" int aps_flann_knn(aps_ctx* c, const void* train, int64_t Ft, const void* query, int64_t Fq, int D,
+                             int dtype, int layout, int k, const char* method, int trees, int checks,
+                             uint32_t* idx, float* dist) {
+  (void)trees;
+  (void)checks;
+  APS_CTX(c);
+  if (dtype != APS_F32 && dtype != APS_U8)
+    APS_FAIL(APS_ERR_TYPE, "flann_knn:type", "Descriptors must be single (float) or uint8 (binary)");
+  if (k <= 0) APS_FAIL(APS_ERR_K, "flann_knn:k", "k must be > 0");
+  if (k > APS_MAX_K) APS_FAIL(APS_ERR_K, "flann_knn:k", "k must be <= %d in this implementation", APS_MAX_K);
+  if (D <= 0 && (Ft > 0 || Fq > 0)) APS_FAIL(APS_ERR_DIM, "flann_knn:dim", "descriptor dimension must be positive");
+  std::string m = method ? method : "flann";
+  if (m != "flann" && m != "bf") APS_FAIL(APS_ERR_METHOD, "flann_knn:args", "unknown method '%s'", m.c_str());
+  if (m == "bf" && dtype != APS_U8)
+    APS_FAIL(APS_ERR_BF, "flann_knn:bf", "BFMatcher only supports uint8 (binary) descriptors");
+  if ((Ft > 0 && !train) || (Fq > 0 && (!query || !idx || !dist)))
+    APS_FAIL(APS_ERR_ARGS, "flann_knn:args", "null pointer argument");
+  if (Fq == 0) return APS_OK;
+  c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
+  DevBuf<uint32_t> didx;
+  DevBuf<float> ddist;
+  DevBuf<uint8_t> tmp;
+  APS_TRY(didx.alloc((size_t)Fq * k, c->stream));
+  APS_TRY(ddist.alloc((size_t)Fq * k, c->stream));
+  const bool self = (train == query && Ft == Fq);
+  if (dtype == APS_U8) {
+    const int nb16 = (D + 15) / 16 * 16;
+    DevBuf<uint8_t> t_raw, q_raw, t_pad, q_pad;
+    APS_TRY(t_raw.alloc((size_t)Ft * D, c->stream));
+    APS_TRY(t_pad.alloc((size_t)Ft * nb16, c->stream));
+    APS_TRY(stage_matrix(c, train, Ft, D, 1, layout, t_raw.p, tmp));
+    APS_TRY(pad_rows(c->stream, t_raw.p, Ft, D, nb16, t_pad.p));
+    const uint8_t* qp = t_pad.p;
+    if (!self) {
+      APS_TRY(q_raw.alloc((size_t)Fq * D, c->stream));
+      APS_TRY(q_pad.alloc((size_t)Fq * nb16, c->stream));
+      APS_TRY(stage_matrix(c, query, Fq, D, 1, layout, q_raw.p, tmp));
+      APS_TRY(pad_rows(c->stream, q_raw.p, Fq, D, nb16, q_pad.p));
+      qp = q_pad.p;
+    }
+    APS_TRY(aps_k_knn_hamming(c->stream, qp, 0, Fq, t_pad.p, 0, Ft, nb16, k, 0, didx.p, ddist.p));
+    c->stats[0] = Fq;
+    c->stats[2] = 1;
+    return copy_out_matrix(c, didx.p, ddist.p, Fq, k, layout, idx, dist);
+  }
+  // float: the caller passes what featureMatchingGlobal.m:80-84 already normalised -> no normalisation here
+  const bool tc = tc_wanted(c, D, Fq, Ft);
+  FloatSet T, Q;
+  APS_TRY(floatset_alloc(c, T, Ft, D));
+  APS_TRY(floatset_reset_flags(c, T));
+  APS_TRY(stage_matrix(c, train, Ft, D, 4, layout, T.raw.p, tmp));
+  APS_TRY(floatset_prepare(c, T, APS_NORM_NONE, tc, /*bias: rows need not be unit norm*/ 1));
+  FloatSide qs = T.side();
+  if (!self) {
+    APS_TRY(floatset_alloc(c, Q, Fq, D));
+    Q.flags.release();
+    // share the flag words with the train set: exactness / magnitude bounds must hold for both sides
+    APS_TRY(stage_matrix(c, query, Fq, D, 4, layout, Q.raw.p, tmp));
+    if (Fq > 0) {
+      APS_TRY(aps_k_prepare_norm(c->stream, Q.raw.p, Fq, D, APS_NORM_NONE, Q.raw.p, Q.sq.p, Q.invn.p, T.flags.p));
+      if (tc) {
+        const int Dp = (D + 63) / 64 * 64;
+        APS_TRY(Q.xb.alloc((size_t)Fq * Dp, c->stream));
+        APS_TRY(Q.colsb.alloc((size_t)Fq, c->stream));
+        // NOTE: operands of BOTH sides are built after both flag passes ran (same stream order)
+        APS_TRY(aps_k_prepare_operands(c->stream, Q.raw.p, Q.raw.p, Q.sq.p, Q.invn.p, Fq, D, Dp, T.flags.p, 1,
+                                       Q.xb.p, Q.colsb.p));
+        APS_TRY(aps_k_prepare_operands(c->stream, T.raw.p, T.raw.p, T.sq.p, T.invn.p, Ft, D, Dp, T.flags.p, 1,
+                                       T.xb.p, T.colsb.p));
+      }
+    }
+    qs = Q.side();
+    qs.xn = Q.raw.p;
+  }
+  APS_TRY(float_knn(c, qs, 0, Fq, T.side(), 0, Ft, D, k, /*metric*/ 0, /*bias_mode*/ 1, T.flags.p, 0, didx.p,
+                    ddist.p, tc));
+  int rc = copy_out_matrix(c, didx.p, ddist.p, Fq, k, layout, idx, dist);
+  c->stats[1] = c->h_flags[32];
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest2HammingExhaustive{,OMP}MEX
+static int hamming2_device(aps_ctx* c, const uint8_t* qpad, int64_t q0, int64_t N1, const uint8_t* tpad, int64_t t0,
+                           int64_t N2, int nb, int nb16, uint32_t* idx2, float* d1, float* d2) {
+  DevBuf<uint32_t> i2;
+  DevBuf<float> dd;
+  APS_TRY(i2.alloc((size_t)N1 * 2, c->stream));
+  APS_TRY(dd.alloc((size_t)N1 * 2, c->stream));
+  if (N2 > 0) APS_TRY(aps_k_knn_hamming(c->stream, qpad, q0, N1, tpad, t0, t0 + N2, nb16, 2, q0, i2.p, dd.p));
+  APS_TRY(aps_k_hamming2_finalize(c->stream, N1, N2, nb, i2.p, dd.p, idx2, d1, d2));
+  return APS_OK;
+}
+
+extern "C" int aps_nearest2_hamming(aps_ctx* c, const uint8_t* A, int64_t N1, const uint8_t* B, int64_t N2, int nb,
+                                    int layout, uint32_t* idx2, float* d1, float* d2) {
+  APS_CTX(c);
+  if ((N1 > 0 && (!A || !idx2 || !d1 || !d2)) || (N2 > 0 && !B))
+    APS_FAIL(APS_ERR_ARGS, "hamm2nn:nrhs", "Need Abytes,Bbytes");
+  if (nb <= 0 && (N1 > 0 || N2 > 0)) APS_FAIL(APS_ERR_DIM, "hamm2nn:cols", "Byte width mismatch.");
+  if (N1 == 0) return APS_OK;
+  const int nb16 = (nb + 15) / 16 * 16;
+  DevBuf<uint8_t> a_raw, b_raw, a_pad, b_pad, tmp;
+  APS_TRY(a_raw.alloc((size_t)N1 * nb, c->stream));
+  APS_TRY(a_pad.alloc((size_t)N1 * nb16, c->stream));
+  APS_TRY(b_raw.alloc((size_t)N2 * nb, c->stream));
+  APS_TRY(b_pad.alloc((size_t)N2 * nb16, c->stream));
+  APS_TRY(stage_matrix(c, A, N1, nb, 1, layout, a_raw.p, tmp));
+  APS_TRY(stage_matrix(c, B, N2, nb, 1, layout, b_raw.p, tmp));
+  APS_TRY(pad_rows(c->stream, a_raw.p, N1, nb, nb16, a_pad.p));
+  APS_TRY(pad_rows(c->stream, b_raw.p, N2, nb, nb16, b_pad.p));
+  DevBuf<uint32_t> di;
+  DevBuf<float> dd1, dd2;
+  APS_TRY(di.alloc((size_t)N1, c->stream));
+  APS_TRY(dd1.alloc((size_t)N1, c->stream));
+  APS_TRY(dd2.alloc((size_t)N1, c->stream));
+  APS_TRY(hamming2_device(c, a_pad.p, 0, N1, b_pad.p, 0, N2, nb, nb16, di.p, dd1.p, dd2.p));
+  APS_CUDA(cudaMemcpyAsync(idx2, di.p, (size_t)N1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaMemcpyAsync(d1, dd1.p, (size_t)N1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaMemcpyAsync(d2, dd2.p, (size_t)N1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  return APS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest2SSDExhaustive (device part shared with matchFeaturesScratch / pairwise)
+static int ssd2_device(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t N1, const FloatSide& T, int64_t t0,
+                       int64_t N2, int D, const int32_t* flags, bool tc, int bias_mode, uint32_t* idx2, float* d1,
+                       float* d2) {
+  DevBuf<uint32_t> i2;
+  DevBuf<float> dd;
+  APS_TRY(i2.alloc((size_t)N1 * 2, c->stream));
+  APS_TRY(dd.alloc((size_t)N1 * 2, c->stream));
+  if (N2 > 0) {
+    APS_TRY(float_knn(c, Q, q0, q0 + N1, T, t0, t0 + N2, D, 2, /*metric*/ 1, bias_mode, flags, q0, i2.p, dd.p, tc));
+  } else {
+    // N2 == 0 -> idx 0, +inf, +inf (documented deviation: MATLAB's validateattributes throws)
+    APS_CUDA(cudaMemsetAsync(i2.p, 0, (size_t)N1 * 2 * 4, c->stream));
+    std::vector<float> inf((size_t)N1 * 2, std::numeric_limits<float>::infinity());
+    APS_CUDA(cudaMemcpyAsync(dd.p, inf.data(), inf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    APS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  APS_TRY(aps_k_split_k2(c->stream, N1, i2.p, dd.p, idx2, d1, d2));
+  return APS_OK;
+}
+
+extern "C" int aps_nearest2_ssd(aps_ctx* c, const float* A, int64_t N1, const float* B, int64_t N2, int D,
+                                int layout, uint32_t* idx2, float* d1, float* d2) {
+  APS_CTX(c);
+  if ((N1 > 0 && (!A || !idx2 || !d1 || !d2)) || (N2 > 0 && !B)) APS_FAIL(APS_ERR_ARGS, "", "null pointer argument");
+  if (D <= 0) APS_FAIL(APS_ERR_DIM, "", "descriptor dimension must be positive");
+  if (N1 == 0) return APS_OK;
+  c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
+  const bool tc = tc_wanted(c, D, N1, N2);
+  FloatSet QA, TB;
+  DevBuf<uint8_t> tmp;
+  APS_TRY(floatset_alloc(c, QA, N1, D));
+  APS_TRY(floatset_alloc(c, TB, N2, D));
+  APS_TRY(floatset_reset_flags(c, TB));
+  APS_TRY(stage_matrix(c, A, N1, D, 4, layout, QA.raw.p, tmp));
+  APS_TRY(stage_matrix(c, B, N2, D, 4, layout, TB.raw.p, tmp));
+  APS_TRY(aps_k_prepare_norm(c->stream, QA.raw.p, N1, D, APS_NORM_NONE, QA.raw.p, QA.sq.p, QA.invn.p, TB.flags.p));
+  APS_TRY(aps_k_prepare_norm(c->stream, TB.raw.p, N2, D, APS_NORM_NONE, TB.raw.p, TB.sq.p, TB.invn.p, TB.flags.p));
+  if (tc) {
+    const int Dp = (D + 63) / 64 * 64;
+    APS_TRY(QA.xb.alloc((size_t)N1 * Dp, c->stream));
+    APS_TRY(QA.colsb.alloc((size_t)N1, c->stream));
+    APS_TRY(TB.xb.alloc((size_t)N2 * Dp, c->stream));
+    APS_TRY(TB.colsb.alloc((size_t)N2, c->stream));
+    APS_TRY(aps_k_prepare_operands(c->stream, QA.raw.p, QA.raw.p, QA.sq.p, QA.invn.p, N1, D, Dp, TB.flags.p, 1,
+                                   QA.xb.p, QA.colsb.p));
+    APS_TRY(aps_k_prepare_operands(c->stream, TB.raw.p, TB.raw.p, TB.sq.p, TB.invn.p, N2, D, Dp, TB.flags.p, 1,
+                                   TB.xb.p, TB.colsb.p));
+  }
+  DevBuf<uint32_t> di;
+  DevBuf<float> dd1, dd2;
+  APS_TRY(di.alloc((size_t)N1, c->stream));
+  APS_TRY(dd1.alloc((size_t)N1, c->stream));
+  APS_TRY(dd2.alloc((size_t)N1, c->stream));
+  APS_TRY(ssd2_device(c, QA.side(), 0, N1, TB.side(), 0, N2, D, TB.flags.p, tc, 1, di.p, dd1.p, dd2.p));
+  APS_CUDA(cudaMemcpyAsync(idx2, di.p, (size_t)N1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaMemcpyAsync(d1, dd1.p, (size_t)N1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaMemcpyAsync(d2, dd2.p, (size_t)N1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  c->stats[1] = c->h_flags[32];
+  return APS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// match lists
+struct aps_matchlist {
+  int n = 0;
+  int64_t total = 0;
+  std::vector<int64_t> pair_ptr;
+  std::vector<uint32_t> rows;
+  std::vector<double> metric;
+  bool has_metric = false;
+};
+extern "C" int aps_matchlist_n(const aps_matchlist* m) { return m ? m->n : 0; }
+extern "C" int64_t aps_matchlist_total(const aps_matchlist* m) { return m ? m->total : 0; }
+extern "C" const int64_t* aps_matchlist_pair_ptr(const aps_matchlist* m) { return m ? m->pair_ptr.data() : nullptr; }
+extern "C" const uint32_t* aps_matchlist_rows(const aps_matchlist* m) { return m ? m->rows.data() : nullptr; }
+extern "C" const double* aps_matchlist_metric(const aps_matchlist* m) {
+  return (m && m->has_metric) ? m->metric.data() : nullptr;
+}
+extern "C" void aps_matchlist_free(aps_matchlist* m) { delete m; }
+
+// ------------------------------------------------------------------------------------------------
+// staged global pipeline
+struct aps_gplan {
+  aps_ctx* c = nullptr;
+  int n = 0, D = 0, dtype = 0, k = 0;
+  int64_t F = 0, maxcount = 0;
+  std::vector<int64_t> counts, off;
+  bool tensor = false;
+  // descriptors
+  FloatSet fs;                    // float
+  DevBuf<uint8_t> u8raw, u8pad;   // binary
+  int nb16 = 0;
+  DevBuf<uint8_t> stage_tmp;
+  // bookkeeping
+  DevBuf<int64_t> d_off;
+  DevBuf<int32_t> img_of_row;
+  // results
+  DevBuf<uint32_t> knn_idx;
+  DevBuf<float> knn_dist;
+  DevBuf<int32_t> records;  // target[F] then partner[F]
+  DevBuf<int64_t> dir_counts, pair_counts, pair_ptr, rank;
+  DevBuf<uint32_t> rows;
+  bool compacted = false;
+};
+
+extern "C" int aps_gplan_create(aps_ctx* c, const int64_t* counts, int n, int D, int dtype, int k, aps_gplan** out) {
+  APS_CTX(c);
+  if (!out || n < 0 || (n > 0 && !counts)) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  if (dtype != APS_F32 && dtype != APS_U8)
+    APS_FAIL(APS_ERR_TYPE, "flann_knn:type", "Descriptors must be single (float) or uint8 (binary)");
+  if (k <= 0) APS_FAIL(APS_ERR_K, "flann_knn:k", "k must be > 0");
+  if (k > APS_MAX_K) APS_FAIL(APS_ERR_K, "flann_knn:k", "k must be <= %d in this implementation", APS_MAX_K);
+  aps_gplan* p = new (std::nothrow) aps_gplan();
+  if (!p) APS_FAIL(APS_ERR_ALLOC, "", "out of host memory");
+  p->c = c;
+  p->n = n;
+  p->D = D;
+  p->dtype = dtype;
+  p->k = k;
+  p->counts.assign(counts, counts + n);
+  p->off.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    if (counts[i] < 0) {
+      delete p;
+      APS_FAIL(APS_ERR_ARGS, "", "negative feature count");
+    }
+    p->off[i + 1] = p->off[i] + counts[i];
+    if (counts[i] > p->maxcount) p->maxcount = counts[i];
+  }
+  p->F = p->off[n];
+  if (p->F > 0 && D <= 0) {
+    delete p;
+    APS_FAIL(APS_ERR_DIM, "flann_knn:dim", "descriptor dimension must be positive");
+  }
+  if (p->F >= ((int64_t)1 << 31) - 1) {
+    delete p;
+    APS_FAIL(APS_ERR_ARGS, "", "more than 2^31 descriptors are not supported");
+  }
+  const int64_t F = p->F;
+  cudaStream_t s = c->stream;
+  int rc = APS_OK;
+  auto A = [&](int r) { if (rc == APS_OK) rc = r; };
+  if (dtype == APS_F32) {
+    p->tensor = tc_wanted(c, D, F, F);
+    A(floatset_alloc(c, p->fs, F, D));
+  } else {
+    p->nb16 = (D + 15) / 16 * 16;
+    A(p->u8raw.alloc((size_t)F * D, s));
+    A(p->u8pad.alloc((size_t)F * p->nb16, s));
+  }
+  A(p->d_off.alloc((size_t)n + 1, s));
+  A(p->img_of_row.alloc((size_t)F, s));
+  A(p->knn_idx.alloc((size_t)F * k, s));
+  A(p->knn_dist.alloc((size_t)F * k, s));
+  A(p->records.alloc((size_t)F * 2, s));
+  A(p->dir_counts.alloc((size_t)n * n, s));
+  A(p->pair_counts.alloc((size_t)n * n, s));
+  A(p->pair_ptr.alloc((size_t)n * n + 1, s));
+  A(p->rank.alloc((size_t)F, s));
+  A(p->rows.alloc((size_t)F * 2, s));
+  if (rc == APS_OK && cudaMemcpyAsync(p->d_off.p, p->off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s) != cudaSuccess)
+    rc = APS_ERR_CUDA;
+  if (rc == APS_OK) rc = aps_k_fill_img_of_row(s, p->d_off.p, n, p->maxcount, p->img_of_row.p);
+  if (rc == APS_OK && F > 0 && cudaMemsetAsync(p->records.p, 0, (size_t)F * 8, s) != cudaSuccess) rc = APS_ERR_CUDA;
+  if (rc != APS_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return APS_OK;
+}
+
+extern "C" void aps_gplan_destroy(aps_gplan* p) {
+  if (!p) return;
+  cudaSetDevice(p->c->device);
+  delete p;
+}
+extern "C" int64_t aps_gplan_total(const aps_gplan* p) { return p ? p->F : 0; }
+extern "C" void* aps_gplan_desc_device(aps_gplan* p) {
+  if (!p) return nullptr;
+  return p->dtype == APS_F32 ? (void*)p->fs.raw.p : (void*)p->u8raw.p;
+}
+extern "C" void* aps_gplan_records_device(aps_gplan* p) { return p ? p->records.p : nullptr; }
+extern "C" void* aps_gplan_knn_idx_device(aps_gplan* p) { return p ? p->knn_idx.p : nullptr; }
+extern "C" void* aps_gplan_knn_dist_device(aps_gplan* p) { return p ? p->knn_dist.p : nullptr; }
+
+extern "C" int aps_gplan_upload(aps_gplan* p, const void* const* desc, int layout) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  const int esz = p->dtype == APS_F32 ? 4 : 1;
+  char* base = (char*)aps_gplan_desc_device(p);
+  if (layout == APS_COL_MAJOR && p->F > 0) APS_TRY(p->stage_tmp.alloc((size_t)p->F * p->D * esz, c->stream));
+  for (int i = 0; i < p->n; ++i) {
+    const int64_t Ni = p->counts[i];
+    if (Ni == 0) continue;
+    if (!desc || !desc[i]) APS_FAIL(APS_ERR_ARGS, "", "descriptor pointer %d is NULL but its count is %lld", i, (long long)Ni);
+    char* dst = base + (size_t)p->off[i] * p->D * esz;
+    size_t bytes = (size_t)Ni * p->D * esz;
+    if (layout == APS_ROW_MAJOR) {
+      APS_CUDA(cudaMemcpyAsync(dst, desc[i], bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+      char* st = (char*)p->stage_tmp.p + (size_t)p->off[i] * p->D * esz;
+      APS_CUDA(cudaMemcpyAsync(st, desc[i], bytes, cudaMemcpyHostToDevice, c->stream));
+      APS_TRY(aps_k_transpose_in(c->stream, st, Ni, p->D, esz, dst));
+    }
+  }
+  return APS_OK;
+}
+
+extern "C" int aps_gplan_prepare(aps_gplan* p) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  if (p->F == 0) return APS_OK;
+  if (p->dtype == APS_F32) {
+    APS_TRY(floatset_reset_flags(c, p->fs));
+    // featureMatchingGlobal.m:80-84 ; operands: scale-only scoring (rows are unit norm up to rounding)
+    APS_TRY(floatset_prepare(c, p->fs, APS_NORM_GLOBAL, p->tensor, /*bias_mode*/ 0));
+  } else {
+    APS_TRY(pad_rows(c->stream, p->u8raw.p, p->F, p->D, p->nb16, p->u8pad.p));
+  }
+  return APS_OK;
+}
+
+extern "C" int aps_gplan_knn(aps_gplan* p, int64_t q0, int64_t q1) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  if (q0 < 0 || q1 > p->F || q0 > q1) APS_FAIL(APS_ERR_ARGS, "", "query range out of bounds");
+  if (q0 == q1) return APS_OK;
+  c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
+  if (p->dtype == APS_F32) {
+    FloatSide s = p->fs.side();
+    APS_TRY(float_knn(c, s, q0, q1, s, 0, p->F, p->D, p->k, /*metric*/ 0, /*bias*/ 0, p->fs.flags.p, 0,
+                      p->knn_idx.p, p->knn_dist.p, p->tensor));
+  } else {
+    APS_TRY(aps_k_knn_hamming(c->stream, p->u8pad.p, q0, q1 - q0, p->u8pad.p, 0, p->F, p->nb16, p->k, 0,
+                              p->knn_idx.p, p->knn_dist.p));
+    c->stats[0] = q1 - q0;
+    c->stats[2] = 1;
+  }
+  return APS_OK;
+}
+
+extern "C" int aps_gplan_filter(aps_gplan* p, int64_t q0, int64_t q1, double ratio) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  if (q0 < 0 || q1 > p->F || q0 > q1) APS_FAIL(APS_ERR_ARGS, "", "query range out of bounds");
+  return aps_k_global_filter(c->stream, p->knn_idx.p, p->knn_dist.p, p->k, q0, q1, p->img_of_row.p, p->d_off.p,
+                             (float)ratio, p->records.p, (uint32_t*)(p->records.p + p->F));
+}
+
+extern "C" int aps_gplan_compact(aps_gplan* p) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  APS_TRY(aps_k_global_compact(c->stream, p->records.p, (const uint32_t*)(p->records.p + p->F), p->img_of_row.p,
+                               p->d_off.p, p->n, p->F, p->dir_counts.p, p->pair_counts.p, p->pair_ptr.p, p->rank.p,
+                               p->rows.p));
+  p->compacted = true;
+  return APS_OK;
+}
+
+extern "C" int aps_gplan_pair_counts_device(aps_gplan* p, void** counts_i64) {
+  if (!p || !counts_i64 || !p->compacted) APS_FAIL(APS_ERR_ARGS, "", "compact() has not run");
+  *counts_i64 = p->pair_counts.p;
+  return APS_OK;
+}
+
+extern "C" int aps_gplan_download(aps_gplan* p, aps_matchlist** out) {
+  if (!p || !out) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  aps_matchlist* m = new (std::nothrow) aps_matchlist();
+  if (!m) APS_FAIL(APS_ERR_ALLOC, "", "out of host memory");
+  m->n = p->n;
+  const size_t cells = (size_t)p->n * p->n;
+  m->pair_ptr.assign(cells + 1, 0);
+  if (p->n > 0 && p->compacted) {
+    cudaError_t e = cudaMemcpyAsync(m->pair_ptr.data(), p->pair_ptr.p, (cells + 1) * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      delete m;
+      APS_FAIL(APS_ERR_CUDA, "", "download failed: %s", cudaGetErrorString(e));
+    }
+    m->total = m->pair_ptr[cells];
+    m->rows.resize((size_t)m->total * 2);
+    if (m->total > 0) {
+      e = cudaMemcpyAsync(m->rows.data(), p->rows.p, (size_t)m->total * 8, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) {
+        delete m;
+        APS_FAIL(APS_ERR_CUDA, "", "download failed: %s", cudaGetErrorString(e));
+      }
+    }
+  } else {
+    APS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (p->dtype == APS_F32 && p->tensor) c->stats[1] = c->h_flags[32];
+  if (p->dtype == APS_F32 && p->F > 0) {
+    int32_t fl[8];
+    if (cudaMemcpy(fl, p->fs.flags.p, sizeof fl, cudaMemcpyDeviceToHost) == cudaSuccess) c->stats[3] = fl[0];
+  }
+  *out = m;
+  return APS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// featureMatchingGlobal : one call
+extern "C" int aps_feature_matching_global(aps_ctx* c, const void* const* desc, const int64_t* counts, int n, int D,
+                                           int dtype, int layout, int k, double ratio, int use_bf,
+                                           aps_matchlist** out) {
+  (void)use_bf;
+  APS_CTX(c);
+  if (!out) APS_FAIL(APS_ERR_ARGS, "", "out is NULL");
+  *out = nullptr;
+  aps_gplan* p = nullptr;
+  APS_TRY(aps_gplan_create(c, counts, n, D, dtype, k, &p));
+  int rc = APS_OK;
+  if (p->F > 0) {  // featureMatchingGlobal.m:49-52,65-67: all empty -> cell(numImg)
+    rc = aps_gplan_upload(p, desc, layout);
+    if (rc == APS_OK) rc = aps_gplan_prepare(p);
+    if (rc == APS_OK) rc = aps_gplan_knn(p, 0, p->F);
+    if (rc == APS_OK) rc = aps_gplan_filter(p, 0, p->F, ratio);
+    if (rc == APS_OK) rc = aps_gplan_compact(p);
+  }
+  if (rc == APS_OK) rc = aps_gplan_download(p, out);
+  aps_gplan_destroy(p);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// matchFeaturesScratch / featureMatchingPairwise
+struct PairwiseSets {
+  // per-image views: raw (un-normalised) and normalised (matchFeaturesScratch.m:105-110 is a
+  // per-PAIR decision: normalise both iff max|A|>2 or max|B|>2)
+  FloatSet rawset, normset;  // float
+  DevBuf<uint8_t> u8raw, u8pad;
+  int nb16 = 0;
+  std::vector<int64_t> off;
+  std::vector<int> big;  // per image: max|.| > 2
+};
+
+static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* desc, const int64_t* counts, int n,
+                            int D, int dtype, int layout, bool tensor) {
+  ps.off.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) ps.off[i + 1] = ps.off[i] + counts[i];
+  const int64_t F = ps.off[n];
+  DevBuf<uint8_t> tmp;
+  const int esz = dtype == APS_F32 ? 4 : 1;
+  char* base = nullptr;
+  if (dtype == APS_F32) {
+    APS_TRY(floatset_alloc(c, ps.rawset, F, D));
+    base = (char*)ps.rawset.raw.p;
+  } else {
+    ps.nb16 = (D + 15) / 16 * 16;
+    APS_TRY(ps.u8raw.alloc((size_t)F * D, c->stream));
+    APS_TRY(ps.u8pad.alloc((size_t)F * ps.nb16, c->stream));
+    base = (char*)ps.u8raw.p;
+  }
+  DevBuf<uint8_t> stage;
+  if (layout == APS_COL_MAJOR && F > 0) APS_TRY(stage.alloc((size_t)F * D * esz, c->stream));
+  for (int i = 0; i < n; ++i) {
+    if (counts[i] == 0) continue;
+    if (!desc || !desc[i]) APS_FAIL(APS_ERR_ARGS, "", "descriptor pointer %d is NULL", i);
+    char* dst = base + (size_t)ps.off[i] * D * esz;
+    size_t bytes = (size_t)counts[i] * D * esz;
+    if (layout == APS_ROW_MAJOR) {
+      APS_CUDA(cudaMemcpyAsync(dst, desc[i], bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+      char* st = (char*)stage.p + (size_t)ps.off[i] * D * esz;
+      APS_CUDA(cudaMemcpyAsync(st, desc[i], bytes, cudaMemcpyHostToDevice, c->stream));
+      APS_TRY(aps_k_transpose_in(c->stream, st, counts[i], D, esz, dst));
+    }
+  }
+  if (dtype == APS_U8) {
+    APS_TRY(pad_rows(c->stream, ps.u8raw.p, F, D, ps.nb16, ps.u8pad.p));
+    return APS_OK;
+  }
+  if (F == 0) return APS_OK;
+  // per-image max|.|: run the norm pass image by image with its own flag words
+  DevBuf<int32_t> imgflags;
+  APS_TRY(imgflags.alloc((size_t)n * 8, c->stream));
+  std::vector<int32_t> init((size_t)n * 8, 0);
+  for (int i = 0; i < n; ++i) init[(size_t)i * 8] = 1;
+  APS_CUDA(cudaMemcpyAsync(imgflags.p, init.data(), init.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  for (int i = 0; i < n; ++i)
+    if (counts[i] > 0)
+      APS_TRY(aps_k_prepare_norm(c->stream, ps.rawset.raw.p + (size_t)ps.off[i] * D, counts[i], D, APS_NORM_NONE,
+                                 ps.rawset.raw.p + (size_t)ps.off[i] * D, ps.rawset.sq.p + ps.off[i],
+                                 ps.rawset.invn.p + ps.off[i], imgflags.p + (size_t)i * 8));
+  std::vector<int32_t> hf((size_t)n * 8);
+  APS_CUDA(cudaMemcpyAsync(hf.data(), imgflags.p, hf.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  ps.big.assign(n, 0);
+  bool any_big = false, all_exact = true, any_small = false;
+  for (int i = 0; i < n; ++i) {
+    if (counts[i] == 0) continue;
+    float maxabs;
+    memcpy(&maxabs, &hf[(size_t)i * 8 + 3], 4);
+    ps.big[i] = maxabs > 2.0f;
+    any_big |= ps.big[i] != 0;
+    any_small |= ps.big[i] == 0;
+    all_exact &= hf[(size_t)i * 8] != 0;
+  }
+  (void)any_small;
+  // flag words shared by all images of a view (exactness must hold on both sides of every pair)
+  APS_TRY(floatset_reset_flags(c, ps.rawset));
+  {
+    int32_t fl[8] = {all_exact ? 1 : 0, 0, 0, 0, 0, 0, 0, 0};
+    APS_CUDA(cudaMemcpyAsync(ps.rawset.flags.p, fl, sizeof fl, cudaMemcpyHostToDevice, c->stream));
+    APS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (tensor) {
+    const int Dp = (D + 63) / 64 * 64;
+    APS_TRY(ps.rawset.xb.alloc((size_t)F * Dp, c->stream));
+    APS_TRY(ps.rawset.colsb.alloc((size_t)F, c->stream));
+    APS_TRY(aps_k_prepare_operands(c->stream, ps.rawset.raw.p, ps.rawset.raw.p, ps.rawset.sq.p, ps.rawset.invn.p, F,
+                                   D, Dp, ps.rawset.flags.p, 1, ps.rawset.xb.p, ps.rawset.colsb.p));
+  }
+  if (any_big) {
+    APS_TRY(floatset_alloc(c, ps.normset, F, D));
+    APS_TRY(floatset_reset_flags(c, ps.normset));
+    APS_CUDA(cudaMemcpyAsync(ps.normset.raw.p, ps.rawset.raw.p, (size_t)F * D * 4, cudaMemcpyDeviceToDevice, c->stream));
+    // normalised rows: scale-only scoring (bias would have to be scaled per query row)
+    APS_TRY(floatset_prepare(c, ps.normset, APS_NORM_PAIRWISE, tensor, 0));
+  }
+  return APS_OK;
+}
+
+// one pair on the device: results into caller regions; count stays on the device
+static int pair_device(aps_ctx* c, PairwiseSets& ps, int i, int j, const int64_t* counts, int D, int dtype,
+                       double match_threshold, double max_ratio, int unique, bool tensor, uint32_t* matches,
+                       double* metric, int32_t* count_dev) {
+  const int64_t N1 = counts[i], N2 = counts[j];
+  if (N1 == 0 || N2 == 0) {  // matchFeaturesScratch.m:84-88 (binary); float: documented deviation
+    APS_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int32_t), c->stream));
+    return APS_OK;
+  }
+  DevBuf<uint32_t> idx2;
+  DevBuf<float> d1, d2;
+  DevBuf<unsigned long long> best, keys;
+  APS_TRY(idx2.alloc((size_t)N1, c->stream));
+  APS_TRY(d1.alloc((size_t)N1, c->stream));
+  APS_TRY(d2.alloc((size_t)N1, c->stream));
+  APS_TRY(best.alloc((size_t)N2, c->stream));
+  APS_TRY(keys.alloc((size_t)N1 * 2, c->stream));
+  if (dtype == APS_U8) {
+    APS_TRY(hamming2_device(c, ps.u8pad.p, ps.off[i], N1, ps.u8pad.p, ps.off[j], N2, D, ps.nb16, idx2.p, d1.p, d2.p));
+    APS_TRY(aps_k_pair_filter_unique(c->stream, idx2.p, d1.p, d2.p, N1, N2, 1, D * 8, match_threshold, max_ratio,
+                                     unique, best.p, keys.p, count_dev, matches, metric));
+  } else {
+    const bool norm = ps.big[i] || ps.big[j];
+    FloatSet& S = norm ? ps.normset : ps.rawset;
+    FloatSide side = S.side();
+    APS_TRY(ssd2_device(c, side, ps.off[i], N1, side, ps.off[j], N2, D, S.flags.p, tensor, norm ? 0 : 1, idx2.p,
+                        d1.p, d2.p));
+    APS_TRY(aps_k_pair_filter_unique(c->stream, idx2.p, d1.p, d2.p, N1, N2, 0, 0, match_threshold, max_ratio,
+                                     unique, best.p, keys.p, count_dev, matches, metric));
+  }
+  return APS_OK;
+}
+
+extern "C" int aps_match_features(aps_ctx* c, const void* F1, int64_t N1, const void* F2, int64_t N2, int D,
+                                  int dtype, int layout, double match_threshold, double max_ratio, int unique,
+                                  uint32_t* matches, double* metric, int64_t* K) {
+  APS_CTX(c);
+  if (!K) APS_FAIL(APS_ERR_ARGS, "", "K is NULL");
+  *K = 0;
+  if (dtype != APS_F32 && dtype != APS_U8) APS_FAIL(APS_ERR_TYPE, "", "descriptors must be single or uint8");
+  if (N1 == 0 || N2 == 0) return APS_OK;
+  if (!F1 || !F2 || !matches || !metric) APS_FAIL(APS_ERR_ARGS, "", "null pointer argument");
+  if (D <= 0) APS_FAIL(APS_ERR_DIM, "", "descriptor dimension must be positive");
+  c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
+  const void* desc[2] = {F1, F2};
+  const int64_t counts[2] = {N1, N2};
+  const bool tensor = dtype == APS_F32 && tc_wanted(c, D, N1, N2);
+  PairwiseSets ps;
+  APS_TRY(pairwise_prepare(c, ps, desc, counts, 2, D, dtype, layout, tensor));
+  DevBuf<uint32_t> dm;
+  DevBuf<double> dmet;
+  DevBuf<int32_t> cnt;
+  APS_TRY(dm.alloc((size_t)N1 * 2, c->stream));
+  APS_TRY(dmet.alloc((size_t)N1, c->stream));
+  APS_TRY(cnt.alloc(1, c->stream));
+  APS_TRY(pair_device(c, ps, 0, 1, counts, D, dtype, match_threshold, max_ratio, unique, tensor, dm.p, dmet.p, cnt.p));
+  int32_t hk = 0;
+  APS_CUDA(cudaMemcpyAsync(&hk, cnt.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  if (hk > 0) {
+    APS_CUDA(cudaMemcpyAsync(matches, dm.p, (size_t)hk * 8, cudaMemcpyDeviceToHost, c->stream));
+    APS_CUDA(cudaMemcpyAsync(metric, dmet.p, (size_t)hk * 8, cudaMemcpyDeviceToHost, c->stream));
+    APS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  *K = hk;
+  c->stats[1] = c->h_flags[32];
+  return APS_OK;
+}
+
+__global__ void k_gather_pairs(const uint32_t* __restrict__ src_m, const double* __restrict__ src_d,
+                               const int64_t* __restrict__ region_off, const int64_t* __restrict__ out_off,
+                               uint32_t* __restrict__ rows, double* __restrict__ metric) {
+  const int p = blockIdx.x;
+  const int64_t a = out_off[p], b = out_off[p + 1], r0 = region_off[p];
+  for (int64_t t = threadIdx.x; t < b - a; t += blockDim.x) {
+    rows[2 * (a + t)] = src_m[2 * (r0 + t)];
+    rows[2 * (a + t) + 1] = src_m[2 * (r0 + t) + 1];
+    metric[a + t] = src_d[r0 + t];
+  }
+}
+
+extern "C" int aps_feature_matching_pairwise(aps_ctx* c, const void* const* desc, const int64_t* counts, int n,
+                                             int D, int dtype, int layout, double match_threshold, double max_ratio,
+                                             aps_matchlist** out) {
+  APS_CTX(c);
+  if (!out) APS_FAIL(APS_ERR_ARGS, "", "out is NULL");
+  *out = nullptr;
+  if (n < 0 || (n > 0 && !counts)) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  if (dtype != APS_F32 && dtype != APS_U8) APS_FAIL(APS_ERR_TYPE, "", "descriptors must be single or uint8");
+  c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
+  aps_matchlist* m = new (std::nothrow) aps_matchlist();
+  if (!m) APS_FAIL(APS_ERR_ALLOC, "", "out of host memory");
+  m->n = n;
+  m->has_metric = true;
+  const size_t cells = (size_t)n * n;
+  m->pair_ptr.assign(cells + 1, 0);
+  int64_t F = 0, maxc = 0;
+  for (int i = 0; i < n; ++i) {
+    F += counts[i];
+    if (counts[i] > maxc) maxc = counts[i];
+  }
+  if (F == 0 || n < 2) {
+    *out = m;
+    return APS_OK;
+  }
+  int rc = APS_OK;
+  {
+    const bool tensor = dtype == APS_F32 && tc_wanted(c, D, maxc, maxc);
+    PairwiseSets ps;
+    // pair list in column-major cell order (featureMatchingPairwise.m:48): j outer, i < j inner
+    std::vector<int> pi, pj;
+    std::vector<int64_t> region(1, 0);
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < j; ++i) {
+        pi.push_back(i);
+        pj.push_back(j);
+        region.push_back(region.back() + counts[i]);
+      }
+    const size_t NP = pi.size();
+    DevBuf<uint32_t> dm, rows;
+    DevBuf<double> dmet, met;
+    DevBuf<int32_t> cnt;
+    DevBuf<int64_t> d_region, d_outoff;
+    auto A = [&](int r) { if (rc == APS_OK) rc = r; };
+    A(pairwise_prepare(c, ps, desc, counts, n, D, dtype, layout, tensor));
+    A(dm.alloc((size_t)region.back() * 2, c->stream));
+    A(dmet.alloc((size_t)region.back(), c->stream));
+    A(cnt.alloc(NP, c->stream));
+    for (size_t p = 0; p < NP && rc == APS_OK; ++p)
+      rc = pair_device(c, ps, pi[p], pj[p], counts, D, dtype, match_threshold, max_ratio, 1, tensor,
+                       dm.p + 2 * region[p], dmet.p + region[p], cnt.p + p);
+    std::vector<int32_t> hc(NP, 0);
+    if (rc == APS_OK && cudaMemcpyAsync(hc.data(), cnt.p, NP * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = APS_ERR_CUDA;
+    if (rc == APS_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = APS_ERR_CUDA;
+    if (rc == APS_OK) {
+      std::vector<int64_t> outoff(NP + 1, 0);
+      for (size_t p = 0; p < NP; ++p) outoff[p + 1] = outoff[p] + hc[p];
+      m->total = outoff[NP];
+      // CSR over all n*n cells
+      size_t p = 0;
+      for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+          size_t cell = (size_t)i + (size_t)j * n;
+          int64_t add = 0;
+          if (i < j) add = hc[p++];
+          m->pair_ptr[cell + 1] = m->pair_ptr[cell] + add;
+        }
+      m->rows.resize((size_t)m->total * 2);
+      m->metric.resize((size_t)m->total);
+      if (m->total > 0) {
+        A(rows.alloc((size_t)m->total * 2, c->stream));
+        A(met.alloc((size_t)m->total, c->stream));
+        A(d_region.alloc(NP + 1, c->stream));
+        A(d_outoff.alloc(NP + 1, c->stream));
+        if (rc == APS_OK) {
+          cudaMemcpyAsync(d_region.p, region.data(), (NP + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+          cudaMemcpyAsync(d_outoff.p, outoff.data(), (NP + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+          k_gather_pairs<<<(unsigned)NP, 128, 0, c->stream>>>(dm.p, dmet.p, d_region.p, d_outoff.p, rows.p, met.p);
+          cudaMemcpyAsync(m->rows.data(), rows.p, (size_t)m->total * 8, cudaMemcpyDeviceToHost, c->stream);
+          cudaMemcpyAsync(m->metric.data(), met.p, (size_t)m->total * 8, cudaMemcpyDeviceToHost, c->stream);
+          if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            aps_set_error(APS_ERR_CUDA, "", "pairwise gather failed");
+            rc = APS_ERR_CUDA;
+          }
+        }
+      }
+    }
+    c->stats[1] = c->h_flags[32];
+  }
+  if (rc != APS_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return APS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// imageMatching.m:75-100
+extern "C" int aps_select_partners(aps_ctx* c, const int64_t* counts, int n, int m, uint8_t* cand,
+                                   int64_t* pairs_lin, int64_t* npairs) {
+  APS_CTX(c);
+  if (n < 0 || (n > 0 && (!counts || !cand))) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  if (npairs) *npairs = 0;
+  if (n == 0) return APS_OK;
+  const size_t cells = (size_t)n * n;
+  DevBuf<int64_t> dc;
+  DevBuf<uint8_t> dcand;
+  APS_TRY(dc.alloc(cells, c->stream));
+  APS_TRY(dcand.alloc(cells, c->stream));
+  APS_CUDA(cudaMemcpyAsync(dc.p, counts, cells * 8, cudaMemcpyHostToDevice, c->stream));
+  APS_TRY(aps_k_select_partners(c->stream, dc.p, n, m, dcand.p));
+  APS_CUDA(cudaMemcpyAsync(cand, dcand.p, cells, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  int64_t np = 0;
+  for (size_t i = 0; i < cells; ++i)  // find(): ascending linear index (imageMatching.m:99)
+    if (cand[i]) {
+      if (pairs_lin) pairs_lin[np] = (int64_t)i;
+      ++np;
+    }
+  if (npairs) *npairs = np;
+  return APS_OK;
+}

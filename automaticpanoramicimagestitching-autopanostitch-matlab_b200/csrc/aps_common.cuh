@@ -1,0 +1,159 @@
+// aps_common.cuh -- shared declarations of libapsmatch (B200 / sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/apsmatch.h"
+
+#define APS_EPS32 1.1920928955078125e-07f  // eps('single')
+
+void aps_set_error(int code, const char* id, const char* fmt, ...);
+
+#define APS_CUDA(call)                                                                                        \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess) {                                                                                 \
+      aps_set_error(APS_ERR_CUDA, "", "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,     \
+                    __LINE__);                                                                                \
+      return APS_ERR_CUDA;                                                                                    \
+    }                                                                                                         \
+  } while (0)
+
+#define APS_TRY(call)          \
+  do {                         \
+    int rc__ = (call);         \
+    if (rc__ != APS_OK) return rc__; \
+  } while (0)
+
+struct aps_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int float_engine = 0;  // 0 auto, 1 exact only, 2 tensor required
+  int64_t stats[4] = {0, 0, 0, 0};
+  int32_t* d_scratch_flags = nullptr;  // small persistent device scratch (64 ints)
+  int32_t* h_flags = nullptr;          // pinned mirror
+};
+
+// Stream-ordered device buffer (cudaMallocAsync pool: repeated calls re-use the same memory).
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(size_t count, cudaStream_t stream) {
+    release();
+    s = stream;
+    n = count;
+    if (count == 0) return APS_OK;
+    cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), stream);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      aps_set_error(APS_ERR_ALLOC, "", "cudaMallocAsync(%zu bytes) failed: %s", count * sizeof(T),
+                    cudaGetErrorString(e));
+      return APS_ERR_ALLOC;
+    }
+    return APS_OK;
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+static inline int64_t aps_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t aps_min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// ---- kernel launchers (one translation unit each) ------------------------------------------
+// K1  aps_prep.cu
+enum { APS_NORM_NONE = 0, APS_NORM_GLOBAL = 1, APS_NORM_PAIRWISE = 2 };
+// transposes one image's column-major [N x D] block into rows [row0,row0+N) of the row-major pool
+int aps_k_transpose_in(cudaStream_t s, const void* src_cm, int64_t N, int D, int elem_size, void* dst_rm);
+int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const float* dist_rm, int64_t N, int k,
+                               uint32_t* idx_cm, float* dist_cm);
+// pass 1: xn = normalised rows (norm_mode), sq[r] = sum(xn^2) (sequential f32), invn[r] = 1/norm (1 when
+// norm_mode NONE), flags[0] &= all raw values exactly representable in bf16, flags[1] = max bits |sq-1|,
+// flags[2] = max bits sq, flags[3] = max bits |raw| (for the max|.|>2 test of matchFeaturesScratch.m:105)
+int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int norm_mode, float* xn, float* sq,
+                       float* invn, int32_t* flags);
+// pass 2: bf16 operands [F x Dp] (Dp multiple of 64, zero padded) + per-column (scale,bias)
+//   exact_flag (device int): 1 -> operand = bf16(raw), scale = invn ; 0 -> operand = bf16(xn), scale = 1
+//   bias_mode: 0 -> bias 0 ; 1 -> bias = -sq/2 (SSD on un-normalised rows)
+int aps_k_prepare_operands(cudaStream_t s, const float* raw, const float* xn, const float* sq, const float* invn,
+                           int64_t F, int D, int Dp, const int32_t* exact_flag, int bias_mode, __nv_bfloat16* xb,
+                           float2* colsb);
+
+// K2f aps_knn_exact.cu : exact CUDA-core kNN.  rows==nullptr -> queries [q0,q0+nq) ; else rows[i].
+//   metric 0: FLANN-order squared L2 ; metric 1: SSD order (a2 + b2) - 2*G with sq arrays.
+//   train columns [t0,t1) ; output idx 1-based RELATIVE TO t0 (idx = j - t0 + 1), row-major [.. x k],
+//   written at out row = (rows ? rows[i] : q0 + i) - out_row0.
+int aps_k_knn_exact(cudaStream_t s, const float* Q, const float* sqQ, const int32_t* rows, const int32_t* nrows_dev,
+                    int64_t q0, int64_t nq, const float* T, const float* sqT, int64_t t0, int64_t t1, int D,
+                    int k, int metric, int64_t out_row0, uint32_t* idx, float* dist);
+
+// K4 aps_hamming.cu : exact Hamming kNN, thread per query, k <= APS_MAX_K.  idx relative to t0, 1-based.
+int aps_k_knn_hamming(cudaStream_t s, const uint8_t* Q, int64_t q0, int64_t nq, const uint8_t* T, int64_t t0,
+                      int64_t t1, int nb, int k, int64_t out_row0, uint32_t* idx, float* dist);
+
+// K2 aps_knn_tc.cu : tcgen05 candidate search.  See the file header.
+struct aps_tc_problem {
+  const __nv_bfloat16* Qb;  // [Fq_total x Dp] query operands
+  const __nv_bfloat16* Tb;  // [Ft_total x Dp] train operands
+  const float2* colsb;      // [Ft_total] (scale,bias) per train row
+  int64_t Fq_total, Ft_total;
+  int Dp;
+  int64_t q0, q1;  // query rows to search
+  int64_t t0, t1;  // train rows searched
+  int nseg;        // column segments per query row block
+  int kcand;       // candidates kept per (row, segment): 8
+  uint32_t* cand_idx;   // [ (q1-q0) x nseg x kcand ] global train row (0-based) or 0xFFFFFFFF
+  float* cand_score;    // same shape: score (dot*scale+bias), -inf for empty slots
+  float* dump;          // optional [ (q1-q0) x (t1-t0) ] raw scores (tests only), else nullptr
+};
+int aps_k_knn_tc_supported(int Dp);
+int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p);
+
+// K3 aps_rerank.cu : exact FP32 re-rank of the candidates + completeness proof.
+//   approx distance of a score: alpha[row] + beta[row]*score ; row proven iff
+//   (worst retained approx distance over segments) - eps_bound > exact k-th distance.
+//   Unproven rows are appended to fb_rows/fb_count for the exact kernel.
+int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* invnQ, const float* T,
+                 const float* sqT, int D, int metric, int64_t q0, int64_t nq, int64_t t0, int nseg, int kcand,
+                 const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
+                 const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
+                 int32_t* fb_count);
+
+// K5 aps_filter.cu
+int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, int k, int64_t q0, int64_t q1,
+                        const int32_t* img_of_row, const int64_t* img_off, float ratio_thr, int32_t* target,
+                        uint32_t* partner);
+// compaction of per-query records into the CSR cell order (featureMatchingGlobal.m:149-159)
+int aps_k_fill_img_of_row(cudaStream_t s, const int64_t* img_off, int n, int64_t maxcount, int32_t* img_of_row);
+int aps_k_global_compact(cudaStream_t s, const int32_t* target, const uint32_t* partner, const int32_t* img_of_row,
+                         const int64_t* img_off, int n, int64_t F, int64_t* dir_counts /*n*n*/,
+                         int64_t* pair_counts /*n*n*/, int64_t* pair_ptr /*n*n+1*/, int64_t* rank /*F*/,
+                         uint32_t* rows /*2F*/);
+int aps_k_hamming2_finalize(cudaStream_t s, int64_t N1, int64_t N2, int nb, const uint32_t* idx_k2,
+                            const float* dist_k2, uint32_t* idx2, float* d1, float* d2);
+int aps_k_split_k2(cudaStream_t s, int64_t N1, const uint32_t* idx_k2, const float* dist_k2, uint32_t* idx2,
+                   float* d1, float* d2);
+// pairwise: ratio/threshold filter + unique + sort for one (query image, train image) pair
+int aps_k_pair_filter_unique(cudaStream_t s, const uint32_t* idx2, const float* d1, const float* d2, int64_t N1,
+                             int64_t N2, int is_binary, int nbits, double match_threshold, double max_ratio,
+                             int unique, unsigned long long* best_by_train /*N2*/, unsigned long long* keys /*2*N1*/,
+                             int32_t* count_dev, uint32_t* matches /*2*N1*/, double* metric /*N1*/);
+
+// K6 aps_select.cu
+int aps_k_select_partners(cudaStream_t s, const int64_t* counts_cm, int n, int m, uint8_t* cand_cm);

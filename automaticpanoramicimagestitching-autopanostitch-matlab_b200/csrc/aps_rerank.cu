@@ -1,0 +1,173 @@
+// aps_rerank.cu -- K3: exact FP32 re-rank of the tensor-core candidates + completeness proof.
+//
+// The tcgen05 pass (aps_knn_tc.cu) ranks train rows by an APPROXIMATE score (bf16 operands).  The
+// reference contract (PP/mex/flann_knn.cpp:229-252, matchFeaturesScratch.m:351-362) is the exact
+// ordering, so every candidate's distance is recomputed here with the oracle's own operation order
+// and the row's top-k is PROVEN complete:
+//
+//   approx distance  s~(score) = alpha_row + beta_row * score        (monotone decreasing in score)
+//   |s~ - s_exact| <= eps  for every train row (bound derived in DESIGN.md "Exactness")
+//   every row that is not a candidate has s~ >= W := min over segments of the worst retained s~
+//   => if  W - eps > (k-th smallest exact candidate distance)  no outsider can enter or tie the top-k.
+//
+// Rows failing the test are appended to a list and re-searched by the exact CUDA-core kernel.
+// One warp per query row, one lane per candidate (nseg*kcand <= 32).
+#include <math_constants.h>
+
+#include "aps_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float l2sq_flann(const float* __restrict__ a, const float* __restrict__ b, int D) {
+  float result = 0.f;
+  int d = 0;
+  for (; d + 3 < D; d += 4) {
+    float4 x, y;
+    if ((D & 3) == 0) {
+      x = *reinterpret_cast<const float4*>(a + d);
+      y = *reinterpret_cast<const float4*>(b + d);
+    } else {
+      x = make_float4(a[d], a[d + 1], a[d + 2], a[d + 3]);
+      y = make_float4(b[d], b[d + 1], b[d + 2], b[d + 3]);
+    }
+    float e0 = __fsub_rn(x.x, y.x), e1 = __fsub_rn(x.y, y.y), e2 = __fsub_rn(x.z, y.z), e3 = __fsub_rn(x.w, y.w);
+    float s = __fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1));
+    s = __fadd_rn(s, __fmul_rn(e2, e2));
+    s = __fadd_rn(s, __fmul_rn(e3, e3));
+    result = __fadd_rn(result, s);
+  }
+  for (; d < D; ++d) {
+    float e0 = __fsub_rn(a[d], b[d]);
+    result = __fadd_rn(result, __fmul_rn(e0, e0));
+  }
+  return result;
+}
+
+__device__ __forceinline__ float ssd_seq(const float* __restrict__ a, const float* __restrict__ b, int D, float a2,
+                                         float b2) {
+  float g = 0.f;
+  for (int d = 0; d < D; ++d) g = __fadd_rn(g, __fmul_rn(a[d], b[d]));
+  return __fsub_rn(__fadd_rn(a2, b2), __fmul_rn(2.0f, g));
+}
+
+// error bound of the approximate distance; flags: [0] operands exact in bf16, [1] bits of max|sq-1|,
+// [2] bits of max sq.  See DESIGN.md "Exactness of the tensor-core search".
+__device__ __forceinline__ float eps_bound(const int32_t* __restrict__ flags, int bias_mode) {
+  const bool exact = flags[0] != 0;
+  const float dev = __int_as_float(flags[1]);
+  const float maxsq = fmaxf(__int_as_float(flags[2]), 1.0f);
+  const float slop = 1.0e-4f * maxsq;                     // fp32 evaluation-order differences
+  const float bf = exact ? 0.0f : 7.9e-3f * maxsq;        // 2 * 2^-8 * (1+2^-9)^2 * |a||b|
+  return bias_mode ? (slop + bf) : (slop + bf + dev);     // normalised rows: |sq_b - 1| <= dev is ignored by the score
+}
+
+__global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, const float* __restrict__ sqQ,
+                                                const float* __restrict__ invnQ, const float* __restrict__ T,
+                                                const float* __restrict__ sqT, int D, int metric, int64_t q0,
+                                                int64_t nq, int64_t t0, int nseg, int kcand,
+                                                const uint32_t* __restrict__ cand_idx,
+                                                const float* __restrict__ cand_score,
+                                                const int32_t* __restrict__ flags, int bias_mode, int k,
+                                                int64_t out_row0, uint32_t* __restrict__ idx,
+                                                float* __restrict__ dist, int32_t* __restrict__ fb_rows,
+                                                int32_t* __restrict__ fb_count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= nq) return;
+  const int64_t q = q0 + r;
+  const int ncand = nseg * kcand;
+  const float eps = eps_bound(flags, bias_mode);
+  const bool exact = flags[0] != 0;
+  const float a2 = sqQ[q];
+  // s~ = alpha + beta*score
+  const float alpha = bias_mode ? a2 : __fadd_rn(a2, 1.0f);
+  const float beta = bias_mode ? -2.0f : (exact ? -2.0f * invnQ[q] : -2.0f);
+
+  uint32_t ci = 0xffffffffu;
+  float sc = -CUDART_INF_F;
+  if (lane < ncand) {
+    ci = cand_idx[r * ncand + lane];
+    sc = cand_score[r * ncand + lane];
+  }
+  const bool valid = ci != 0xffffffffu;
+  const float sapx = valid ? fmaf(beta, sc, alpha) : CUDART_INF_F;  // monotone in sc; its own rounding is inside eps
+
+  // W = min over segments of the worst (largest) retained approx distance
+  float W = CUDART_INF_F;
+  for (int s = 0; s < nseg; ++s) {
+    float m = (lane >= s * kcand && lane < (s + 1) * kcand) ? sapx : -CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    W = fminf(W, m);
+  }
+  // prune: lanes whose lower bound exceeds the k-th smallest upper bound cannot be in the top-k
+  const float ub = sapx + eps, lb = sapx - eps;
+  int below = 0;
+  for (int l = 0; l < 32; ++l) {
+    float o = __shfl_sync(0xffffffffu, ub, l);
+    below += (o < lb);
+  }
+  const bool need = valid && below < k;
+  float d = CUDART_INF_F;
+  if (need) {
+    const float* a = Q + q * D;
+    const float* b = T + (int64_t)ci * D;
+    d = (metric == 0) ? l2sq_flann(a, b, D) : ssd_seq(a, b, D, a2, sqT[ci]);
+  }
+  const bool nan_seen = __any_sync(0xffffffffu, need && !(d == d));
+  // rank by (distance, index)
+  int rank = 0;
+  for (int l = 0; l < 32; ++l) {
+    float od = __shfl_sync(0xffffffffu, d, l);
+    uint32_t oi = __shfl_sync(0xffffffffu, ci, l);
+    bool oneed = __shfl_sync(0xffffffffu, (int)need, l);
+    rank += oneed && (od < d || (od == d && oi < ci));
+  }
+  const int nvalid = __popc(__ballot_sync(0xffffffffu, need));
+  if (need && rank < k) {
+    idx[(q - out_row0) * k + rank] = (uint32_t)((int64_t)ci - t0 + 1);
+    dist[(q - out_row0) * k + rank] = d;
+  }
+  if (lane >= nvalid && lane < k) {  // fewer than k neighbours exist: flann_knn.cpp:216-219
+    idx[(q - out_row0) * k + lane] = 0u;
+    dist[(q - out_row0) * k + lane] = CUDART_INF_F;
+  }
+  // completeness proof
+  float dk = -CUDART_INF_F;  // k-th smallest exact distance (or -inf when fewer than k candidates)
+  {
+    float mine = (need && rank == k - 1) ? d : -CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+    dk = mine;
+  }
+  bool proven;
+  if (nvalid >= k)
+    proven = (W - eps > dk);
+  else
+    proven = (W == CUDART_INF_F);  // every train row was a candidate
+  if (nan_seen) proven = false;
+  if (!proven && lane == 0) {
+    int pos = atomicAdd(fb_count, 1);
+    fb_rows[pos] = (int32_t)q;
+  }
+}
+
+}  // namespace
+
+int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* invnQ, const float* T,
+                 const float* sqT, int D, int metric, int64_t q0, int64_t nq, int64_t t0, int nseg, int kcand,
+                 const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
+                 const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
+                 int32_t* fb_count) {
+  (void)exact_flag;
+  if (nq == 0) return APS_OK;
+  if (nseg * kcand > 32) {
+    aps_set_error(APS_ERR_ARGS, "", "rerank: nseg*kcand must be <= 32");
+    return APS_ERR_ARGS;
+  }
+  k_rerank<<<(unsigned)aps_ceil_div(nq, 8), 256, 0, s>>>(Q, sqQ, invnQ, T, sqT, D, metric, q0, nq, t0, nseg, kcand,
+                                                        cand_idx, cand_score, flags, bias_mode, k, out_row0, idx,
+                                                        dist, fb_rows, fb_count);
+  APS_CUDA(cudaGetLastError());
+  return APS_OK;
+}

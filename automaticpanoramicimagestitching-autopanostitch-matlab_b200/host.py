@@ -1,0 +1,413 @@
+"""Host-side mirror of the reference's MATLAB interface for the feature-matching path.
+
+Same function names, argument meaning and error behaviour as the reference (PP/ = "Procedural
+Program/"), so the parity tests read like the reference's call sites:
+
+  featureMatchingGlobal(input, allDescriptors, numImg)        PP/featureMatching/featureMatchingGlobal.m:1
+  featureMatchingPairwise(input, allDescriptors, numImg)      PP/featureMatching/featureMatchingPairwise.m:1
+  matchFeaturesScratch(F1, F2, Method=..., MatchThreshold=..) PP/featureMatching/matchFeaturesScratch.m:1
+  flann_knn_win(train[, query], k[, method, trees, checks])   PP/mex/flann_knn.cpp:118-253
+  nearest2HammingExhaustiveMEX(A, B) / ...OMPMEX(A, B)        PP/mex/nearest2HammingExhaustive{,OMP}MEX.cpp
+  nearest2SSDExhaustive(A, B)                                 PP/featureMatching/matchFeaturesScratch.m:322-366
+  selectImagePartners(matchesAll, m)                          PP/imageMatching/imageMatching.m:75-100
+
+MATLAB is not available in this image, so this mirror is Python; it only marshals arguments into
+the C ABI (include/apsmatch.h).  All arithmetic runs in libapsmatch.so on the GPU; nothing here
+computes a distance.  `input` may be a dict or any object with the reference's field names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import APS_COL_MAJOR, APS_F32, APS_ROW_MAJOR, APS_U8, ApsError, check, default_context, lib
+
+
+class binaryFeatures:
+    """Stand-in for MATLAB's binaryFeatures object: packed uint8 rows in `.Features`."""
+
+    def __init__(self, features):
+        f = np.asarray(features)
+        if f.dtype != np.uint8 or f.ndim != 2:
+            raise TypeError("binaryFeatures expects an [N x nbytes] uint8 matrix")
+        self.Features = f
+        self.NumFeatures = f.shape[0]
+
+
+def _field(inp, name, default=None, required=False):
+    if isinstance(inp, dict):
+        if name in inp:
+            return inp[name]
+    elif hasattr(inp, name):
+        return getattr(inp, name)
+    if required:
+        raise KeyError(f"input.{name} is required")
+    return default
+
+
+def _as_matrix(a, dtype):
+    """numpy array -> (buffer, layout).  Fortran-ordered arrays go through as MATLAB column-major."""
+    a = np.asarray(a)
+    if a.ndim != 2:
+        raise ApsError(2, "flann_knn:type", "descriptors must be 2D")
+    if a.dtype != dtype:
+        a = a.astype(dtype)
+    if a.flags.c_contiguous:
+        return a, APS_ROW_MAJOR
+    if a.flags.f_contiguous:
+        return a, APS_COL_MAJOR
+    return np.ascontiguousarray(a), APS_ROW_MAJOR
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a.size else C.c_void_p(0)
+
+
+def _cells_from_matchlist(h, n, want_metric=False):
+    L = lib()
+    total = L.aps_matchlist_total(h)
+    pp = np.ctypeslib.as_array(L.aps_matchlist_pair_ptr(h), shape=(n * n + 1,)).copy()
+    rows = (np.ctypeslib.as_array(L.aps_matchlist_rows(h), shape=(total, 2)).copy() if total
+            else np.zeros((0, 2), np.uint32))
+    mp = L.aps_matchlist_metric(h)
+    metric = np.ctypeslib.as_array(mp, shape=(total,)).copy() if (want_metric and total and mp) else None
+    matches = [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]  # cell(numImg): every entry []
+    metrics = [[None] * n for _ in range(n)]
+    for j in range(n):
+        for i in range(j):
+            c = i + j * n
+            a, b = int(pp[c]), int(pp[c + 1])
+            if b > a:
+                matches[i][j] = rows[a:b].astype(np.float64)  # double, [M x 2] (featureMatchingGlobal.m:155-159)
+                if metric is not None:
+                    metrics[i][j] = metric[a:b]
+    return matches, metrics, pp, rows
+
+
+def _describe(allDescriptors, numImg):
+    """Shared front end: detect binary vs float, per-image matrices, counts (featureMatchingGlobal.m:48-63)."""
+    n = int(numImg)
+    cells = list(allDescriptors) if allDescriptors is not None else []
+    if len(cells) < n:
+        cells = cells + [None] * (n - len(cells))
+
+    def is_empty(x):
+        if x is None:
+            return True
+        if isinstance(x, binaryFeatures):
+            return x.NumFeatures == 0
+        return np.asarray(x).size == 0
+
+    first = next((x for x in cells[:n] if not is_empty(x)), None)
+    if first is None:
+        return n, None, [], [], 0, False
+    is_binary = isinstance(first, binaryFeatures)
+    mats, counts = [], []
+    D = None
+    for x in cells[:n]:
+        if is_empty(x):
+            mats.append(None)
+            counts.append(0)
+            continue
+        m = x.Features if isinstance(x, binaryFeatures) else np.asarray(x)
+        if is_binary:
+            if m.dtype != np.uint8:
+                raise ApsError(2, "flann_knn:type", "binary descriptors must be uint8")
+        elif m.dtype not in (np.float32, np.float64) and not np.issubdtype(m.dtype, np.integer):
+            raise ApsError(2, "flann_knn:type", "Descriptors must be single (float) or uint8 (binary)")
+        m, _ = _as_matrix(m, np.uint8 if is_binary else np.float32)  # single(allDesc), :81
+        if D is None:
+            D = m.shape[1]
+        elif m.shape[1] != D:
+            raise ApsError(4, "flann_knn:dim", "all descriptor matrices must have the same number of columns")
+        mats.append(m)
+        counts.append(m.shape[0])
+    return n, first, mats, counts, D, is_binary
+
+
+def _desc_args(mats, counts):
+    n = len(counts)
+    layouts = {(_as_matrix(m, m.dtype)[1]) for m in mats if m is not None}
+    layout = APS_ROW_MAJOR
+    if layouts == {APS_COL_MAJOR}:
+        layout = APS_COL_MAJOR
+    elif len(layouts) > 1:
+        mats = [None if m is None else np.ascontiguousarray(m) for m in mats]
+    ptrs = (C.c_void_p * max(n, 1))()
+    for i, m in enumerate(mats):
+        ptrs[i] = m.ctypes.data if m is not None and m.size else None
+    cnt = (C.c_int64 * max(n, 1))(*counts) if n else (C.c_int64 * 1)()
+    return ptrs, cnt, layout, mats
+
+
+def featureMatchingGlobal(input, allDescriptors, numImg, ctx=None):
+    """matches = featureMatchingGlobal(input, allDescriptors, numImg)   (featureMatchingGlobal.m:1-163)
+
+    Returns an n x n nested list `matches[i][j]` (0-based): [M x 2] float64 index pairs (1-based
+    local feature indices, column 0 -> image i, column 1 -> image j) for i < j, empty elsewhere."""
+    ctx = ctx or default_context()
+    if not (np.isscalar(numImg) and np.isfinite(numImg) and numImg > 0):
+        raise ValueError("numImg must be a positive finite scalar")  # arguments block :35-39
+    k = int(_field(input, "k", required=True))
+    ratio = float(_field(input, "Ratiothreshold", required=True))
+    use_bf = bool(_field(input, "BFMatch", 0))
+    n, first, mats, counts, D, is_binary = _describe(allDescriptors, numImg)
+    if first is None:
+        return [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]  # :49-52
+    ptrs, cnt, layout, keep = _desc_args(mats, counts)
+    h = C.c_void_p()
+    check(lib().aps_feature_matching_global(ctx.handle, ptrs, cnt, n, int(D), APS_U8 if is_binary else APS_F32, layout,
+                                            k, ratio, int(use_bf), C.byref(h)))
+    try:
+        matches, _, _, _ = _cells_from_matchlist(h, n)
+    finally:
+        lib().aps_matchlist_free(h)
+    return matches
+
+
+def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metric=False):
+    """matches = featureMatchingPairwise(input, allDescriptors, numImg)  (featureMatchingPairwise.m:1-63)
+
+    Runs getMatches' matchFeaturesScratch branch (:108-117) with Method 'Exhaustive' and Unique=true
+    for every i<j.  The MathWorks matchFeatures branch (input.useMATLABFeatureMatch=1) is closed
+    source and the approximate modes are out of scope: both raise."""
+    ctx = ctx or default_context()
+    if not (np.isscalar(numImg) and np.isfinite(numImg) and numImg > 0):
+        raise ValueError("numImg must be a positive finite scalar")
+    method = str(_field(input, "Matchingmethod", "Exhaustive")).lower()
+    if method != "exhaustive":
+        raise NotImplementedError("Matchingmethod='Approximate' is outside the exhaustive hot path")
+    thr = float(_field(input, "Matchingthreshold", required=True))
+    ratio = float(_field(input, "Ratiothreshold", required=True))
+    n, first, mats, counts, D, is_binary = _describe(allDescriptors, numImg)
+    if first is None:
+        m = [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]
+        return (m, [[None] * n for _ in range(n)]) if return_metric else m
+    ptrs, cnt, layout, keep = _desc_args(mats, counts)
+    h = C.c_void_p()
+    check(lib().aps_feature_matching_pairwise(ctx.handle, ptrs, cnt, n, int(D), APS_U8 if is_binary else APS_F32,
+                                              layout, thr, ratio, C.byref(h)))
+    try:
+        matches, metrics, _, _ = _cells_from_matchlist(h, n, want_metric=True)
+    finally:
+        lib().aps_matchlist_free(h)
+    # featureMatchingPairwise fills EVERY upper-triangle cell (possibly 0 x 2), :62
+    for j in range(n):
+        for i in range(j):
+            if matches[i][j].size == 0:
+                matches[i][j] = np.zeros((0, 2))
+    return (matches, metrics) if return_metric else matches
+
+
+def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRatio=0.6, Unique=True, ctx=None, **nv):
+    """[matches, matchMetric] = matchFeaturesScratch(F1, F2, 'Method','Exhaustive', ...)  (:1-215)
+
+    matches: [K x 2] uint32 (1-based rows of F1 / F2); matchMetric: [K x 1] (SSD, or percent Hamming)."""
+    ctx = ctx or default_context()
+    if str(Method).lower() != "exhaustive":
+        raise NotImplementedError("Method='Approximate' is outside the exhaustive hot path")
+    if not (MaxRatio > 0 and MaxRatio <= 1) or MatchThreshold < 0:
+        raise ValueError("invalid MaxRatio / MatchThreshold")  # inputParser validators :60-62
+    # normalizeInputs :237-292
+    if isinstance(F1, binaryFeatures) and isinstance(F2, binaryFeatures):
+        A, B, is_binary = F1.Features, F2.Features, True
+    else:
+        a, b = np.asarray(F1), np.asarray(F2)
+
+        def isbin(x):
+            return x.dtype == np.bool_ or (x.dtype == np.uint8 and bool(np.all((x == 0) | (x == 1))))
+
+        if isbin(a) and isbin(b):
+            if a.size == 0 or b.size == 0:
+                return np.zeros((0, 2), np.uint32), np.zeros((0,), np.float32)
+            A = np.packbits(a.astype(np.uint8), axis=1)  # packBits :617-646 (MSB first)
+            B = np.packbits(b.astype(np.uint8), axis=1)
+            is_binary = True
+            if a.shape[1] % 8:
+                raise NotImplementedError("unpacked bit widths that are not a multiple of 8")
+        else:
+            A, B, is_binary = a, b, False
+    A, la = _as_matrix(A, np.uint8 if is_binary else np.float32)
+    B, lb = _as_matrix(B, np.uint8 if is_binary else np.float32)
+    if la != lb:
+        A, B, la = np.ascontiguousarray(A), np.ascontiguousarray(B), APS_ROW_MAJOR
+    if A.shape[0] and B.shape[0] and A.shape[1] != B.shape[1]:
+        raise ValueError("Descriptor dimensions must match for non-binary.")  # :284-286
+    N1, N2 = A.shape[0], B.shape[0]
+    m = np.zeros((max(N1, 1), 2), np.uint32)
+    met = np.zeros(max(N1, 1), np.float64)
+    K = C.c_int64(0)
+    check(lib().aps_match_features(ctx.handle, _ptr(A), N1, _ptr(B), N2, int(A.shape[1]),
+                                   APS_U8 if is_binary else APS_F32, la, float(MatchThreshold), float(MaxRatio),
+                                   int(bool(Unique)), _ptr(m), _ptr(met), C.byref(K)))
+    return m[:K.value].copy(), met[:K.value].copy()
+
+
+def flann_knn_win(train, *args, ctx=None):
+    """[idx, dist] = flann_knn_win(train, k[,method,trees,checks]) or (train, query, k[,...])
+
+    PP/mex/flann_knn.cpp:118-253.  idx [Fq x k] uint32 1-based, dist [Fq x k] single; float
+    descriptors: squared L2 (exact search); uint8: Hamming.  Missing neighbours: 0 / +inf."""
+    ctx = ctx or default_context()
+    if len(args) < 1:
+        raise ApsError(1, "flann_knn:args", "Usage: [idx, dist] = flann_knn(train, k [, method, trees, checks])")
+    train = np.asarray(train)
+    if train.dtype not in (np.float32, np.uint8):
+        raise ApsError(2, "flann_knn:type", "Descriptors must be single (float) or uint8 (binary)")
+    args = list(args)
+    query = train
+    if len(args) >= 2 and isinstance(args[0], np.ndarray) and args[0].dtype == train.dtype and args[0].ndim == 2:
+        query = args.pop(0)
+    kk = args.pop(0)
+    if not np.isscalar(kk):
+        raise ApsError(2, "flann_knn:type", "k must be a scalar double")
+    k = int(kk)
+    method = str(args.pop(0)) if args else "flann"
+    trees = int(args.pop(0)) if args else 4
+    checks = int(args.pop(0)) if args else 32
+    dt = np.float32 if train.dtype == np.float32 else np.uint8
+    T, lt = _as_matrix(train, dt)
+    Q, lq = (T, lt) if query is train else _as_matrix(query, dt)
+    if lt != lq:
+        T, Q, lt = np.ascontiguousarray(T), np.ascontiguousarray(Q), APS_ROW_MAJOR
+    if T.shape[1] != Q.shape[1]:
+        raise ApsError(4, "flann_knn:dim", "query must have same descriptor dimension as train")
+    Fq = Q.shape[0]
+    order = "C" if lt == APS_ROW_MAJOR else "F"
+    idx = np.zeros((Fq, max(k, 1)), np.uint32, order=order)
+    dist = np.zeros((Fq, max(k, 1)), np.float32, order=order)
+    check(lib().aps_flann_knn(ctx.handle, _ptr(T), T.shape[0], _ptr(Q), Fq, int(T.shape[1]),
+                              APS_F32 if dt == np.float32 else APS_U8, lt, k, method.encode(), trees, checks,
+                              _ptr(idx), _ptr(dist)))
+    return idx, dist
+
+
+def nearest2HammingExhaustiveMEX(A, B, ctx=None):
+    """[idx2, d1, d2] = nearest2HammingExhaustiveMEX(Abytes, Bbytes)  (nearest2HammingExhaustiveMEX.cpp:16-80)"""
+    ctx = ctx or default_context()
+    A, B = np.asarray(A), np.asarray(B)
+    if A.dtype != np.uint8 or B.dtype != np.uint8:
+        raise ApsError(2, "hamm2nn:type", "Inputs must be uint8.")
+    if A.ndim != 2 or B.ndim != 2:
+        raise ApsError(4, "hamm2nn:dim", "2D only.")
+    if A.shape[1] != B.shape[1]:
+        raise ApsError(4, "hamm2nn:cols", "Byte width mismatch.")
+    A, la = _as_matrix(A, np.uint8)
+    B, lb = _as_matrix(B, np.uint8)
+    if la != lb:
+        A, B, la = np.ascontiguousarray(A), np.ascontiguousarray(B), APS_ROW_MAJOR
+    N1 = A.shape[0]
+    idx2 = np.zeros(N1, np.uint32)
+    d1 = np.zeros(N1, np.float32)
+    d2 = np.zeros(N1, np.float32)
+    check(lib().aps_nearest2_hamming(ctx.handle, _ptr(A), N1, _ptr(B), B.shape[0], int(A.shape[1]), la, _ptr(idx2),
+                                     _ptr(d1), _ptr(d2)))
+    return idx2, d1, d2
+
+
+nearest2HammingExhaustiveOMPMEX = nearest2HammingExhaustiveMEX  # same contract (…OMPMEX.cpp:18-83)
+
+
+def nearest2SSDExhaustive(A, B, ctx=None):
+    """[idx1, idx2, d1, d2] = nearest2SSDExhaustive(A, B)  (matchFeaturesScratch.m:322-366)"""
+    ctx = ctx or default_context()
+    A, la = _as_matrix(A, np.float32)
+    B, lb = _as_matrix(B, np.float32)
+    if la != lb:
+        A, B, la = np.ascontiguousarray(A), np.ascontiguousarray(B), APS_ROW_MAJOR
+    N1 = A.shape[0]
+    idx2 = np.zeros(N1, np.uint32)
+    d1 = np.zeros(N1, np.float32)
+    d2 = np.zeros(N1, np.float32)
+    check(lib().aps_nearest2_ssd(ctx.handle, _ptr(A), N1, _ptr(B), B.shape[0], int(A.shape[1]), la, _ptr(idx2),
+                                 _ptr(d1), _ptr(d2)))
+    return np.arange(1, N1 + 1, dtype=np.float64), idx2, d1, d2
+
+
+def selectImagePartners(matchesAll, m, ctx=None):
+    """Top-m candidate selection of imageMatching.m:75-100.
+
+    matchesAll: n x n nested list of [M x 2] arrays (or an [n x n] integer count matrix).
+    Returns (candidatePairs [n x n] bool, IuptriIdx: 1-based column-major linear indices)."""
+    ctx = ctx or default_context()
+    if isinstance(matchesAll, np.ndarray):
+        counts = matchesAll.astype(np.int64)
+    else:
+        n = len(matchesAll)
+        counts = np.array([[np.asarray(matchesAll[i][j]).shape[0] if np.asarray(matchesAll[i][j]).ndim == 2 else 0
+                            for j in range(n)] for i in range(n)], np.int64)
+    n = counts.shape[0]
+    if counts.shape != (n, n):
+        raise ValueError("matchesAll must be an n-by-n cell array.")  # imageMatching.m:58-60
+    cm = np.ascontiguousarray(counts.T)  # column-major buffer: cm.flat[i + j*n] = counts[i, j]
+    cand = np.zeros(n * n, np.uint8)
+    pairs = np.zeros(max(n * n, 1), np.int64)
+    npairs = C.c_int64(0)
+    check(lib().aps_select_partners(ctx.handle, _ptr(cm), n, int(m), _ptr(cand), _ptr(pairs), C.byref(npairs)))
+    return cand.reshape(n, n).T.astype(bool), pairs[:npairs.value] + 1
+
+
+class GlobalPlan:
+    """Staged global pipeline (aps_gplan_*): the building block bench.py and the multi-GPU host use."""
+
+    def __init__(self, ctx, counts, D, is_binary, k):
+        self.ctx, self.n, self.D, self.k = ctx, len(counts), int(D), int(k)
+        self.counts = np.asarray(counts, np.int64)
+        self.is_binary = bool(is_binary)
+        h = C.c_void_p()
+        cnt = (C.c_int64 * max(self.n, 1))(*[int(c) for c in counts])
+        check(lib().aps_gplan_create(ctx.handle, cnt, self.n, self.D, APS_U8 if is_binary else APS_F32, self.k,
+                                     C.byref(h)))
+        self._h = h
+        self.F = int(lib().aps_gplan_total(h))
+
+    def upload(self, mats):
+        ptrs, _, layout, keep = _desc_args(list(mats), [0 if m is None else m.shape[0] for m in mats])
+        check(lib().aps_gplan_upload(self._h, ptrs, layout))
+        self._keep = keep
+
+    def upload_pointers(self, ptr_list, layout=APS_ROW_MAJOR):
+        ptrs = (C.c_void_p * max(self.n, 1))(*ptr_list)
+        check(lib().aps_gplan_upload(self._h, ptrs, layout))
+
+    def desc_device(self):
+        return lib().aps_gplan_desc_device(self._h)
+
+    def records_device(self):
+        return lib().aps_gplan_records_device(self._h)
+
+    def knn_device(self):
+        return lib().aps_gplan_knn_idx_device(self._h), lib().aps_gplan_knn_dist_device(self._h)
+
+    def prepare(self):
+        check(lib().aps_gplan_prepare(self._h))
+
+    def knn(self, q0=0, q1=None):
+        check(lib().aps_gplan_knn(self._h, int(q0), int(self.F if q1 is None else q1)))
+
+    def filter(self, ratio, q0=0, q1=None):
+        check(lib().aps_gplan_filter(self._h, int(q0), int(self.F if q1 is None else q1), float(ratio)))
+
+    def compact(self):
+        check(lib().aps_gplan_compact(self._h))
+
+    def download(self):
+        h = C.c_void_p()
+        check(lib().aps_gplan_download(self._h, C.byref(h)))
+        try:
+            return _cells_from_matchlist(h, self.n)
+        finally:
+            lib().aps_matchlist_free(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().aps_gplan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

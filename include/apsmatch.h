@@ -1,0 +1,170 @@
+/*
+ * apsmatch.h -- C ABI of libapsmatch.so: the B200 (sm_100a) implementation of AutoPanoStitch's
+ * featureMatching/ hot path.  Plain pointers and sizes only; no CUDA, torch or MATLAB types.
+ *
+ * PP/ = "Procedural Program/" in preethamam/AutomaticPanoramicImageStitching-AutoPanoStitch-MATLAB.
+ * Every entry point names the reference interface it replaces.  The MEX gateways in mex/ and the
+ * Python host mirror in the package bind exactly these symbols.
+ *
+ * Conventions
+ *   - status: 0 = APS_OK, otherwise an APS_ERR_* code; aps_last_error() gives the message and
+ *     aps_error_id() the MATLAB error identifier the reference would have raised for it.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry returns
+ *     APS_ERR_NOGPU (the reference's silent canUseGPU() fallback, matchFeaturesScratch.m:575-585,
+ *     is deliberately not reproduced).
+ *   - `layout`: APS_COL_MAJOR is the mxGetData layout of a MATLAB [N x D] matrix (element (r,c) at
+ *     r + c*N); APS_ROW_MAJOR is a C / NumPy [N][D] array.  Outputs that are matrices use the same
+ *     layout as the inputs of the call.
+ *   - indices returned are 1-based, exactly as the reference returns them.
+ *   - host entry points (aps_*) take HOST pointers and are synchronous.  The staged plan API
+ *     (aps_gplan_*) exposes the same pipeline step by step on the context's stream, with DEVICE
+ *     buffers reachable for collectives (NCCL broadcast / all-gather between ranks).
+ */
+#ifndef APSMATCH_H
+#define APSMATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APS_ABI_VERSION 1
+
+enum aps_status {
+  APS_OK = 0,
+  APS_ERR_ARGS = 1,  /* flann_knn:args / hamm2nn:nrhs : bad argument count or null pointer       */
+  APS_ERR_TYPE = 2,  /* flann_knn:type / hamm2nn:type : unsupported descriptor class             */
+  APS_ERR_K = 3,     /* flann_knn:k                   : k <= 0 (or k > APS_MAX_K)                */
+  APS_ERR_DIM = 4,   /* flann_knn:dim / hamm2nn:cols  : descriptor width mismatch                */
+  APS_ERR_BF = 5,    /* flann_knn:bf                  : 'bf' requested for float descriptors     */
+  APS_ERR_NOGPU = 6, /* no CUDA device / driver: the product has no CPU path                     */
+  APS_ERR_CUDA = 7,  /* a CUDA call failed; message carries cudaGetErrorString                   */
+  APS_ERR_ALLOC = 8,
+  APS_ERR_METHOD = 9 /* unknown method string                                                    */
+};
+
+enum aps_layout { APS_COL_MAJOR = 0, APS_ROW_MAJOR = 1 };
+enum aps_dtype { APS_F32 = 0, APS_U8 = 1 };
+
+#define APS_MAX_K 8 /* neighbours per query supported by the kNN entry points (reference uses 4 and 2) */
+
+typedef struct aps_ctx aps_ctx;             /* one per (process, GPU): device buffers, stream          */
+typedef struct aps_matchlist aps_matchlist; /* CSR form of the reference's n x n `matches` cell        */
+typedef struct aps_gplan aps_gplan;         /* staged global-matching pipeline (multi-GPU building block) */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int aps_ctx_create(int device, aps_ctx** out);
+void aps_ctx_destroy(aps_ctx* ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int aps_ctx_set_stream(aps_ctx* ctx, void* cuda_stream);
+int aps_ctx_synchronize(aps_ctx* ctx);
+const char* aps_last_error(void); /* thread-local */
+const char* aps_error_id(void);   /* e.g. "flann_knn:type"; "" when no MATLAB id applies */
+int aps_abi_version(void);
+/* Force a search engine for float descriptors: 0 = auto (tcgen05 candidates + exact FP32 re-rank
+ * when the shape allows, else exact CUDA-core search), 1 = exact CUDA-core search only,
+ * 2 = tcgen05 path required (error if the shape is unsupported). */
+int aps_ctx_set_float_engine(aps_ctx* ctx, int engine);
+/* Counters of the last float search on this context: [0] rows searched, [1] rows whose
+ * candidate set could not be PROVEN complete and were re-searched exactly, [2] engine used
+ * (1 exact, 2 tcgen05), [3] 1 if operands were exactly representable in bf16. */
+int aps_ctx_last_stats(aps_ctx* ctx, int64_t stats[4]);
+/* Pinned host memory for callers that want asynchronous-speed copies (bench, MEX staging). */
+void* aps_host_alloc(size_t bytes);
+void aps_host_free(void* p);
+
+/* ---- flann_knn_win(train, query, k, method, trees, checks) ------------- PP/mex/flann_knn.cpp:118-253
+ * idx [Fq x k] uint32 1-based, dist [Fq x k] float, ascending; missing neighbours idx 0 / +inf
+ * (:216-219).  float: SQUARED L2 with FLANN's L2 functor order, EXACT search (the reference's
+ * KD-tree(4)/checks=32 is approximate: results here are the exhaustive answer of the same
+ * contract).  uint8: Hamming bit counts, exact for both 'bf' (:199-223) and 'flann' (:235-240,
+ * LSH in the reference).  method NULL = "flann".  trees/checks are accepted and ignored.
+ * Errors mirror :125-177,:201-202 (float + 'bf' -> APS_ERR_BF, k<=0 -> APS_ERR_K ...). */
+int aps_flann_knn(aps_ctx* ctx, const void* train, int64_t Ft, const void* query, int64_t Fq, int D, int dtype,
+                  int layout, int k, const char* method, int trees, int checks, uint32_t* idx, float* dist);
+
+/* ---- [idx2,d1,d2] = nearest2HammingExhaustiveMEX(A,B) / ...OMPMEX(A,B) ----------------------
+ * PP/mex/nearest2HammingExhaustiveMEX.cpp:16-80, PP/mex/nearest2HammingExhaustiveOMPMEX.cpp:18-83.
+ * best = first index attaining the minimum, d2 = second smallest value with multiplicity,
+ * N2==0 -> idx 0 / NaN / NaN, N2==1 -> d2 = 8*nb. */
+int aps_nearest2_hamming(aps_ctx* ctx, const uint8_t* A, int64_t N1, const uint8_t* B, int64_t N2, int nb,
+                         int layout, uint32_t* idx2, float* d1, float* d2);
+
+/* ---- [~,idx2,d1,d2] = nearest2SSDExhaustive(A,B) --- PP/featureMatching/matchFeaturesScratch.m:322-366
+ * D2 = a2 + b2' - 2*A*B' in float32 (fixed sequential summation order), first index on ties,
+ * d2 = min over j != idx2, no clamp at zero; N2==1 -> d2 = +inf; N2==0 -> idx 0, +inf, +inf. */
+int aps_nearest2_ssd(aps_ctx* ctx, const float* A, int64_t N1, const float* B, int64_t N2, int D, int layout,
+                     uint32_t* idx2, float* d1, float* d2);
+
+/* ---- [matches, metric] = matchFeaturesScratch(F1,F2,'Method','Exhaustive',...) ---------------
+ * PP/featureMatching/matchFeaturesScratch.m:1-215 (exhaustive branches :116-126, filters :169-215).
+ * dtype APS_U8 = packed binaryFeatures rows (nBits = 8*D); APS_F32 = float descriptors, L2-normalised
+ * iff max|.|>2 (:105-110).  matches: caller buffer of 2*N1 uint32, interleaved (query,train) rows;
+ * metric: N1 doubles.  *K receives the number of matches. */
+int aps_match_features(aps_ctx* ctx, const void* F1, int64_t N1, const void* F2, int64_t N2, int D, int dtype,
+                       int layout, double match_threshold, double max_ratio, int unique, uint32_t* matches,
+                       double* metric, int64_t* K);
+
+/* ---- matches = featureMatchingGlobal(input, allDescriptors, numImg) --------------------------
+ * PP/featureMatching/featureMatchingGlobal.m:1-163.  desc[i] -> image i's [counts[i] x D] matrix
+ * (may be NULL when counts[i]==0).  k = input.k, ratio = input.Ratiothreshold.  use_bf is accepted
+ * for interface parity (binary search is exact either way). */
+int aps_feature_matching_global(aps_ctx* ctx, const void* const* desc, const int64_t* counts, int n, int D,
+                                int dtype, int layout, int k, double ratio, int use_bf, aps_matchlist** out);
+
+/* ---- matches = featureMatchingPairwise(input, allDescriptors, numImg) ------------------------
+ * PP/featureMatching/featureMatchingPairwise.m:1-63 with getMatches :103-120 on the
+ * matchFeaturesScratch 'Exhaustive' branch (input.useMATLABFeatureMatch = 0), Unique = true. */
+int aps_feature_matching_pairwise(aps_ctx* ctx, const void* const* desc, const int64_t* counts, int n, int D,
+                                  int dtype, int layout, double match_threshold, double max_ratio,
+                                  aps_matchlist** out);
+
+/* ---- match list: the n x n cell in CSR form ---------------------------------------------------
+ * cell (i,j) (0-based, i<j) is linear index c = i + j*n (MATLAB's column-major cell index);
+ * its rows are rows[2*pair_ptr[c] .. 2*pair_ptr[c+1]) interleaved (col1,col2) = (index into image i,
+ * index into image j), 1-based -- the layout imageMatching.m:229-230 and
+ * bundleAdjustmentRKf.m:430-431 consume.  metric is NULL for global lists. */
+int aps_matchlist_n(const aps_matchlist* m);
+int64_t aps_matchlist_total(const aps_matchlist* m);
+const int64_t* aps_matchlist_pair_ptr(const aps_matchlist* m); /* n*n + 1 entries */
+const uint32_t* aps_matchlist_rows(const aps_matchlist* m);    /* 2 * total entries */
+const double* aps_matchlist_metric(const aps_matchlist* m);
+void aps_matchlist_free(aps_matchlist* m);
+
+/* ---- top-m image-partner selection ------------------------- PP/imageMatching/imageMatching.m:75-100
+ * counts: putativeCount [n x n] column-major (counts[i + j*n] = size(matchesAll{i,j},1)), m =
+ * input.mBrownLowe.  cand [n x n] column-major logical (strict upper triangle); pairs_lin (may be
+ * NULL) receives find(candidatePairs) as 0-based linear indices, *npairs their number. */
+int aps_select_partners(aps_ctx* ctx, const int64_t* counts, int n, int m, uint8_t* cand, int64_t* pairs_lin,
+                        int64_t* npairs);
+
+/* ---- staged global pipeline (building block of the multi-GPU host; bench.py times these) -----
+ * All work is enqueued on the context's stream.  Query rows [q0,q1) of the pooled matrix may be
+ * sharded across ranks: every rank holds all descriptors, so a query's neighbours are complete
+ * locally and no cross-GPU merge exists. */
+int aps_gplan_create(aps_ctx* ctx, const int64_t* counts, int n, int D, int dtype, int k, aps_gplan** out);
+void aps_gplan_destroy(aps_gplan* p);
+int64_t aps_gplan_total(const aps_gplan* p); /* F */
+/* Device pointer of the pooled ROW-major raw descriptor matrix [F x D] (float or uint8): fill it
+ * with aps_gplan_upload(), or write it directly (device copy / ncclBroadcast) before prepare(). */
+void* aps_gplan_desc_device(aps_gplan* p);
+int aps_gplan_upload(aps_gplan* p, const void* const* desc, int layout); /* H2D + pooling (A1 :70-77) */
+int aps_gplan_prepare(aps_gplan* p);                                     /* K1: A1 :80-97 */
+int aps_gplan_knn(aps_gplan* p, int64_t q0, int64_t q1);                 /* K2/K3/K4: A2 */
+int aps_gplan_filter(aps_gplan* p, int64_t q0, int64_t q1, double ratio); /* K5a: A3 :123-147 */
+/* Per-query records written by filter(): int32 target_img[F] (1-based, 0 = rejected) followed by
+ * uint32 partner[F]; contiguous, 8*F bytes.  Rows outside [q0,q1) are left untouched, so ranks
+ * can all-gather their slices in place. */
+void* aps_gplan_records_device(aps_gplan* p);
+void* aps_gplan_knn_idx_device(aps_gplan* p);  /* uint32 [F][k] row-major, 1-based */
+void* aps_gplan_knn_dist_device(aps_gplan* p); /* float  [F][k] row-major */
+int aps_gplan_compact(aps_gplan* p);                         /* K5b: A3 :149-159 on all F records */
+int aps_gplan_download(aps_gplan* p, aps_matchlist** out);   /* D2H of the CSR lists (synchronises) */
+int aps_gplan_pair_counts_device(aps_gplan* p, void** counts_i64); /* n*n int64, column-major, after compact() */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APSMATCH_H */

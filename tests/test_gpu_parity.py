@@ -1,0 +1,245 @@
+"""GPU parity tests: the CUDA path (through the C ABI / host mirror) against the oracle on the same
+seeded inputs and against the committed golden vectors.  Integer/index work is compared bit-exact;
+float distances are compared bit-exact too (the re-rank uses the oracle's operation order) with the
+north star's 1e-4 relative tolerance stated as the fallback bar."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4  # north-star tolerance for float distances (BASELINE.json); we assert bit equality first
+
+
+@pytest.fixture(scope="module")
+def ctx(aps):
+    return aps._lib.default_context()
+
+
+def _cells_equal(got, ref_cells, n):
+    rows = 0
+    for j in range(n):
+        for i in range(n):
+            g = got[i][j]
+            exp = ref_cells.get((i, j)) if i < j else None
+            if exp is None:
+                assert g.size == 0, (i, j, g.shape)
+            else:
+                assert g.shape == exp.shape, (i, j, g.shape, exp.shape)
+                assert (g == exp).all(), (i, j)
+                assert g.dtype == np.float64
+                rows += len(exp)
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------
+# flann_knn_win
+@pytest.mark.parametrize("name,k", [("sift_self", 4), ("kaze", 4), ("tail37", 3)])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_flann_knn_float_golden(aps, golden, name, k, order):
+    T = np.array(golden[f"flann_{name}_T"], order=order)
+    Q = np.array(golden[f"flann_{name}_Q"], order=order)
+    idx, dist = aps.flann_knn_win(T, Q, float(k), "flann", 4, 32)
+    assert idx.dtype == np.uint32 and dist.dtype == np.float32 and idx.shape == (Q.shape[0], k)
+    assert np.array_equal(idx, golden[f"flann_{name}_idx"])
+    assert np.array_equal(dist.view(np.uint32), golden[f"flann_{name}_dist"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["rand256", "ties", "self", "kgtF"])
+@pytest.mark.parametrize("method", ["bf", "flann"])
+def test_flann_knn_binary_golden(aps, golden, name, method):
+    idx, dist = aps.flann_knn_win(golden[f"bfknn_{name}_T"], golden[f"bfknn_{name}_Q"], 4, method)
+    assert np.array_equal(idx, golden[f"bfknn_{name}_idx"])
+    assert np.array_equal(dist, golden[f"bfknn_{name}_dist"])
+
+
+@pytest.mark.parametrize("engine", [1, 0])
+def test_flann_knn_float_vs_oracle_medium(aps, orc, ctx, engine):
+    desc, c = aps.synth.make_config(1, n=4, kp=1024)
+    X = orc.normalize_rows_global(np.concatenate(desc))
+    ctx.set_float_engine(engine)
+    try:
+        idx, dist = aps.flann_knn_win(X, X, 4)
+    finally:
+        ctx.set_float_engine(0)
+    oi, od = orc.knn_l2(X, X, 4)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+    assert np.allclose(dist, od, rtol=RTOL)
+
+
+def test_flann_knn_errors_mirror_reference_ids(aps):
+    X = np.zeros((4, 8), np.float32)
+    for bad, ident in (((X, 0), "flann_knn:k"), ((X, X, 2, "bf"), "flann_knn:bf"),
+                       ((X.astype(np.float64), 2), "flann_knn:type"), ((X, np.zeros((2, 5), np.float32), 2), "flann_knn:dim")):
+        with pytest.raises(aps.ApsError) as e:
+            aps.flann_knn_win(*bad)
+        assert e.value.identifier == ident
+
+
+# ------------------------------------------------------------------------------------------------
+# nearest2HammingExhaustive{,OMP}MEX
+@pytest.mark.parametrize("name", ["rand256", "ties", "n2is1", "n2is0", "dups512"])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_nearest2_hamming_golden(aps, golden, name, order):
+    A = np.array(golden[f"ham2nn_{name}_A"], order=order)
+    B = np.array(golden[f"ham2nn_{name}_B"], order=order)
+    for fn in (aps.nearest2HammingExhaustiveMEX, aps.nearest2HammingExhaustiveOMPMEX):
+        idx2, d1, d2 = fn(A, B)
+        assert np.array_equal(idx2, golden[f"ham2nn_{name}_idx2"])
+        assert np.array_equal(d1, golden[f"ham2nn_{name}_d1"], equal_nan=True)
+        assert np.array_equal(d2, golden[f"ham2nn_{name}_d2"], equal_nan=True)
+
+
+def test_nearest2_hamming_vs_oracle_large(aps, orc):
+    rng = np.random.default_rng(5)
+    A = rng.integers(0, 256, (3000, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    B[100:200] = A[:100]
+    got = aps.nearest2HammingExhaustiveMEX(A, B)
+    exp = orc.nearest2_hamming(A, B)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g, e)
+
+
+def test_nearest2_ssd_vs_oracle(aps, orc):
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((700, 64)).astype(np.float32)
+    B = rng.standard_normal((900, 64)).astype(np.float32)
+    B[5] = A[3]
+    B[6] = A[3]
+    _, idx2, d1, d2 = aps.nearest2SSDExhaustive(A, B)
+    oi, o1, o2 = orc.nearest2_ssd(A, B)
+    assert np.array_equal(idx2, oi)
+    assert np.array_equal(d1.view(np.uint32), o1.view(np.uint32))
+    assert np.array_equal(d2.view(np.uint32), o2.view(np.uint32))
+    _, idx2, d1, d2 = aps.nearest2SSDExhaustive(A, B[:1])
+    assert (idx2 == 1).all() and np.isinf(d2).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# featureMatchingGlobal
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_global_float_c1_small(aps, orc, order):
+    desc, c = aps.synth.make_config(1, n=6, kp=512)
+    ref = orc.feature_matching_global(desc, c["k"], c["ratio"])
+    got = aps.featureMatchingGlobal({"k": c["k"], "Ratiothreshold": c["ratio"]},
+                                    [np.array(d, order=order) for d in desc], len(desc))
+    assert _cells_equal(got, ref["cells"], len(desc)) > 500
+
+
+def test_global_float_c1_full_config(aps, orc, ctx):
+    """BASELINE.json configs[0]: 6 images x 2048 SIFT-128 (one empty), k=4, reference-default ratio 0.6."""
+    desc, c = aps.synth.make_config(1)
+    ref = orc.feature_matching_global(desc, c["k"], c["ratio"])
+    got = aps.featureMatchingGlobal({"k": c["k"], "Ratiothreshold": c["ratio"]}, desc, len(desc))
+    assert _cells_equal(got, ref["cells"], len(desc)) == len(ref["rows"])
+    assert ref["n_ambiguous"] == 0  # no ratio within one float of the threshold in this set
+    # partner selection on top of it, m = 4 (BASELINE) and m = 6 (reference default)
+    counts = np.array([[np.asarray(got[i][j]).shape[0] if got[i][j].ndim == 2 else 0 for j in range(6)] for i in range(6)])
+    for m in (4, 6):
+        cand, pairs = aps.selectImagePartners(got, m)
+        oc, op = orc.select_partners(counts, m)
+        assert (cand == oc).all() and np.array_equal(pairs, op + 1)
+
+
+def test_global_binary_vs_oracle(aps, orc):
+    desc, c = aps.synth.make_config(4, n=5, kp=1500)
+    ref = orc.feature_matching_global(desc, c["k"], c["ratio"])
+    got = aps.featureMatchingGlobal({"k": c["k"], "Ratiothreshold": c["ratio"], "BFMatch": 1},
+                                    [aps.binaryFeatures(d) for d in desc], len(desc))
+    assert _cells_equal(got, ref["cells"], len(desc)) > 1000
+
+
+def test_global_kaze_real_valued(aps, orc):
+    desc, c = aps.synth.make_config(5, n=4, kp=1000)
+    ref = orc.feature_matching_global(desc, 4, 0.8)
+    got = aps.featureMatchingGlobal({"k": 4, "Ratiothreshold": 0.8}, desc, len(desc))
+    assert _cells_equal(got, ref["cells"], len(desc)) > 300
+
+
+def test_global_edge_cases(aps, orc):
+    e = np.zeros((0, 128), np.float32)
+    got = aps.featureMatchingGlobal({"k": 4, "Ratiothreshold": 0.6}, [e, e, e], 3)
+    assert all(got[i][j].size == 0 for i in range(3) for j in range(3))
+    # k larger than the number of features; a single non-empty image
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((3, 16)).astype(np.float32)
+    got = aps.featureMatchingGlobal({"k": 8, "Ratiothreshold": 0.9}, [a, e[:, :16]], 2)
+    ref = orc.feature_matching_global([a, e[:, :16]], 8, 0.9)
+    _cells_equal(got, ref["cells"], 2)
+    b = rng.standard_normal((2, 16)).astype(np.float32)
+    got = aps.featureMatchingGlobal({"k": 8, "Ratiothreshold": 0.99}, [a, b], 2)
+    ref = orc.feature_matching_global([a, b], 8, 0.99)
+    _cells_equal(got, ref["cells"], 2)
+
+
+def test_global_staged_plan_matches_one_call(aps, orc, ctx):
+    desc, c = aps.synth.make_config(1, n=4, kp=640)
+    counts = [d.shape[0] for d in desc]
+    plan = aps.GlobalPlan(ctx, counts, 128, False, 4)
+    plan.upload(desc)
+    plan.prepare()
+    F = plan.F
+    plan.knn(0, F // 3)          # the multi-GPU sharding: disjoint query-row ranges
+    plan.knn(F // 3, F)
+    plan.filter(c["ratio"], 0, F // 2)
+    plan.filter(c["ratio"], F // 2, F)
+    plan.compact()
+    matches, _, pair_ptr, rows = plan.download()
+    plan.close()
+    ref = orc.feature_matching_global(desc, 4, c["ratio"])
+    assert np.array_equal(pair_ptr, ref["pair_ptr"]) and np.array_equal(rows, ref["rows"])
+
+
+# ------------------------------------------------------------------------------------------------
+# matchFeaturesScratch / featureMatchingPairwise
+def test_match_features_float_vs_oracle(aps, orc):
+    desc, _ = aps.synth.make_config(1, n=3, kp=900)
+    for unique in (True, False):
+        m, met = aps.matchFeaturesScratch(desc[0], desc[1], MatchThreshold=1.5, MaxRatio=0.6, Unique=unique)
+        om, omet = orc.match_features(desc[0], desc[1], 1.5, 0.6, unique)
+        assert np.array_equal(m, om) and np.array_equal(met, omet)
+        assert len(m) > 100
+
+
+def test_match_features_binary_vs_oracle(aps, orc):
+    desc, _ = aps.synth.make_config(4, n=3, kp=1200)
+    m, met = aps.matchFeaturesScratch(aps.binaryFeatures(desc[0]), aps.binaryFeatures(desc[1]), MatchThreshold=10.0,
+                                      MaxRatio=0.8)
+    om, omet = orc.match_features(desc[0], desc[1], 10.0, 0.8)
+    assert np.array_equal(m, om) and np.array_equal(met, omet) and len(m) > 100
+    bits = np.unpackbits(desc[0][:50], axis=1)
+    bits2 = np.unpackbits(desc[1][:60], axis=1)
+    m2, _ = aps.matchFeaturesScratch(bits, bits2, MatchThreshold=100.0, MaxRatio=1.0)
+    om2, _ = orc.match_features(desc[0][:50], desc[1][:60], 100.0, 1.0)
+    assert np.array_equal(m2, om2)
+
+
+@pytest.mark.parametrize("cid,thr,ratio", [(1, 1.5, 0.6), (5, 1.5, 0.6), (4, 10.0, 0.8)])
+def test_pairwise_vs_oracle(aps, orc, cid, thr, ratio):
+    desc, c = aps.synth.make_config(cid, n=5, kp=600)
+    ref = orc.feature_matching_pairwise(desc, thr, ratio)
+    cells = [aps.binaryFeatures(d) for d in desc] if c["kind"] == "orb" else desc
+    inp = {"Matchingmethod": "Exhaustive", "Matchingthreshold": thr, "Ratiothreshold": ratio,
+           "useMATLABFeatureMatch": 0}
+    got, metrics = aps.featureMatchingPairwise(inp, cells, len(desc), return_metric=True)
+    n = len(desc)
+    rows = 0
+    for j in range(n):
+        for i in range(j):
+            exp = ref["cells"].get((i, j))
+            if exp is None:
+                assert got[i][j].shape == (0, 2)
+            else:
+                assert np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
+                rows += len(exp)
+    assert rows > 200
+
+
+def test_select_partners_vs_oracle_random(aps, orc):
+    rng = np.random.default_rng(11)
+    for n, m in ((1, 4), (2, 1), (7, 3), (40, 6), (300, 4)):
+        C = np.triu(rng.integers(0, 6, (n, n)), 1).astype(np.int64)  # many ties
+        cand, pairs = aps.selectImagePartners(C, m)
+        oc, op = orc.select_partners(C, m)
+        assert (cand == oc).all() and np.array_equal(pairs, op + 1)
