@@ -295,7 +295,7 @@ static int floatset_prepare(aps_ctx* c, FloatSet& fs, int norm_mode, bool tensor
   if (tensor) {
     const int Dp = (fs.D + 63) / 64 * 64;
     APS_TRY(fs.xb.alloc((size_t)fs.N * Dp, c->stream));
-    APS_TRY(fs.colsb.alloc((size_t)fs.N, c->stream));
+    APS_TRY(fs.colsb.alloc((size_t)fs.N + 256, c->stream));  // +256: whole-tile bulk loads
     APS_TRY(aps_k_prepare_operands(c->stream, fs.raw.p, xn, fs.sq.p, fs.invn.p, fs.N, fs.D, Dp, fs.flags.p,
                                    bias_mode, fs.xb.p, fs.colsb.p));
   }
@@ -367,7 +367,7 @@ extern "C" int aps_flann_knn(aps_ctx* c, const void* train, int64_t Ft, const vo
       if (tc) {
         const int Dp = (D + 63) / 64 * 64;
         APS_TRY(Q.xb.alloc((size_t)Fq * Dp, c->stream));
-        APS_TRY(Q.colsb.alloc((size_t)Fq, c->stream));
+        APS_TRY(Q.colsb.alloc((size_t)Fq + 256, c->stream));
         // NOTE: operands of BOTH sides are built after both flag passes ran (same stream order)
         APS_TRY(aps_k_prepare_operands(c->stream, Q.raw.p, Q.raw.p, Q.sq.p, Q.invn.p, Fq, D, Dp, T.flags.p, 1,
                                        Q.xb.p, Q.colsb.p));
@@ -470,9 +470,9 @@ extern "C" int aps_nearest2_ssd(aps_ctx* c, const float* A, int64_t N1, const fl
   if (tc) {
     const int Dp = (D + 63) / 64 * 64;
     APS_TRY(QA.xb.alloc((size_t)N1 * Dp, c->stream));
-    APS_TRY(QA.colsb.alloc((size_t)N1, c->stream));
+    APS_TRY(QA.colsb.alloc((size_t)N1 + 256, c->stream));
     APS_TRY(TB.xb.alloc((size_t)N2 * Dp, c->stream));
-    APS_TRY(TB.colsb.alloc((size_t)N2, c->stream));
+    APS_TRY(TB.colsb.alloc((size_t)N2 + 256, c->stream));
     APS_TRY(aps_k_prepare_operands(c->stream, QA.raw.p, QA.raw.p, QA.sq.p, QA.invn.p, N1, D, Dp, TB.flags.p, 1,
                                    QA.xb.p, QA.colsb.p));
     APS_TRY(aps_k_prepare_operands(c->stream, TB.raw.p, TB.raw.p, TB.sq.p, TB.invn.p, N2, D, Dp, TB.flags.p, 1,
@@ -685,6 +685,20 @@ extern "C" int aps_gplan_filter(aps_gplan* p, int64_t q0, int64_t q1, double rat
                              (float)ratio, p->records.p, (uint32_t*)(p->records.p + p->F));
 }
 
+extern "C" int aps_gplan_download_knn(aps_gplan* p, int64_t q0, int64_t q1, uint32_t* idx, float* dist) {
+  if (!p || !idx || !dist) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  if (q0 < 0 || q1 > p->F || q0 > q1) APS_FAIL(APS_ERR_ARGS, "", "query range out of bounds");
+  const size_t n = (size_t)(q1 - q0) * p->k;
+  if (n) {
+    APS_CUDA(cudaMemcpyAsync(idx, p->knn_idx.p + (size_t)q0 * p->k, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    APS_CUDA(cudaMemcpyAsync(dist, p->knn_dist.p + (size_t)q0 * p->k, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  return APS_OK;
+}
+
 extern "C" int aps_gplan_compact(aps_gplan* p) {
   if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
   aps_ctx* c = p->c;
@@ -849,7 +863,7 @@ static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* des
   if (tensor) {
     const int Dp = (D + 63) / 64 * 64;
     APS_TRY(ps.rawset.xb.alloc((size_t)F * Dp, c->stream));
-    APS_TRY(ps.rawset.colsb.alloc((size_t)F, c->stream));
+    APS_TRY(ps.rawset.colsb.alloc((size_t)F + 256, c->stream));
     APS_TRY(aps_k_prepare_operands(c->stream, ps.rawset.raw.p, ps.rawset.raw.p, ps.rawset.sq.p, ps.rawset.invn.p, F,
                                    D, Dp, ps.rawset.flags.p, 1, ps.rawset.xb.p, ps.rawset.colsb.p));
   }
@@ -1064,5 +1078,48 @@ extern "C" int aps_select_partners(aps_ctx* c, const int64_t* counts, int n, int
       ++np;
     }
   if (npairs) *npairs = np;
+  return APS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics: run the tcgen05 candidate kernel alone and return what its epilogue saw
+extern "C" int aps_debug_tc_scores(aps_ctx* c, const float* Q, int64_t nq, const float* T, int64_t nt, int D,
+                                   int nseg, float* scores, uint32_t* cand_idx, float* cand_score) {
+  APS_CTX(c);
+  if (!Q || !T || nq <= 0 || nt <= 0 || D <= 0 || nseg < 1 || nseg > 4) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  const int Dp = (D + 63) / 64 * 64;
+  if (!aps_k_knn_tc_supported(Dp)) APS_FAIL(APS_ERR_DIM, "", "unsupported descriptor length %d", D);
+  FloatSet qs, ts;
+  DevBuf<uint8_t> tmp;
+  APS_TRY(floatset_alloc(c, qs, nq, D));
+  APS_TRY(floatset_alloc(c, ts, nt, D));
+  APS_TRY(floatset_reset_flags(c, ts));
+  APS_TRY(stage_matrix(c, Q, nq, D, 4, APS_ROW_MAJOR, qs.raw.p, tmp));
+  APS_TRY(stage_matrix(c, T, nt, D, 4, APS_ROW_MAJOR, ts.raw.p, tmp));
+  APS_TRY(aps_k_prepare_norm(c->stream, qs.raw.p, nq, D, APS_NORM_NONE, qs.raw.p, qs.sq.p, qs.invn.p, ts.flags.p));
+  APS_TRY(aps_k_prepare_norm(c->stream, ts.raw.p, nt, D, APS_NORM_NONE, ts.raw.p, ts.sq.p, ts.invn.p, ts.flags.p));
+  APS_TRY(qs.xb.alloc((size_t)nq * Dp, c->stream));
+  APS_TRY(qs.colsb.alloc((size_t)nq + 256, c->stream));
+  APS_TRY(ts.xb.alloc((size_t)nt * Dp, c->stream));
+  APS_TRY(ts.colsb.alloc((size_t)nt + 256, c->stream));
+  APS_TRY(aps_k_prepare_operands(c->stream, qs.raw.p, qs.raw.p, qs.sq.p, qs.invn.p, nq, D, Dp, ts.flags.p, 1, qs.xb.p, qs.colsb.p));
+  APS_TRY(aps_k_prepare_operands(c->stream, ts.raw.p, ts.raw.p, ts.sq.p, ts.invn.p, nt, D, Dp, ts.flags.p, 1, ts.xb.p, ts.colsb.p));
+  DevBuf<float> dump, cscore;
+  DevBuf<uint32_t> cidx;
+  if (scores) APS_TRY(dump.alloc((size_t)nq * nt, c->stream));
+  APS_TRY(cidx.alloc((size_t)nq * nseg * 8, c->stream));
+  APS_TRY(cscore.alloc((size_t)nq * nseg * 8, c->stream));
+  aps_tc_problem p;
+  p.Qb = qs.xb.p; p.Tb = ts.xb.p; p.colsb = ts.colsb.p;
+  p.Fq_total = nq; p.Ft_total = nt; p.Dp = Dp;
+  p.q0 = 0; p.q1 = nq; p.t0 = 0; p.t1 = nt;
+  p.nseg = nseg; p.kcand = 8;
+  p.cand_idx = cidx.p; p.cand_score = cscore.p;
+  p.dump = scores ? dump.p : nullptr;
+  APS_TRY(aps_k_knn_tc(c->stream, c->sm_count, p));
+  if (scores) APS_CUDA(cudaMemcpyAsync(scores, dump.p, (size_t)nq * nt * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (cand_idx) APS_CUDA(cudaMemcpyAsync(cand_idx, cidx.p, (size_t)nq * nseg * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (cand_score) APS_CUDA(cudaMemcpyAsync(cand_score, cscore.p, (size_t)nq * nseg * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+  APS_CUDA(cudaStreamSynchronize(c->stream));
   return APS_OK;
 }

@@ -1,8 +1,489 @@
-// placeholder replaced by the tcgen05 kernel
+// aps_knn_tc.cu -- K2: float nearest-neighbour CANDIDATE search on the 5th-gen tensor cores.
+//
+// Replaces the O(F^2 D) search behind  PP/mex/flann_knn.cpp:229-234 (global path) and the GEMM +
+// two min passes of  PP/featureMatching/matchFeaturesScratch.m:351-358 (pairwise path) with
+//     score(q, j) = (a_q . b_j) * scale_j + bias_j          (||a-b||^2 = ||a||^2 + ||b||^2 - 2 a.b)
+// evaluated as a dense bf16 contraction: tcgen05.mma (cta_group::1, M=128, N=256, K=16 per
+// instruction) with the accumulator in TMEM, operands staged in shared memory by TMA
+// (SWIZZLE_128B, K-major), and a fused top-K' selection in the epilogue: the distance matrix is
+// never written.  The K' = 8 best train rows per (query row, column segment) go to aps_rerank.cu,
+// which recomputes them exactly in FP32 and proves the top-k complete.
+//
+// CTA = 192 threads, persistent over work units (128-query-row block x column segment):
+//   warp 0   : TMA producer  (A tile once per unit, B tiles + per-column (scale,bias) per step)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
+//   warps 2-5: epilogue, thread == query row (tcgen05.ld 32x32b: lane i of the warp's TMEM
+//              quadrant), running top-K' in registers.  Fast path per 32-column chunk is a
+//              FMNMX3 tree on the raw accumulators against a conservative per-row threshold
+//              (theta - bias_max) / scale_max: no shared-memory traffic, no multiply; only chunks
+//              that may contain a candidate read (scale,bias) and do the exact compare/insert.
+// Pipelines (all mbarrier based): B smem ring (2 x 64 KB) TMA<->MMA, A double buffer, TMEM
+// accumulator double buffer (2 x 256 columns = all 512) MMA<->epilogue, (scale,bias) ring.
+//
+// Roofline: tensor pipe.  Algorithmic FLOPs = 2*D per (query, train) pair.  HBM traffic is
+// negligible (operands stream from L2: every concurrently running CTA walks the same B tiles).
+#include <cuda.h>
+#include <math_constants.h>
+
 #include "aps_common.cuh"
-int aps_k_knn_tc_supported(int Dp) { (void)Dp; return 0; }
+
+namespace {
+
+constexpr int TM = 128;        // query rows per CTA tile (UMMA M)
+constexpr int TN = 256;        // train rows per step (UMMA N)
+constexpr int KSLAB = 64;      // bf16 elements per 128-byte swizzle row
+constexpr int NUM_B_STAGES = 2;
+constexpr int NUM_A_STAGES = 2;
+constexpr int NUM_ACC_STAGES = 2;
+constexpr int NUM_CS_STAGES = 4;
+constexpr int KC = 8;          // candidates per (row, segment)
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+
+struct SmemLayout {
+  // operand buffers first: 1024-byte alignment required by SWIZZLE_128B
+  static constexpr int a_bytes(int dp) { return TM * dp * 2; }
+  static constexpr int b_bytes(int dp) { return TN * dp * 2; }
+};
+
+struct Barriers {
+  uint64_t b_full[NUM_B_STAGES], b_empty[NUM_B_STAGES];
+  uint64_t a_full[NUM_A_STAGES], a_empty[NUM_A_STAGES];
+  uint64_t acc_full[NUM_ACC_STAGES], acc_empty[NUM_ACC_STAGES];
+  uint64_t cs_full[NUM_CS_STAGES], cs_empty[NUM_CS_STAGES];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns of 32-bit accumulators: thread i <- TMEM lane (quadrant*32 + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// The wait names the destination registers as in/out operands so the compiler cannot schedule a use of
+// them above the wait (tcgen05.ld is asynchronous).
+__device__ __forceinline__ void tmem_wait_ld(float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bit 46,
+// layout type 2 at bits 61-63, SBO = 1024 B between 8-row groups, LBO unused for swizzled K-major).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                             // leading byte offset (ignored)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: kind::f16, A/B = BF16, D = F32, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ascending-by-score insertion into the register-resident top-KC (bv[0] best ... bv[KC-1] worst)
+__device__ __forceinline__ void topk_insert(float (&bv)[KC], uint32_t (&bi)[KC], float v, uint32_t col) {
+  bv[KC - 1] = v;
+  bi[KC - 1] = col;
+#pragma unroll
+  for (int p = KC - 1; p > 0; --p) {
+    if (bv[p] > bv[p - 1]) {
+      float tv = bv[p]; bv[p] = bv[p - 1]; bv[p - 1] = tv;
+      uint32_t ti = bi[p]; bi[p] = bi[p - 1]; bi[p - 1] = ti;
+    }
+  }
+}
+
+struct KParams {
+  int64_t q0, q1, t0, t1;
+  int dp;              // padded descriptor length (64 or 128)
+  int nseg;
+  int row_blocks;      // ceil((q1-q0)/128)
+  int64_t tile_lo;     // first 256-column tile (global tile grid)
+  int64_t tile_hi;     // one past the last tile
+  int tiles_per_seg;
+  const float2* colsb;  // [Ft_total + pad] (scale, bias)
+  const float* bounds;  // device: [0] 1/scale_max, [1] 1/scale_min, [2] bias_max
+  uint32_t* cand_idx;
+  float* cand_score;
+  float* dump;
+};
+
+template <bool DUMP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const KParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16-byte aligned: align by hand
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = TM * P.dp * 2, b_bytes = TN * P.dp * 2;
+  uint8_t* smem_a = smem;                                   // NUM_A_STAGES x a_bytes
+  uint8_t* smem_b = smem_a + NUM_A_STAGES * a_bytes;        // NUM_B_STAGES x b_bytes
+  float2* smem_cs = (float2*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x TN float2
+  Barriers* bars = (Barriers*)(smem_cs + NUM_CS_STAGES * TN);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ksl = P.dp / KSLAB;   // 128-byte K slabs per operand row
+  const int kst = P.dp / 16;      // UMMA K steps per tile
+  const int64_t num_units = (int64_t)P.row_blocks * P.nseg;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+    for (int i = 0; i < NUM_A_STAGES; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
+    for (int i = 0; i < NUM_ACC_STAGES; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], NUM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (2 accumulator stages x 256); one CTA per SM
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t bs = 0, bph = 0, as = 0, aph = 0, cs = 0, cph = 0;
+      for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int sg = (int)(u / P.row_blocks), rb = (int)(u % P.row_blocks);  // segment-major: neighbours share B tiles in L2
+        const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
+        const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
+        if (tl >= th) continue;
+        mbar_wait(&bars->a_empty[as], aph ^ 1);
+        mbar_arrive_expect_tx(&bars->a_full[as], (uint32_t)a_bytes);
+        for (int s = 0; s < ksl; ++s)
+          tma_load_2d(smem_a + as * a_bytes + s * (TM * 128), &map_q, s * KSLAB, (int)(P.q0 + (int64_t)rb * TM), &bars->a_full[as]);
+        if (++as == NUM_A_STAGES) { as = 0; aph ^= 1; }
+        for (int64_t t = tl; t < th; ++t) {
+          mbar_wait(&bars->cs_empty[cs], cph ^ 1);
+          mbar_arrive_expect_tx(&bars->cs_full[cs], TN * (uint32_t)sizeof(float2));
+          bulk_load_1d(smem_cs + cs * TN, P.colsb + t * TN, TN * (uint32_t)sizeof(float2), &bars->cs_full[cs]);
+          if (++cs == NUM_CS_STAGES) { cs = 0; cph ^= 1; }
+          mbar_wait(&bars->b_empty[bs], bph ^ 1);
+          mbar_arrive_expect_tx(&bars->b_full[bs], (uint32_t)b_bytes);
+          for (int s = 0; s < ksl; ++s)
+            tma_load_2d(smem_b + bs * b_bytes + s * (TN * 128), &map_t, s * KSLAB, (int)(t * TN), &bars->b_full[bs]);
+          if (++bs == NUM_B_STAGES) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(TM, TN);
+      uint32_t bs = 0, bph = 0, as = 0, aph = 0, acs = 0, acph = 0;
+      for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int sg = (int)(u / P.row_blocks);
+        const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
+        const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
+        if (tl >= th) continue;
+        mbar_wait(&bars->a_full[as], aph);
+        const uint32_t a_addr = smem_u32(smem_a + as * a_bytes);
+        for (int64_t t = tl; t < th; ++t) {
+          mbar_wait(&bars->acc_empty[acs], acph ^ 1);
+          mbar_wait(&bars->b_full[bs], bph);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(smem_b + bs * b_bytes);
+          const uint32_t d_tmem = tmem_base + acs * TN;
+          for (int k = 0; k < kst; ++k) {
+            const int slab = k >> 2, kin = k & 3;  // 4 K steps (32 B each) per 128-byte swizzle row
+            const uint64_t adesc = make_kmajor_sw128_desc(a_addr + slab * (TM * 128) + kin * 32);
+            const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + slab * (TN * 128) + kin * 32);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+          }
+          tc_commit(&bars->b_empty[bs]);     // smem slot reusable once these MMAs have read it
+          tc_commit(&bars->acc_full[acs]);   // accumulator ready for the epilogue
+          if (++bs == NUM_B_STAGES) { bs = 0; bph ^= 1; }
+          if (++acs == NUM_ACC_STAGES) { acs = 0; acph ^= 1; }
+        }
+        tc_commit(&bars->a_empty[as]);
+        if (++as == NUM_A_STAGES) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    const float inv_smax = P.bounds[0], inv_smin = P.bounds[1], bias_max = P.bounds[2];
+    uint32_t acs = 0, acph = 0, cs = 0, cph = 0;
+    for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int sg = (int)(u / P.row_blocks), rb = (int)(u % P.row_blocks);
+      const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
+      const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
+      const int64_t qrow = P.q0 + (int64_t)rb * TM + row_in_tile;
+      float bv[KC];
+      uint32_t bi[KC];
+#pragma unroll
+      for (int i = 0; i < KC; ++i) { bv[i] = -CUDART_INF_F; bi[i] = 0xffffffffu; }
+      float thr_pre = -CUDART_INF_F;  // conservative threshold on the RAW accumulator
+      for (int64_t t = tl; t < th; ++t) {
+        mbar_wait(&bars->acc_full[acs], acph);
+        mbar_wait(&bars->cs_full[cs], cph);
+        tc_fence_after();
+        const float2* csb = smem_cs + cs * TN;
+        const int64_t col0 = t * TN;
+        const bool partial = DUMP || (col0 < P.t0) || (col0 + TN > P.t1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * TN;
+        float va[32], vb[32];
+        tmem_ld32(taddr, va);
+        tmem_wait_ld(va);
+#pragma unroll
+        for (int c = 0; c < TN / 32; ++c) {
+          float(&cur)[32] = (c & 1) ? vb : va;
+          float(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < TN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
+          bool slow = partial;
+          if (!partial) {
+            float m = cur[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fmaxf(m, cur[j]);
+            slow = m > thr_pre;
+          }
+          if (slow) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float gm = cur[8 * g];
+#pragma unroll
+              for (int j = 1; j < 8; ++j) gm = fmaxf(gm, cur[8 * g + j]);
+              if (partial || gm > thr_pre) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int cc = c * 32 + 8 * g + j;
+                  const float2 sb = csb[cc];
+                  const float v = fmaf(cur[8 * g + j], sb.x, sb.y);
+                  const int64_t col = col0 + cc;
+                  const bool ok = !partial || (col >= P.t0 && col < P.t1);
+                  if (DUMP && ok && qrow < P.q1) P.dump[(qrow - P.q0) * (P.t1 - P.t0) + (col - P.t0)] = v;
+                  if (ok && v > bv[KC - 1]) {
+                    topk_insert(bv, bi, v, (uint32_t)col);
+                    // every later candidate needs fl(acc*scale + bias) > theta  =>  acc > thr_pre
+                    // (bounds carry a 1e-6 relative and a rounding-sized absolute slack)
+                    const float theta = bv[KC - 1];
+                    const float num = theta - bias_max - 1.0e-6f * (fabsf(theta) + fabsf(bias_max));
+                    thr_pre = num * (num >= 0.f ? inv_smax : inv_smin);
+                  }
+                }
+              }
+            }
+          }
+          if (c + 1 < TN / 32) tmem_wait_ld(nxt);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars->acc_empty[acs]);
+          mbar_arrive(&bars->cs_empty[cs]);
+        }
+        if (++acs == NUM_ACC_STAGES) { acs = 0; acph ^= 1; }
+        if (++cs == NUM_CS_STAGES) { cs = 0; cph ^= 1; }
+      }
+      if (qrow < P.q1) {
+        const int64_t o = ((qrow - P.q0) * P.nseg + sg) * KC;
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+          P.cand_idx[o + i] = bi[i];
+          P.cand_score[o + i] = bv[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dp, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    aps_set_error(APS_ERR_CUDA, "", "cuTensorMapEncodeTiled is not available from the driver");
+    return APS_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)dp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KSLAB, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    aps_set_error(APS_ERR_CUDA, "", "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return APS_ERR_CUDA;
+  }
+  return APS_OK;
+}
+
+// (1/scale_max, 1/scale_min, bias_max) over the searched train rows
+__global__ void k_bounds(const float2* __restrict__ colsb, int64_t t0, int64_t t1, float* __restrict__ out) {
+  __shared__ float s_smax[32], s_smin[32], s_bmax[32];
+  float smax = 0.f, smin = CUDART_INF_F, bmax = -CUDART_INF_F;
+  for (int64_t j = t0 + threadIdx.x; j < t1; j += blockDim.x) {
+    float2 v = colsb[j];
+    smax = fmaxf(smax, v.x);
+    smin = fminf(smin, v.x);
+    bmax = fmaxf(bmax, v.y);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_smax[threadIdx.x >> 5] = smax;
+    s_smin[threadIdx.x >> 5] = smin;
+    s_bmax[threadIdx.x >> 5] = bmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      smax = fmaxf(smax, s_smax[w]);
+      smin = fminf(smin, s_smin[w]);
+      bmax = fmaxf(bmax, s_bmax[w]);
+    }
+    // conservative by one ulp-ish factor: the product (theta-bias_max)*inv must never exceed the true bound
+    out[0] = (smax > 0.f) ? (1.0f / smax) * (1.0f - 1.0e-6f) : 0.f;
+    out[1] = (smin > 0.f && smin < CUDART_INF_F) ? (1.0f / smin) * (1.0f + 1.0e-6f) : CUDART_INF_F;
+    out[2] = bmax;
+  }
+}
+
+}  // namespace
+
+int aps_k_knn_tc_supported(int Dp) { return Dp == 64 || Dp == 128; }
+
 int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p) {
-  (void)s; (void)sm_count; (void)p;
-  aps_set_error(APS_ERR_ARGS, "", "tcgen05 path not built");
-  return APS_ERR_ARGS;
+  if (!aps_k_knn_tc_supported(p.Dp)) {
+    aps_set_error(APS_ERR_DIM, "", "tcgen05 path supports padded descriptor lengths 64 and 128 (got %d)", p.Dp);
+    return APS_ERR_DIM;
+  }
+  if (p.kcand != KC) {
+    aps_set_error(APS_ERR_ARGS, "", "kcand must be %d", KC);
+    return APS_ERR_ARGS;
+  }
+  if (p.q1 <= p.q0 || p.t1 <= p.t0) return APS_OK;
+  CUtensorMap map_q, map_t;
+  APS_TRY(make_map(&map_q, p.Qb, p.Fq_total, p.Dp, TM));
+  APS_TRY(make_map(&map_t, p.Tb, p.Ft_total, p.Dp, TN));
+  KParams P;
+  P.q0 = p.q0; P.q1 = p.q1; P.t0 = p.t0; P.t1 = p.t1;
+  P.dp = p.Dp;
+  P.nseg = p.nseg;
+  P.row_blocks = (int)aps_ceil_div(p.q1 - p.q0, TM);
+  P.tile_lo = p.t0 / TN;
+  P.tile_hi = aps_ceil_div(p.t1, TN);
+  P.tiles_per_seg = (int)aps_ceil_div(P.tile_hi - P.tile_lo, p.nseg);
+  P.colsb = p.colsb;
+  P.cand_idx = p.cand_idx;
+  P.cand_score = p.cand_score;
+  P.dump = p.dump;
+  DevBuf<float> bounds;
+  APS_TRY(bounds.alloc(4, s));
+  k_bounds<<<1, 1024, 0, s>>>(p.colsb, p.t0, p.t1, bounds.p);
+  APS_CUDA(cudaGetLastError());
+  P.bounds = bounds.p;
+  // every (row, segment) slot is written by exactly one work unit (empty segments write empty slots)
+  const size_t smem = 1024 + (size_t)NUM_A_STAGES * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
+                      (size_t)NUM_CS_STAGES * TN * sizeof(float2) + sizeof(Barriers);
+  const int64_t units = (int64_t)P.row_blocks * P.nseg;
+  const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);
+  if (p.dump) {
+    APS_CUDA(cudaFuncSetAttribute(k_knn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<true><<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
+  } else {
+    APS_CUDA(cudaFuncSetAttribute(k_knn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<false><<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
+  }
+  APS_CUDA(cudaGetLastError());
+  return APS_OK;
 }

@@ -393,6 +393,13 @@ class GlobalPlan:
     def compact(self):
         check(lib().aps_gplan_compact(self._h))
 
+    def download_knn(self, q0=0, q1=None):
+        q1 = self.F if q1 is None else q1
+        idx = np.zeros((max(q1 - q0, 0), self.k), np.uint32)
+        dist = np.zeros((max(q1 - q0, 0), self.k), np.float32)
+        check(lib().aps_gplan_download_knn(self._h, int(q0), int(q1), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
     def download(self):
         h = C.c_void_p()
         check(lib().aps_gplan_download(self._h, C.byref(h)))

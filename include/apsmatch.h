@@ -160,9 +160,19 @@ int aps_gplan_filter(aps_gplan* p, int64_t q0, int64_t q1, double ratio); /* K5a
 void* aps_gplan_records_device(aps_gplan* p);
 void* aps_gplan_knn_idx_device(aps_gplan* p);  /* uint32 [F][k] row-major, 1-based */
 void* aps_gplan_knn_dist_device(aps_gplan* p); /* float  [F][k] row-major */
+/* D2H of the kNN table rows [q0,q1): idx/dist host buffers of (q1-q0)*k entries, row-major (synchronises) */
+int aps_gplan_download_knn(aps_gplan* p, int64_t q0, int64_t q1, uint32_t* idx, float* dist);
 int aps_gplan_compact(aps_gplan* p);                         /* K5b: A3 :149-159 on all F records */
 int aps_gplan_download(aps_gplan* p, aps_matchlist** out);   /* D2H of the CSR lists (synchronises) */
 int aps_gplan_pair_counts_device(aps_gplan* p, void** counts_i64); /* n*n int64, column-major, after compact() */
+
+/* ---- diagnostics (tests only): raw output of the tcgen05 candidate kernel -----------------------
+ * Q [nq x D], T [nt x D] ROW-major float (used as given, no normalisation).  scores [nq x nt]
+ * receives (bf16(q).bf16(t))*scale_t + bias_t as the kernel's epilogue computes it (scale = 1,
+ * bias = -|t|^2/2); cand_idx / cand_score [nq x nseg x 8] the candidates it selects (0-based train
+ * rows, 0xFFFFFFFF = empty).  Any of the three outputs may be NULL. */
+int aps_debug_tc_scores(aps_ctx* ctx, const float* Q, int64_t nq, const float* T, int64_t nt, int D, int nseg,
+                        float* scores, uint32_t* cand_idx, float* cand_score);
 
 #ifdef __cplusplus
 }

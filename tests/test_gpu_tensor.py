@@ -1,0 +1,121 @@
+"""GPU: the tcgen05 candidate kernel in isolation (raw scores against a float64 matmul of the
+bf16-rounded operands) and the tensor engine end to end (forced) against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16_round(x):
+    """float32 -> nearest-even bfloat16, returned as float32."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+def tc_scores(aps, Q, T, nseg=1, want_scores=True):
+    ctx = aps._lib.default_context()
+    L = aps._lib.lib()
+    Q = np.ascontiguousarray(Q, np.float32)
+    T = np.ascontiguousarray(T, np.float32)
+    nq, nt = Q.shape[0], T.shape[0]
+    scores = np.zeros((nq, nt), np.float32) if want_scores else None
+    cidx = np.zeros((nq, nseg, 8), np.uint32)
+    csc = np.zeros((nq, nseg, 8), np.float32)
+    aps._lib.check(L.aps_debug_tc_scores(ctx.handle, Q.ctypes.data, nq, T.ctypes.data, nt, Q.shape[1], nseg,
+                                         scores.ctypes.data if want_scores else None, cidx.ctypes.data, csc.ctypes.data))
+    return scores, cidx, csc
+
+
+@pytest.mark.parametrize("nq,nt,D", [(128, 256, 128), (100, 300, 128), (257, 1000, 64), (130, 513, 100), (64, 40, 128)])
+def test_tc_raw_scores_match_bf16_matmul(aps, nq, nt, D):
+    rng = np.random.default_rng(nq * 7 + nt)
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    T = rng.standard_normal((nt, D)).astype(np.float32)
+    got, cidx, csc = tc_scores(aps, Q, T)
+    Qb, Tb = bf16_round(Q).astype(np.float64), bf16_round(T).astype(np.float64)
+    sq = np.zeros(nt, np.float32)
+    for d in range(D):  # sequential float32 sum of squares, as K1 computes it
+        sq = sq + T[:, d] * T[:, d]
+    exp = Qb @ Tb.T - 0.5 * sq.astype(np.float64)[None, :]
+    err = np.abs(got - exp).max()
+    assert err < 2e-3, err          # fp32 accumulation of 128 products of magnitude ~1
+    # candidates = the 8 largest scores of each row, as the kernel's own epilogue values rank them
+    order = np.argsort(-got, axis=1, kind="stable")[:, :8]
+    k8 = min(8, nt)
+    assert np.array_equal(np.sort(cidx[:, 0, :k8], axis=1), np.sort(order[:, :k8].astype(np.uint32), axis=1))
+    assert np.allclose(np.sort(csc[:, 0, :k8], axis=1), np.sort(np.take_along_axis(got, order[:, :k8], 1), axis=1))
+
+
+def test_tc_integer_descriptors_are_exact(aps):
+    """0..255 integer descriptors are exact in bf16 and their dot products exact in fp32 accumulate."""
+    rng = np.random.default_rng(3)
+    Q = rng.integers(0, 256, (256, 128)).astype(np.float32)
+    T = rng.integers(0, 256, (512, 128)).astype(np.float32)
+    got, _, _ = tc_scores(aps, Q, T)
+    sq = (T.astype(np.float64) ** 2).sum(1)
+    exp = Q.astype(np.float64) @ T.astype(np.float64).T - 0.5 * sq[None, :]
+    assert np.array_equal(got.astype(np.float64), exp.astype(np.float32).astype(np.float64))
+
+
+@pytest.mark.parametrize("nseg", [2, 4])
+def test_tc_segments_partition_columns(aps, nseg):
+    rng = np.random.default_rng(nseg)
+    Q = rng.standard_normal((300, 128)).astype(np.float32)
+    T = rng.standard_normal((5000, 128)).astype(np.float32)
+    got, cidx, csc = tc_scores(aps, Q, T, nseg=nseg)
+    tiles = -(-5000 // 256)
+    tps = -(-tiles // nseg)
+    for s in range(nseg):
+        lo, hi = s * tps * 256, min(5000, (s + 1) * tps * 256)
+        seg = got[:, lo:hi]
+        order = np.argsort(-seg, axis=1, kind="stable")[:, :8] + lo
+        assert np.array_equal(np.sort(cidx[:, s, :], axis=1), np.sort(order.astype(np.uint32), axis=1)), s
+
+
+@pytest.mark.parametrize("cid,n,kp", [(1, 6, 2048), (5, 6, 1500)])
+def test_tensor_engine_global_vs_oracle(aps, orc, cid, n, kp):
+    ctx = aps._lib.default_context()
+    desc, c = aps.synth.make_config(cid, n=n, kp=kp)
+    ref = orc.feature_matching_global(desc, 4, c["ratio"], return_knn=True)
+    ctx.set_float_engine(2)
+    try:
+        counts = [d.shape[0] for d in desc]
+        plan = aps.GlobalPlan(ctx, counts, desc[0].shape[1], False, 4)
+        plan.upload(desc)
+        plan.prepare()
+        plan.knn()
+        plan.filter(c["ratio"])
+        plan.compact()
+        matches, _, pair_ptr, rows = plan.download()
+        stats = ctx.last_stats()
+        F = plan.F
+        idx, dist = plan.download_knn()
+        plan.close()
+    finally:
+        ctx.set_float_engine(0)
+    assert stats["engine"] == "tcgen05"
+    assert np.array_equal(idx, ref["knn_idx"])
+    assert np.array_equal(dist.view(np.uint32), ref["knn_dist"].view(np.uint32))
+    assert np.array_equal(pair_ptr, ref["pair_ptr"]) and np.array_equal(rows, ref["rows"])
+    print("tensor engine stats", cid, stats)
+    if cid == 1:
+        assert stats["bf16_exact_operands"] and stats["fallback_rows"] < 0.02 * F
+
+
+def test_tensor_engine_pairwise_and_knn_entry(aps, orc):
+    ctx = aps._lib.default_context()
+    desc, c = aps.synth.make_config(5, n=3, kp=2100)
+    ctx.set_float_engine(2)
+    try:
+        m, met = aps.matchFeaturesScratch(desc[0], desc[1], MatchThreshold=1.5, MaxRatio=0.7)
+        X = orc.normalize_rows_global(np.concatenate(desc))
+        idx, dist = aps.flann_knn_win(X, X[:1000].copy(), 4)
+    finally:
+        ctx.set_float_engine(0)
+    om, omet = orc.match_features(desc[0], desc[1], 1.5, 0.7)
+    assert np.array_equal(m, om) and np.array_equal(met, omet) and len(m) > 100
+    oi, od = orc.knn_l2(X, X[:1000], 4)
+    assert np.array_equal(idx, oi) and np.array_equal(dist.view(np.uint32), od.view(np.uint32))
