@@ -70,6 +70,9 @@ def lib():
         "aps_abi_version": (i32, []),
         "aps_ctx_set_float_engine": (i32, [vp, i32]),
         "aps_ctx_last_stats": (i32, [vp, C.POINTER(i64)]),
+        "aps_ctx_enable_timing": (i32, [vp, i32]),
+        "aps_ctx_tc_time": (i32, [vp, C.POINTER(dbl), C.POINTER(i64)]),
+        "aps_launch_count": (i64, []),
         "aps_host_alloc": (vp, [C.c_size_t]),
         "aps_host_free": (None, [vp]),
         "aps_flann_knn": (i32, [vp, vp, i64, vp, i64, i32, i32, i32, i32, cp, i32, i32, vp, vp]),
@@ -134,6 +137,15 @@ class Context:
 
     def set_float_engine(self, engine: int):
         check(lib().aps_ctx_set_float_engine(self._h, int(engine)))
+
+    def enable_timing(self, on=True):
+        check(lib().aps_ctx_enable_timing(self._h, int(bool(on))))
+
+    def tc_time(self):
+        """(summed tcgen05-kernel milliseconds, launches) since the last call; synchronises."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(lib().aps_ctx_tc_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def synchronize(self):
         check(lib().aps_ctx_synchronize(self._h))

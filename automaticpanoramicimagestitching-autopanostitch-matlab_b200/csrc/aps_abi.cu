@@ -1,6 +1,7 @@
 // aps_abi.cu -- the extern "C" surface declared in include/apsmatch.h: argument checks with the
 // reference's error identifiers, host<->device staging, and the kernel pipelines.
 // No CPU compute path exists here: without a CUDA device every entry fails with APS_ERR_NOGPU.
+#include <atomic>
 #include <cmath>
 #include <limits>
 #include <new>
@@ -23,6 +24,10 @@ void aps_set_error(int code, const char* id, const char* fmt, ...) {
   g_err_id = id ? id : "";
   (void)code;
 }
+
+static std::atomic<int64_t> g_launches{0};
+void aps_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t aps_launch_count(void) { return g_launches.load(); }
 
 extern "C" const char* aps_last_error(void) { return g_err_msg.c_str(); }
 extern "C" const char* aps_error_id(void) { return g_err_id.c_str(); }
@@ -72,6 +77,7 @@ extern "C" void aps_ctx_destroy(aps_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (cudaEvent_t e : c->tc_events) cudaEventDestroy(e);
   if (c->d_scratch_flags) cudaFree(c->d_scratch_flags);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -93,6 +99,29 @@ extern "C" int aps_ctx_synchronize(aps_ctx* c) {
   return APS_OK;
 }
 
+extern "C" int aps_ctx_enable_timing(aps_ctx* c, int enable) {
+  if (!c) APS_FAIL(APS_ERR_ARGS, "", "ctx is NULL");
+  c->timing = enable != 0;
+  return APS_OK;
+}
+
+extern "C" int aps_ctx_tc_time(aps_ctx* c, double* ms_total, int64_t* launches) {
+  if (!c || !ms_total || !launches) APS_FAIL(APS_ERR_ARGS, "", "bad args");
+  APS_CUDA(cudaSetDevice(c->device));
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < c->tc_events.size(); i += 2) {
+    float ms = 0.f;
+    APS_CUDA(cudaEventElapsedTime(&ms, c->tc_events[i], c->tc_events[i + 1]));
+    total += ms;
+  }
+  *ms_total = total;
+  *launches = (int64_t)(c->tc_events.size() / 2);
+  for (cudaEvent_t e : c->tc_events) cudaEventDestroy(e);
+  c->tc_events.clear();
+  return APS_OK;
+}
+
 extern "C" int aps_ctx_set_float_engine(aps_ctx* c, int engine) {
   if (!c || engine < 0 || engine > 2) APS_FAIL(APS_ERR_ARGS, "", "bad engine");
   c->float_engine = engine;
@@ -101,6 +130,9 @@ extern "C" int aps_ctx_set_float_engine(aps_ctx* c, int engine) {
 
 extern "C" int aps_ctx_last_stats(aps_ctx* c, int64_t stats[4]) {
   if (!c || !stats) APS_FAIL(APS_ERR_ARGS, "", "bad args");
+  APS_CUDA(cudaSetDevice(c->device));
+  APS_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->stats[2] == 2) c->stats[1] = c->h_flags[32];  // fallback-row count of the last tensor search
   for (int i = 0; i < 4; ++i) stats[i] = c->stats[i];
   return APS_OK;
 }
@@ -146,7 +178,7 @@ __global__ void k_pad_rows_u8(const uint8_t* __restrict__ src, int64_t N, int nb
 static int pad_rows(cudaStream_t s, const uint8_t* src, int64_t N, int nb, int nb16, uint8_t* dst) {
   if (N == 0) return APS_OK;
   k_pad_rows_u8<<<(unsigned)aps_ceil_div(N * nb16, 256), 256, 0, s>>>(src, N, nb, nb16, dst);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -184,7 +216,8 @@ struct FloatSide {          // one prepared descriptor set
   const float* sq = nullptr;   // sum(xn^2)
   const float* invn = nullptr;
   const __nv_bfloat16* xb = nullptr;  // [N x Dp] or nullptr when the tensor path is not prepared
-  const float2* colsb = nullptr;
+  const float* colscale = nullptr;
+  const float* colbias = nullptr;
   int64_t N = 0;
 };
 
@@ -226,7 +259,9 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   aps_tc_problem p;
   p.Qb = Q.xb;
   p.Tb = T.xb;
-  p.colsb = T.colsb;
+  p.colscale = T.colscale;
+  p.colbias = T.colbias;
+  p.bias = bias_mode;
   p.Fq_total = Q.N;
   p.Ft_total = T.N;
   p.Dp = Dp;
@@ -239,7 +274,16 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   p.cand_idx = cidx.p;
   p.cand_score = cscore.p;
   p.dump = nullptr;
-  APS_TRY(aps_k_knn_tc(c->stream, c->sm_count, p));
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (c->timing) {
+    APS_CUDA(cudaEventCreate(&ev0));
+    APS_CUDA(cudaEventCreate(&ev1));
+  }
+  APS_TRY(aps_k_knn_tc(c->stream, c->sm_count, p, ev0, ev1));
+  if (c->timing) {
+    c->tc_events.push_back(ev0);
+    c->tc_events.push_back(ev1);
+  }
   APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nseg, kcand, cidx.p,
                        cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq));
   // rows that could not be proven complete: exact search (device-side count, no host round trip)
@@ -253,7 +297,7 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
 struct FloatSet {
   DevBuf<float> raw, xn, sq, invn;
   DevBuf<__nv_bfloat16> xb;
-  DevBuf<float2> colsb;
+  DevBuf<float> colscale, colbias;
   DevBuf<int32_t> flags;  // [8]: exact, maxdev bits, maxsq bits, maxabs bits
   int64_t N = 0;
   int D = 0;
@@ -264,7 +308,8 @@ struct FloatSet {
     s.sq = sq.p;
     s.invn = invn.p;
     s.xb = xb.p;
-    s.colsb = colsb.p;
+    s.colscale = colscale.p;
+    s.colbias = colbias.p;
     s.N = N;
     return s;
   }
@@ -295,9 +340,10 @@ static int floatset_prepare(aps_ctx* c, FloatSet& fs, int norm_mode, bool tensor
   if (tensor) {
     const int Dp = (fs.D + 63) / 64 * 64;
     APS_TRY(fs.xb.alloc((size_t)fs.N * Dp, c->stream));
-    APS_TRY(fs.colsb.alloc((size_t)fs.N + 256, c->stream));  // +256: whole-tile bulk loads
+    APS_TRY(fs.colscale.alloc((size_t)fs.N + 256, c->stream));
+    APS_TRY(fs.colbias.alloc((size_t)fs.N + 256, c->stream));  // +256: whole-tile bulk loads
     APS_TRY(aps_k_prepare_operands(c->stream, fs.raw.p, xn, fs.sq.p, fs.invn.p, fs.N, fs.D, Dp, fs.flags.p,
-                                   bias_mode, fs.xb.p, fs.colsb.p));
+                                   bias_mode, fs.xb.p, fs.colscale.p, fs.colbias.p));
   }
   return APS_OK;
 }
@@ -367,12 +413,13 @@ extern "C" int aps_flann_knn(aps_ctx* c, const void* train, int64_t Ft, const vo
       if (tc) {
         const int Dp = (D + 63) / 64 * 64;
         APS_TRY(Q.xb.alloc((size_t)Fq * Dp, c->stream));
-        APS_TRY(Q.colsb.alloc((size_t)Fq + 256, c->stream));
+        APS_TRY(Q.colscale.alloc((size_t)Fq + 256, c->stream));
+    APS_TRY(Q.colbias.alloc((size_t)Fq + 256, c->stream));
         // NOTE: operands of BOTH sides are built after both flag passes ran (same stream order)
         APS_TRY(aps_k_prepare_operands(c->stream, Q.raw.p, Q.raw.p, Q.sq.p, Q.invn.p, Fq, D, Dp, T.flags.p, 1,
-                                       Q.xb.p, Q.colsb.p));
+                                       Q.xb.p, Q.colscale.p, Q.colbias.p));
         APS_TRY(aps_k_prepare_operands(c->stream, T.raw.p, T.raw.p, T.sq.p, T.invn.p, Ft, D, Dp, T.flags.p, 1,
-                                       T.xb.p, T.colsb.p));
+                                       T.xb.p, T.colscale.p, T.colbias.p));
       }
     }
     qs = Q.side();
@@ -470,13 +517,15 @@ extern "C" int aps_nearest2_ssd(aps_ctx* c, const float* A, int64_t N1, const fl
   if (tc) {
     const int Dp = (D + 63) / 64 * 64;
     APS_TRY(QA.xb.alloc((size_t)N1 * Dp, c->stream));
-    APS_TRY(QA.colsb.alloc((size_t)N1 + 256, c->stream));
+    APS_TRY(QA.colscale.alloc((size_t)N1 + 256, c->stream));
+    APS_TRY(QA.colbias.alloc((size_t)N1 + 256, c->stream));
     APS_TRY(TB.xb.alloc((size_t)N2 * Dp, c->stream));
-    APS_TRY(TB.colsb.alloc((size_t)N2 + 256, c->stream));
+    APS_TRY(TB.colscale.alloc((size_t)N2 + 256, c->stream));
+    APS_TRY(TB.colbias.alloc((size_t)N2 + 256, c->stream));
     APS_TRY(aps_k_prepare_operands(c->stream, QA.raw.p, QA.raw.p, QA.sq.p, QA.invn.p, N1, D, Dp, TB.flags.p, 1,
-                                   QA.xb.p, QA.colsb.p));
+                                   QA.xb.p, QA.colscale.p, QA.colbias.p));
     APS_TRY(aps_k_prepare_operands(c->stream, TB.raw.p, TB.raw.p, TB.sq.p, TB.invn.p, N2, D, Dp, TB.flags.p, 1,
-                                   TB.xb.p, TB.colsb.p));
+                                   TB.xb.p, TB.colscale.p, TB.colbias.p));
   }
   DevBuf<uint32_t> di;
   DevBuf<float> dd1, dd2;
@@ -863,9 +912,10 @@ static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* des
   if (tensor) {
     const int Dp = (D + 63) / 64 * 64;
     APS_TRY(ps.rawset.xb.alloc((size_t)F * Dp, c->stream));
-    APS_TRY(ps.rawset.colsb.alloc((size_t)F + 256, c->stream));
+    APS_TRY(ps.rawset.colscale.alloc((size_t)F + 256, c->stream));
+    APS_TRY(ps.rawset.colbias.alloc((size_t)F + 256, c->stream));
     APS_TRY(aps_k_prepare_operands(c->stream, ps.rawset.raw.p, ps.rawset.raw.p, ps.rawset.sq.p, ps.rawset.invn.p, F,
-                                   D, Dp, ps.rawset.flags.p, 1, ps.rawset.xb.p, ps.rawset.colsb.p));
+                                   D, Dp, ps.rawset.flags.p, 1, ps.rawset.xb.p, ps.rawset.colscale.p, ps.rawset.colbias.p));
   }
   if (any_big) {
     APS_TRY(floatset_alloc(c, ps.normset, F, D));
@@ -1099,18 +1149,20 @@ extern "C" int aps_debug_tc_scores(aps_ctx* c, const float* Q, int64_t nq, const
   APS_TRY(aps_k_prepare_norm(c->stream, qs.raw.p, nq, D, APS_NORM_NONE, qs.raw.p, qs.sq.p, qs.invn.p, ts.flags.p));
   APS_TRY(aps_k_prepare_norm(c->stream, ts.raw.p, nt, D, APS_NORM_NONE, ts.raw.p, ts.sq.p, ts.invn.p, ts.flags.p));
   APS_TRY(qs.xb.alloc((size_t)nq * Dp, c->stream));
-  APS_TRY(qs.colsb.alloc((size_t)nq + 256, c->stream));
+  APS_TRY(qs.colscale.alloc((size_t)nq + 256, c->stream));
+    APS_TRY(qs.colbias.alloc((size_t)nq + 256, c->stream));
   APS_TRY(ts.xb.alloc((size_t)nt * Dp, c->stream));
-  APS_TRY(ts.colsb.alloc((size_t)nt + 256, c->stream));
-  APS_TRY(aps_k_prepare_operands(c->stream, qs.raw.p, qs.raw.p, qs.sq.p, qs.invn.p, nq, D, Dp, ts.flags.p, 1, qs.xb.p, qs.colsb.p));
-  APS_TRY(aps_k_prepare_operands(c->stream, ts.raw.p, ts.raw.p, ts.sq.p, ts.invn.p, nt, D, Dp, ts.flags.p, 1, ts.xb.p, ts.colsb.p));
+  APS_TRY(ts.colscale.alloc((size_t)nt + 256, c->stream));
+    APS_TRY(ts.colbias.alloc((size_t)nt + 256, c->stream));
+  APS_TRY(aps_k_prepare_operands(c->stream, qs.raw.p, qs.raw.p, qs.sq.p, qs.invn.p, nq, D, Dp, ts.flags.p, 1, qs.xb.p, qs.colscale.p, qs.colbias.p));
+  APS_TRY(aps_k_prepare_operands(c->stream, ts.raw.p, ts.raw.p, ts.sq.p, ts.invn.p, nt, D, Dp, ts.flags.p, 1, ts.xb.p, ts.colscale.p, ts.colbias.p));
   DevBuf<float> dump, cscore;
   DevBuf<uint32_t> cidx;
   if (scores) APS_TRY(dump.alloc((size_t)nq * nt, c->stream));
   APS_TRY(cidx.alloc((size_t)nq * nseg * 8, c->stream));
   APS_TRY(cscore.alloc((size_t)nq * nseg * 8, c->stream));
   aps_tc_problem p;
-  p.Qb = qs.xb.p; p.Tb = ts.xb.p; p.colsb = ts.colsb.p;
+  p.Qb = qs.xb.p; p.Tb = ts.xb.p; p.colscale = ts.colscale.p; p.colbias = ts.colbias.p; p.bias = 1;
   p.Fq_total = nq; p.Ft_total = nt; p.Dp = Dp;
   p.q0 = 0; p.q1 = nq; p.t0 = 0; p.t1 = nt;
   p.nseg = nseg; p.kcand = 8;

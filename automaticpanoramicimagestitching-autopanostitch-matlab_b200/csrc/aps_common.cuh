@@ -14,6 +14,7 @@
 #define APS_EPS32 1.1920928955078125e-07f  // eps('single')
 
 void aps_set_error(int code, const char* id, const char* fmt, ...);
+void aps_count_launch(int n = 1);  // every kernel launch of the library is counted (bench.py's gpu_launches)
 
 #define APS_CUDA(call)                                                                                        \
   do {                                                                                                        \
@@ -23,6 +24,13 @@ void aps_set_error(int code, const char* id, const char* fmt, ...);
                     __LINE__);                                                                                \
       return APS_ERR_CUDA;                                                                                    \
     }                                                                                                         \
+  } while (0)
+
+// after every <<<>>> launch: count it and check the launch status
+#define APS_LAUNCHED()       \
+  do {                       \
+    aps_count_launch();      \
+    APS_CUDA(cudaGetLastError()); \
   } while (0)
 
 #define APS_TRY(call)          \
@@ -38,6 +46,8 @@ struct aps_ctx {
   bool own_stream = false;
   int float_engine = 0;  // 0 auto, 1 exact only, 2 tensor required
   int64_t stats[4] = {0, 0, 0, 0};
+  bool timing = false;
+  std::vector<cudaEvent_t> tc_events;  // pairs (start, stop) of tcgen05 kernel launches
   int32_t* d_scratch_flags = nullptr;  // small persistent device scratch (64 ints)
   int32_t* h_flags = nullptr;          // pinned mirror
 };
@@ -93,7 +103,7 @@ int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int n
 //   bias_mode: 0 -> bias 0 ; 1 -> bias = -sq/2 (SSD on un-normalised rows)
 int aps_k_prepare_operands(cudaStream_t s, const float* raw, const float* xn, const float* sq, const float* invn,
                            int64_t F, int D, int Dp, const int32_t* exact_flag, int bias_mode, __nv_bfloat16* xb,
-                           float2* colsb);
+                           float* colscale, float* colbias);
 
 // K2f aps_knn_exact.cu : exact CUDA-core kNN.  rows==nullptr -> queries [q0,q0+nq) ; else rows[i].
 //   metric 0: FLANN-order squared L2 ; metric 1: SSD order (a2 + b2) - 2*G with sq arrays.
@@ -111,7 +121,9 @@ int aps_k_knn_hamming(cudaStream_t s, const uint8_t* Q, int64_t q0, int64_t nq, 
 struct aps_tc_problem {
   const __nv_bfloat16* Qb;  // [Fq_total x Dp] query operands
   const __nv_bfloat16* Tb;  // [Ft_total x Dp] train operands
-  const float2* colsb;      // [Ft_total] (scale,bias) per train row
+  const float* colscale;    // [Ft_total + 256] per train row
+  const float* colbias;     // [Ft_total + 256] per train row (used iff bias)
+  int bias;                 // 0: score = dot*scale ; 1: score = dot*scale + bias
   int64_t Fq_total, Ft_total;
   int Dp;
   int64_t q0, q1;  // query rows to search
@@ -123,7 +135,9 @@ struct aps_tc_problem {
   float* dump;          // optional [ (q1-q0) x (t1-t0) ] raw scores (tests only), else nullptr
 };
 int aps_k_knn_tc_supported(int Dp);
-int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p);
+// ev0/ev1 (optional): recorded immediately before / after the candidate kernel itself
+int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEvent_t ev0 = nullptr,
+                 cudaEvent_t ev1 = nullptr);
 
 // K3 aps_rerank.cu : exact FP32 re-rank of the candidates + completeness proof.
 //   approx distance of a score: alpha[row] + beta[row]*score ; row proven iff

@@ -60,7 +60,7 @@ int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, 
   if (q1 <= q0) return APS_OK;
   k_global_filter<<<(unsigned)aps_ceil_div(q1 - q0, 256), 256, 0, s>>>(idx, dist, k, q0, q1, img_of_row, img_off,
                                                                       ratio_thr, target, partner);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -162,7 +162,7 @@ int aps_k_fill_img_of_row(cudaStream_t s, const int64_t* img_off, int n, int64_t
   if (n == 0 || maxcount == 0) return APS_OK;
   dim3 grid((unsigned)aps_min64(aps_ceil_div(maxcount, 256), 64), (unsigned)n);
   k_fill_img_of_row<<<grid, 256, 0, s>>>(img_off, n, img_of_row);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -171,13 +171,13 @@ int aps_k_global_compact(cudaStream_t s, const int32_t* target, const uint32_t* 
                           int64_t* pair_counts, int64_t* pair_ptr, int64_t* rank, uint32_t* rows) {
   if (n == 0) return APS_OK;
   k_rank_per_image<<<n, 32, (size_t)n * sizeof(int), s>>>(target, img_off, n, dir_counts, rank);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   k_pair_counts_scan<<<1, 1024, 0, s>>>(dir_counts, n, pair_counts, pair_ptr);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   if (F > 0) {
     k_scatter_rows<<<(unsigned)aps_ceil_div(F, 256), 256, 0, s>>>(target, partner, img_of_row, img_off, n, F,
                                                                  dir_counts, pair_ptr, rank, rows);
-    APS_CUDA(cudaGetLastError());
+    APS_LAUNCHED();
   }
   return APS_OK;
 }
@@ -204,7 +204,7 @@ int aps_k_hamming2_finalize(cudaStream_t s, int64_t N1, int64_t N2, int nb, cons
                             const float* dist_k2, uint32_t* idx2, float* d1, float* d2) {
   if (N1 == 0) return APS_OK;
   k_hamming2_finalize<<<(unsigned)aps_ceil_div(N1, 256), 256, 0, s>>>(N1, N2, nb, idx_k2, dist_k2, idx2, d1, d2);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -222,7 +222,7 @@ int aps_k_split_k2(cudaStream_t s, int64_t N1, const uint32_t* idx_k2, const flo
                    float* d1, float* d2) {
   if (N1 == 0) return APS_OK;
   k_split_k2<<<(unsigned)aps_ceil_div(N1, 256), 256, 0, s>>>(N1, idx_k2, dist_k2, idx2, d1, d2);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -330,14 +330,14 @@ int aps_k_pair_filter_unique(cudaStream_t s, const uint32_t* idx2, const float* 
   unsigned grid = (unsigned)aps_ceil_div(N1, 256);
   k_pair_keys<<<grid, 256, 0, s>>>(idx2, d1, d2, N1, is_binary, nbits, match_threshold, max_ratio, unique,
                                    best_by_train, keys);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   // winners are written over best_by_train's tail?  No -- they get their own region: keys[N1..2*N1)
   unsigned long long* winners = keys + N1;
   k_pair_collect<<<grid, 256, 0, s>>>(idx2, N1, unique, best_by_train, keys, count_dev, winners);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   unsigned rgrid = (unsigned)aps_min64(aps_ceil_div(N1, 256), 148);
   k_pair_rank_emit<<<rgrid, 256, 0, s>>>(winners, count_dev, idx2, unique, matches, metric);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -369,8 +369,8 @@ int aps_k_select_partners(cudaStream_t s, const int64_t* counts_cm, int n, int m
   DevBuf<uint8_t> P;
   APS_TRY(P.alloc((size_t)n * n, s));
   k_select_rows<<<n, 128, 0, s>>>(counts_cm, n, take, P.p);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   k_select_sym<<<(unsigned)aps_ceil_div((int64_t)n * n, 256), 256, 0, s>>>(P.p, n, cand_cm);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }

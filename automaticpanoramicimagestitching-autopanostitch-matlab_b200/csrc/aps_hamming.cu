@@ -89,7 +89,7 @@ int launch_nw(cudaStream_t s, const uint8_t* Q, int64_t q0, int64_t nq, const ui
     k_knn_hamming<NW, 4><<<grid, HQ, 0, s>>>(q4, q0, nq, t4, t0, t1, k, out_row0, idx, dist);
   else
     k_knn_hamming<NW, 8><<<grid, HQ, 0, s>>>(q4, q0, nq, t4, t0, t1, k, out_row0, idx, dist);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 

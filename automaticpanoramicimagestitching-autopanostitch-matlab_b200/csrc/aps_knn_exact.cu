@@ -199,6 +199,6 @@ int aps_k_knn_exact(cudaStream_t s, const float* Q, const float* sqQ, const int3
     APS_CUDA(cudaFuncSetAttribute(k_knn_exact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_knn_exact<1><<<grid, TJ, smem, s>>>(Q, sqQ, rows, nrows_dev, q0, nq, T, sqT, t0, t1, D, k, out_row0, idx, dist);
   }
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }

@@ -13,10 +13,13 @@
 //   warp 0   : TMA producer  (A tile once per unit, B tiles + per-column (scale,bias) per step)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
 //   warps 2-5: epilogue, thread == query row (tcgen05.ld 32x32b: lane i of the warp's TMEM
-//              quadrant), running top-K' in registers.  Fast path per 32-column chunk is a
-//              FMNMX3 tree on the raw accumulators against a conservative per-row threshold
-//              (theta - bias_max) / scale_max: no shared-memory traffic, no multiply; only chunks
-//              that may contain a candidate read (scale,bias) and do the exact compare/insert.
+//              quadrant).  Per 32-column chunk: score = acc*scale (+bias) with the per-column
+//              constants read as broadcast LDS.128, a FMNMX3 tree to four 8-column group maxima,
+//              one compare against the row's current K'-th best (theta, a register).  Only groups
+//              that contain a new candidate take the insertion path; the row's sorted top-K' list
+//              lives in shared memory and is updated by a small out-of-line routine, so the hot
+//              loop stays a few hundred instructions (an earlier fully unrolled register version
+//              was 348 KB of SASS and 69 % instruction-fetch stalled -- profiles/).
 // Pipelines (all mbarrier based): B smem ring (2 x 64 KB) TMA<->MMA, A double buffer, TMEM
 // accumulator double buffer (2 x 256 columns = all 512) MMA<->epilogue, (scale,bias) ring.
 //
@@ -151,17 +154,20 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ascending-by-score insertion into the register-resident top-KC (bv[0] best ... bv[KC-1] worst)
-__device__ __forceinline__ void topk_insert(float (&bv)[KC], uint32_t (&bi)[KC], float v, uint32_t col) {
-  bv[KC - 1] = v;
-  bi[KC - 1] = col;
-#pragma unroll
-  for (int p = KC - 1; p > 0; --p) {
-    if (bv[p] > bv[p - 1]) {
-      float tv = bv[p]; bv[p] = bv[p - 1]; bv[p - 1] = tv;
-      uint32_t ti = bi[p]; bi[p] = bi[p - 1]; bi[p - 1] = ti;
-    }
+// The row's top-KC list lives in shared memory, slot-major ([slot][row], conflict-free): sv[p*TM]
+// descending by score.  Out of line on purpose (code size); returns the new K'-th best score.
+__device__ __noinline__ float topk_insert_smem(float* sv, uint32_t* si, float v, uint32_t col) {
+  int p = KC - 1;
+  while (p > 0) {
+    const float u = sv[(p - 1) * TM];
+    if (!(v > u)) break;
+    sv[p * TM] = u;
+    si[p * TM] = si[(p - 1) * TM];
+    --p;
   }
+  sv[p * TM] = v;
+  si[p * TM] = col;
+  return sv[(KC - 1) * TM];
 }
 
 struct KParams {
@@ -172,14 +178,14 @@ struct KParams {
   int64_t tile_lo;     // first 256-column tile (global tile grid)
   int64_t tile_hi;     // one past the last tile
   int tiles_per_seg;
-  const float2* colsb;  // [Ft_total + pad] (scale, bias)
-  const float* bounds;  // device: [0] 1/scale_max, [1] 1/scale_min, [2] bias_max
+  const float* colscale;  // [Ft_total + 256] per train row
+  const float* colbias;   // [Ft_total + 256] per train row (read only by the BIAS variant)
   uint32_t* cand_idx;
   float* cand_score;
   float* dump;
 };
 
-template <bool DUMP>
+template <bool BIAS, bool DUMP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const KParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -188,8 +194,10 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   const int a_bytes = TM * P.dp * 2, b_bytes = TN * P.dp * 2;
   uint8_t* smem_a = smem;                                   // NUM_A_STAGES x a_bytes
   uint8_t* smem_b = smem_a + NUM_A_STAGES * a_bytes;        // NUM_B_STAGES x b_bytes
-  float2* smem_cs = (float2*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x TN float2
-  Barriers* bars = (Barriers*)(smem_cs + NUM_CS_STAGES * TN);
+  float* smem_cs = (float*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x {TN scales, TN biases}
+  float* smem_topv = smem_cs + NUM_CS_STAGES * 2 * TN;         // [KC][TM] row-private top-K' scores
+  uint32_t* smem_topi = (uint32_t*)(smem_topv + KC * TM);      // [KC][TM] and their train rows
+  Barriers* bars = (Barriers*)(smem_topi + KC * TM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksl = P.dp / KSLAB;   // 128-byte K slabs per operand row
@@ -228,8 +236,10 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         if (++as == NUM_A_STAGES) { as = 0; aph ^= 1; }
         for (int64_t t = tl; t < th; ++t) {
           mbar_wait(&bars->cs_empty[cs], cph ^ 1);
-          mbar_arrive_expect_tx(&bars->cs_full[cs], TN * (uint32_t)sizeof(float2));
-          bulk_load_1d(smem_cs + cs * TN, P.colsb + t * TN, TN * (uint32_t)sizeof(float2), &bars->cs_full[cs]);
+          mbar_arrive_expect_tx(&bars->cs_full[cs], (BIAS ? 2u : 1u) * TN * (uint32_t)sizeof(float));
+          bulk_load_1d(smem_cs + cs * 2 * TN, P.colscale + t * TN, TN * (uint32_t)sizeof(float), &bars->cs_full[cs]);
+          if (BIAS)
+            bulk_load_1d(smem_cs + cs * 2 * TN + TN, P.colbias + t * TN, TN * (uint32_t)sizeof(float), &bars->cs_full[cs]);
           if (++cs == NUM_CS_STAGES) { cs = 0; cph ^= 1; }
           mbar_wait(&bars->b_empty[bs], bph ^ 1);
           mbar_arrive_expect_tx(&bars->b_full[bs], (uint32_t)b_bytes);
@@ -276,69 +286,85 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     // ===================================== epilogue =========================================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
-    const float inv_smax = P.bounds[0], inv_smin = P.bounds[1], bias_max = P.bounds[2];
+    float* sv = smem_topv + row_in_tile;
+    uint32_t* si = smem_topi + row_in_tile;
     uint32_t acs = 0, acph = 0, cs = 0, cph = 0;
     for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int sg = (int)(u / P.row_blocks), rb = (int)(u % P.row_blocks);
       const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
       const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
       const int64_t qrow = P.q0 + (int64_t)rb * TM + row_in_tile;
-      float bv[KC];
-      uint32_t bi[KC];
 #pragma unroll
-      for (int i = 0; i < KC; ++i) { bv[i] = -CUDART_INF_F; bi[i] = 0xffffffffu; }
-      float thr_pre = -CUDART_INF_F;  // conservative threshold on the RAW accumulator
+      for (int i = 0; i < KC; ++i) {
+        sv[i * TM] = -CUDART_INF_F;
+        si[i * TM] = 0xffffffffu;
+      }
+      float theta = -CUDART_INF_F;  // the row's current K'-th best score
       for (int64_t t = tl; t < th; ++t) {
         mbar_wait(&bars->acc_full[acs], acph);
         mbar_wait(&bars->cs_full[cs], cph);
         tc_fence_after();
-        const float2* csb = smem_cs + cs * TN;
+        const float* cscale = smem_cs + cs * 2 * TN;
         const int64_t col0 = t * TN;
-        const bool partial = DUMP || (col0 < P.t0) || (col0 + TN > P.t1);
+        const bool partial = (col0 < P.t0) || (col0 + TN > P.t1);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * TN;
         float va[32], vb[32];
         tmem_ld32(taddr, va);
         tmem_wait_ld(va);
+#pragma unroll 1
+        for (int c2 = 0; c2 < TN / 64; ++c2) {
 #pragma unroll
-        for (int c = 0; c < TN / 32; ++c) {
-          float(&cur)[32] = (c & 1) ? vb : va;
-          float(&nxt)[32] = (c & 1) ? va : vb;
-          if (c + 1 < TN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
-          bool slow = partial;
-          if (!partial) {
-            float m = cur[0];
-#pragma unroll
-            for (int j = 1; j < 32; ++j) m = fmaxf(m, cur[j]);
-            slow = m > thr_pre;
-          }
-          if (slow) {
+          for (int h = 0; h < 2; ++h) {
+            const int c = 2 * c2 + h;
+            float(&cur)[32] = h ? vb : va;
+            float(&nxt)[32] = h ? va : vb;
+            if (c + 1 < TN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
+            float gm[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              float gm = cur[8 * g];
+              const float4 s0 = *reinterpret_cast<const float4*>(cscale + c * 32 + 8 * g);
+              const float4 s1 = *reinterpret_cast<const float4*>(cscale + c * 32 + 8 * g + 4);
+              if (BIAS) {
+                const float4 b0 = *reinterpret_cast<const float4*>(cscale + TN + c * 32 + 8 * g);
+                const float4 b1 = *reinterpret_cast<const float4*>(cscale + TN + c * 32 + 8 * g + 4);
+                cur[8 * g + 0] = fmaf(cur[8 * g + 0], s0.x, b0.x); cur[8 * g + 1] = fmaf(cur[8 * g + 1], s0.y, b0.y);
+                cur[8 * g + 2] = fmaf(cur[8 * g + 2], s0.z, b0.z); cur[8 * g + 3] = fmaf(cur[8 * g + 3], s0.w, b0.w);
+                cur[8 * g + 4] = fmaf(cur[8 * g + 4], s1.x, b1.x); cur[8 * g + 5] = fmaf(cur[8 * g + 5], s1.y, b1.y);
+                cur[8 * g + 6] = fmaf(cur[8 * g + 6], s1.z, b1.z); cur[8 * g + 7] = fmaf(cur[8 * g + 7], s1.w, b1.w);
+              } else {
+                cur[8 * g + 0] *= s0.x; cur[8 * g + 1] *= s0.y; cur[8 * g + 2] *= s0.z; cur[8 * g + 3] *= s0.w;
+                cur[8 * g + 4] *= s1.x; cur[8 * g + 5] *= s1.y; cur[8 * g + 6] *= s1.z; cur[8 * g + 7] *= s1.w;
+              }
+            }
+            if (partial || DUMP) {  // first / last tile of the searched range: mask foreign columns
 #pragma unroll
-              for (int j = 1; j < 8; ++j) gm = fmaxf(gm, cur[8 * g + j]);
-              if (partial || gm > thr_pre) {
+              for (int j = 0; j < 32; ++j) {
+                const int64_t col = col0 + c * 32 + j;
+                const bool ok = col >= P.t0 && col < P.t1;
+                if (DUMP && ok && qrow < P.q1) P.dump[(qrow - P.q0) * (P.t1 - P.t0) + (col - P.t0)] = cur[j];
+                if (!ok) cur[j] = -CUDART_INF_F;
+              }
+            }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const int cc = c * 32 + 8 * g + j;
-                  const float2 sb = csb[cc];
-                  const float v = fmaf(cur[8 * g + j], sb.x, sb.y);
-                  const int64_t col = col0 + cc;
-                  const bool ok = !partial || (col >= P.t0 && col < P.t1);
-                  if (DUMP && ok && qrow < P.q1) P.dump[(qrow - P.q0) * (P.t1 - P.t0) + (col - P.t0)] = v;
-                  if (ok && v > bv[KC - 1]) {
-                    topk_insert(bv, bi, v, (uint32_t)col);
-                    // every later candidate needs fl(acc*scale + bias) > theta  =>  acc > thr_pre
-                    // (bounds carry a 1e-6 relative and a rounding-sized absolute slack)
-                    const float theta = bv[KC - 1];
-                    const float num = theta - bias_max - 1.0e-6f * (fabsf(theta) + fabsf(bias_max));
-                    thr_pre = num * (num >= 0.f ? inv_smax : inv_smin);
-                  }
+            for (int g = 0; g < 4; ++g) {
+              float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
+              m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
+              m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
+              gm[g] = fmaxf(m, cur[8 * g + 7]);
+            }
+            if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) > theta) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (gm[g] > theta) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (cur[8 * g + j] > theta)
+                      theta = topk_insert_smem(sv, si, cur[8 * g + j], (uint32_t)(col0 + c * 32 + 8 * g + j));
                 }
               }
             }
+            if (c + 1 < TN / 32) tmem_wait_ld(nxt);
           }
-          if (c + 1 < TN / 32) tmem_wait_ld(nxt);
         }
         tc_fence_before();
         __syncwarp();
@@ -353,8 +379,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         const int64_t o = ((qrow - P.q0) * P.nseg + sg) * KC;
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
-          P.cand_idx[o + i] = bi[i];
-          P.cand_score[o + i] = bv[i];
+          P.cand_idx[o + i] = si[i * TM];
+          P.cand_score[o + i] = sv[i * TM];
         }
       }
     }
@@ -404,45 +430,11 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dp, in
   return APS_OK;
 }
 
-// (1/scale_max, 1/scale_min, bias_max) over the searched train rows
-__global__ void k_bounds(const float2* __restrict__ colsb, int64_t t0, int64_t t1, float* __restrict__ out) {
-  __shared__ float s_smax[32], s_smin[32], s_bmax[32];
-  float smax = 0.f, smin = CUDART_INF_F, bmax = -CUDART_INF_F;
-  for (int64_t j = t0 + threadIdx.x; j < t1; j += blockDim.x) {
-    float2 v = colsb[j];
-    smax = fmaxf(smax, v.x);
-    smin = fminf(smin, v.x);
-    bmax = fmaxf(bmax, v.y);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-    smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
-    bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_smax[threadIdx.x >> 5] = smax;
-    s_smin[threadIdx.x >> 5] = smin;
-    s_bmax[threadIdx.x >> 5] = bmax;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-      smax = fmaxf(smax, s_smax[w]);
-      smin = fminf(smin, s_smin[w]);
-      bmax = fmaxf(bmax, s_bmax[w]);
-    }
-    // conservative by one ulp-ish factor: the product (theta-bias_max)*inv must never exceed the true bound
-    out[0] = (smax > 0.f) ? (1.0f / smax) * (1.0f - 1.0e-6f) : 0.f;
-    out[1] = (smin > 0.f && smin < CUDART_INF_F) ? (1.0f / smin) * (1.0f + 1.0e-6f) : CUDART_INF_F;
-    out[2] = bmax;
-  }
-}
-
 }  // namespace
 
 int aps_k_knn_tc_supported(int Dp) { return Dp == 64 || Dp == 128; }
 
-int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p) {
+int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEvent_t ev0, cudaEvent_t ev1) {
   if (!aps_k_knn_tc_supported(p.Dp)) {
     aps_set_error(APS_ERR_DIM, "", "tcgen05 path supports padded descriptor lengths 64 and 128 (got %d)", p.Dp);
     return APS_ERR_DIM;
@@ -463,27 +455,27 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p) {
   P.tile_lo = p.t0 / TN;
   P.tile_hi = aps_ceil_div(p.t1, TN);
   P.tiles_per_seg = (int)aps_ceil_div(P.tile_hi - P.tile_lo, p.nseg);
-  P.colsb = p.colsb;
+  P.colscale = p.colscale;
+  P.colbias = p.colbias;
   P.cand_idx = p.cand_idx;
   P.cand_score = p.cand_score;
   P.dump = p.dump;
-  DevBuf<float> bounds;
-  APS_TRY(bounds.alloc(4, s));
-  k_bounds<<<1, 1024, 0, s>>>(p.colsb, p.t0, p.t1, bounds.p);
-  APS_CUDA(cudaGetLastError());
-  P.bounds = bounds.p;
   // every (row, segment) slot is written by exactly one work unit (empty segments write empty slots)
   const size_t smem = 1024 + (size_t)NUM_A_STAGES * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
-                      (size_t)NUM_CS_STAGES * TN * sizeof(float2) + sizeof(Barriers);
+                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)2 * KC * TM * 4 + sizeof(Barriers);
   const int64_t units = (int64_t)P.row_blocks * P.nseg;
   const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);
-  if (p.dump) {
-    APS_CUDA(cudaFuncSetAttribute(k_knn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<true><<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
-  } else {
-    APS_CUDA(cudaFuncSetAttribute(k_knn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<false><<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
-  }
-  APS_CUDA(cudaGetLastError());
+  if (ev0) APS_CUDA(cudaEventRecord(ev0, s));
+  auto launch = [&](auto kern) -> int {
+    APS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
+    return APS_OK;
+  };
+  if (p.dump)
+    APS_TRY(p.bias ? launch(k_knn_tc<true, true>) : launch(k_knn_tc<false, true>));
+  else
+    APS_TRY(p.bias ? launch(k_knn_tc<true, false>) : launch(k_knn_tc<false, false>));
+  APS_LAUNCHED();
+  if (ev1) APS_CUDA(cudaEventRecord(ev1, s));
   return APS_OK;
 }

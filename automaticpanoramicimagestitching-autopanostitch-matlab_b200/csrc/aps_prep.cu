@@ -36,7 +36,7 @@ int aps_k_transpose_in(cudaStream_t s, const void* src_cm, int64_t N, int D, int
     k_transpose_in<uint32_t><<<grid, block, 0, s>>>((const uint32_t*)src_cm, N, D, (uint32_t*)dst_rm);
   else
     k_transpose_in<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src_cm, N, D, (uint8_t*)dst_rm);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -55,7 +55,7 @@ int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const flo
                                uint32_t* idx_cm, float* dist_cm) {
   if (N == 0) return APS_OK;
   k_transpose_out<<<(unsigned)aps_ceil_div(N * k, 256), 256, 0, s>>>(idx_rm, dist_rm, N, k, idx_cm, dist_cm);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -143,7 +143,7 @@ int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int n
   }
   size_t smem = (size_t)RB * (D + 1) * sizeof(float);
   k_prepare_norm<<<(unsigned)aps_ceil_div(F, RB), 256, smem, s>>>(raw, F, D, RB, norm_mode, xn, sq, invn, flags);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -152,7 +152,8 @@ int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int n
 __global__ void k_prepare_operands(const float* __restrict__ raw, const float* __restrict__ xn,
                                    const float* __restrict__ sq, const float* __restrict__ invn, int64_t F, int D,
                                    int Dp, const int32_t* __restrict__ exact_flag, int bias_mode,
-                                   __nv_bfloat16* __restrict__ xb, float2* __restrict__ colsb) {
+                                   __nv_bfloat16* __restrict__ xb, float* __restrict__ colscale,
+                                   float* __restrict__ colbias) {
   const int exact = *exact_flag;
   const float* src = exact ? raw : xn;
   const int chunks = Dp / 8;
@@ -167,17 +168,20 @@ __global__ void k_prepare_operands(const float* __restrict__ raw, const float* _
       v[j] = __float2bfloat16_rn(c < D ? src[r * D + c] : 0.0f);
     }
     *reinterpret_cast<uint4*>(xb + r * Dp + c0) = *reinterpret_cast<const uint4*>(v);
-    if (c0 == 0) colsb[r] = make_float2(exact ? invn[r] : 1.0f, bias_mode ? -0.5f * sq[r] : 0.0f);
+    if (c0 == 0) {
+      colscale[r] = exact ? invn[r] : 1.0f;
+      colbias[r] = bias_mode ? -0.5f * sq[r] : 0.0f;
+    }
   }
 }
 
 int aps_k_prepare_operands(cudaStream_t s, const float* raw, const float* xn, const float* sq, const float* invn,
                            int64_t F, int D, int Dp, const int32_t* exact_flag, int bias_mode, __nv_bfloat16* xb,
-                           float2* colsb) {
+                           float* colscale, float* colbias) {
   if (F == 0) return APS_OK;
   int64_t total = F * (Dp / 8);
   unsigned grid = (unsigned)aps_min64(aps_ceil_div(total, 256), 148 * 16);
-  k_prepare_operands<<<grid, 256, 0, s>>>(raw, xn, sq, invn, F, D, Dp, exact_flag, bias_mode, xb, colsb);
-  APS_CUDA(cudaGetLastError());
+  k_prepare_operands<<<grid, 256, 0, s>>>(raw, xn, sq, invn, F, D, Dp, exact_flag, bias_mode, xb, colscale, colbias);
+  APS_LAUNCHED();
   return APS_OK;
 }

@@ -168,6 +168,6 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
   k_rerank<<<(unsigned)aps_ceil_div(nq, 8), 256, 0, s>>>(Q, sqQ, invnQ, T, sqT, D, metric, q0, nq, t0, nseg, kcand,
                                                         cand_idx, cand_score, flags, bias_mode, k, out_row0, idx,
                                                         dist, fb_rows, fb_count);
-  APS_CUDA(cudaGetLastError());
+  APS_LAUNCHED();
   return APS_OK;
 }

@@ -71,6 +71,13 @@ int aps_ctx_set_float_engine(aps_ctx* ctx, int engine);
  * candidate set could not be PROVEN complete and were re-searched exactly, [2] engine used
  * (1 exact, 2 tcgen05), [3] 1 if operands were exactly representable in bf16. */
 int aps_ctx_last_stats(aps_ctx* ctx, int64_t stats[4]);
+/* Measurement hooks (bench.py): with timing enabled the float search brackets every launch of the
+ * tcgen05 candidate kernel with CUDA events on the context's stream; aps_ctx_tc_time() synchronises,
+ * returns the summed kernel time and launch count since the last call, and resets them.
+ * aps_launch_count() = kernels launched by this library in this process so far. */
+int aps_ctx_enable_timing(aps_ctx* ctx, int enable);
+int aps_ctx_tc_time(aps_ctx* ctx, double* ms_total, int64_t* launches);
+int64_t aps_launch_count(void);
 /* Pinned host memory for callers that want asynchronous-speed copies (bench, MEX staging). */
 void* aps_host_alloc(size_t bytes);
 void aps_host_free(void* p);
