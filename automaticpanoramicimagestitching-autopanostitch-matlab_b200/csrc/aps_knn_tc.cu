@@ -40,7 +40,8 @@ constexpr int NUM_A_STAGES = 2;
 constexpr int NUM_ACC_STAGES = 2;
 constexpr int NUM_CS_STAGES = 4;
 constexpr int KC = 8;          // candidates per (row, segment)
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_GROUPS = 2;  // epilogue warp groups; group g owns the tiles with (tile counter & 1) == g
+constexpr int NUM_EPI_WARPS = 4 * NUM_EPI_GROUPS;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 struct SmemLayout {
@@ -82,6 +83,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+// producer / MMA-issuer flavour: back off between probes so the spinning lane does not steal issue
+// slots from the epilogue warp that shares its SM sub-partition
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(40);
+  }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -154,20 +172,39 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// The row's top-KC list lives in shared memory, slot-major ([slot][row], conflict-free): sv[p*TM]
-// descending by score.  Out of line on purpose (code size); returns the new K'-th best score.
-__device__ __noinline__ float topk_insert_smem(float* sv, uint32_t* si, float v, uint32_t col) {
+// The row's top-KC list lives in shared memory, slot-major ([slot][row], conflict-free), descending
+// by score; addressed by 32-bit shared-window addresses (ld/st.shared, not generic).  Out of line
+// on purpose (code size); returns the new K'-th best score.
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+constexpr uint32_t SLOT_STRIDE = TM * 4;                  // bytes between consecutive slots of one row
+constexpr uint32_t IDX_PLANE = NUM_EPI_GROUPS * KC * TM * 4;  // bytes from the score plane to the index plane
+
+// The list is UNSORTED (aps_rerank.cu orders the candidates exactly anyway): a new candidate
+// overwrites the current minimum, then the new minimum and its slot are found with 8 independent
+// loads and a FMNMX tree -- ~40 instructions, no dependent shared-memory chain.
+struct ThetaPos {
+  float theta;  // smallest retained score == the row's K'-th best
+  int pos;      // its slot
+};
+__device__ __noinline__ ThetaPos topk_replace_min(uint32_t sv, int pos, float v, uint32_t col) {
+  sts_f32(sv + pos * SLOT_STRIDE, v);
+  sts_u32(sv + IDX_PLANE + pos * SLOT_STRIDE, col);
+  float x[KC];
+#pragma unroll
+  for (int i = 0; i < KC; ++i) x[i] = lds_f32(sv + i * SLOT_STRIDE);
+  float m = x[0];
+#pragma unroll
+  for (int i = 1; i < KC; ++i) m = fminf(m, x[i]);
   int p = KC - 1;
-  while (p > 0) {
-    const float u = sv[(p - 1) * TM];
-    if (!(v > u)) break;
-    sv[p * TM] = u;
-    si[p * TM] = si[(p - 1) * TM];
-    --p;
-  }
-  sv[p * TM] = v;
-  si[p * TM] = col;
-  return sv[(KC - 1) * TM];
+#pragma unroll
+  for (int i = KC - 2; i >= 0; --i) p = (x[i] == m) ? i : p;
+  ThetaPos r;
+  r.theta = m;
+  r.pos = p;
+  return r;
 }
 
 struct KParams {
@@ -195,9 +232,9 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   uint8_t* smem_a = smem;                                   // NUM_A_STAGES x a_bytes
   uint8_t* smem_b = smem_a + NUM_A_STAGES * a_bytes;        // NUM_B_STAGES x b_bytes
   float* smem_cs = (float*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x {TN scales, TN biases}
-  float* smem_topv = smem_cs + NUM_CS_STAGES * 2 * TN;         // [KC][TM] row-private top-K' scores
-  uint32_t* smem_topi = (uint32_t*)(smem_topv + KC * TM);      // [KC][TM] and their train rows
-  Barriers* bars = (Barriers*)(smem_topi + KC * TM);
+  float* smem_topv = smem_cs + NUM_CS_STAGES * 2 * TN;                      // [groups][KC][TM] row-private top-K' scores
+  uint32_t* smem_topi = (uint32_t*)(smem_topv + NUM_EPI_GROUPS * KC * TM);  // [groups][KC][TM] and their train rows
+  Barriers* bars = (Barriers*)(smem_topi + NUM_EPI_GROUPS * KC * TM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksl = P.dp / KSLAB;   // 128-byte K slabs per operand row
@@ -207,8 +244,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   if (threadIdx.x == 0) {
     for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
     for (int i = 0; i < NUM_A_STAGES; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
-    for (int i = 0; i < NUM_ACC_STAGES; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NUM_EPI_WARPS); }
-    for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < NUM_ACC_STAGES; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
+    for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (2 accumulator stages x 256); one CTA per SM
@@ -229,19 +266,19 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
         const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
         if (tl >= th) continue;
-        mbar_wait(&bars->a_empty[as], aph ^ 1);
+        mbar_wait_backoff(&bars->a_empty[as], aph ^ 1);
         mbar_arrive_expect_tx(&bars->a_full[as], (uint32_t)a_bytes);
         for (int s = 0; s < ksl; ++s)
           tma_load_2d(smem_a + as * a_bytes + s * (TM * 128), &map_q, s * KSLAB, (int)(P.q0 + (int64_t)rb * TM), &bars->a_full[as]);
         if (++as == NUM_A_STAGES) { as = 0; aph ^= 1; }
         for (int64_t t = tl; t < th; ++t) {
-          mbar_wait(&bars->cs_empty[cs], cph ^ 1);
+          mbar_wait_backoff(&bars->cs_empty[cs], cph ^ 1);
           mbar_arrive_expect_tx(&bars->cs_full[cs], (BIAS ? 2u : 1u) * TN * (uint32_t)sizeof(float));
           bulk_load_1d(smem_cs + cs * 2 * TN, P.colscale + t * TN, TN * (uint32_t)sizeof(float), &bars->cs_full[cs]);
           if (BIAS)
             bulk_load_1d(smem_cs + cs * 2 * TN + TN, P.colbias + t * TN, TN * (uint32_t)sizeof(float), &bars->cs_full[cs]);
           if (++cs == NUM_CS_STAGES) { cs = 0; cph ^= 1; }
-          mbar_wait(&bars->b_empty[bs], bph ^ 1);
+          mbar_wait_backoff(&bars->b_empty[bs], bph ^ 1);
           mbar_arrive_expect_tx(&bars->b_full[bs], (uint32_t)b_bytes);
           for (int s = 0; s < ksl; ++s)
             tma_load_2d(smem_b + bs * b_bytes + s * (TN * 128), &map_t, s * KSLAB, (int)(t * TN), &bars->b_full[bs]);
@@ -259,11 +296,11 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
         const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
         if (tl >= th) continue;
-        mbar_wait(&bars->a_full[as], aph);
+        mbar_wait_backoff(&bars->a_full[as], aph);
         const uint32_t a_addr = smem_u32(smem_a + as * a_bytes);
         for (int64_t t = tl; t < th; ++t) {
-          mbar_wait(&bars->acc_empty[acs], acph ^ 1);
-          mbar_wait(&bars->b_full[bs], bph);
+          mbar_wait_backoff(&bars->acc_empty[acs], acph ^ 1);
+          mbar_wait_backoff(&bars->b_full[bs], bph);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(smem_b + bs * b_bytes);
           const uint32_t d_tmem = tmem_base + acs * TN;
@@ -285,10 +322,10 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   } else {
     // ===================================== epilogue =========================================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;  // this warp's epilogue group
     const int row_in_tile = quad * 32 + lane;
-    float* sv = smem_topv + row_in_tile;
-    uint32_t* si = smem_topi + row_in_tile;
-    uint32_t acs = 0, acph = 0, cs = 0, cph = 0;
+    const uint32_t sv = smem_u32(smem_topv + (grp * KC) * TM + row_in_tile);
+    uint32_t tcount = 0;  // tiles issued by this CTA so far (same sequence in the MMA warp)
     for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int sg = (int)(u / P.row_blocks), rb = (int)(u % P.row_blocks);
       const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
@@ -296,11 +333,14 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       const int64_t qrow = P.q0 + (int64_t)rb * TM + row_in_tile;
 #pragma unroll
       for (int i = 0; i < KC; ++i) {
-        sv[i * TM] = -CUDART_INF_F;
-        si[i * TM] = 0xffffffffu;
+        sts_f32(sv + i * SLOT_STRIDE, -CUDART_INF_F);
+        sts_u32(sv + IDX_PLANE + i * SLOT_STRIDE, 0xffffffffu);
       }
-      float theta = -CUDART_INF_F;  // the row's current K'-th best score
-      for (int64_t t = tl; t < th; ++t) {
+      float theta = -CUDART_INF_F;  // the row's current K'-th best score (within this group's tiles)
+      int minpos = 0;               // slot holding it
+      for (int64_t t = tl; t < th; ++t, ++tcount) {
+        if ((int)(tcount & 1) != grp) continue;
+        const uint32_t acs = tcount & 1, acph = (tcount >> 1) & 1, cs = tcount & 3, cph = (tcount >> 2) & 1;
         mbar_wait(&bars->acc_full[acs], acph);
         mbar_wait(&bars->cs_full[cs], cph);
         tc_fence_after();
@@ -358,8 +398,11 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                 if (gm[g] > theta) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j)
-                    if (cur[8 * g + j] > theta)
-                      theta = topk_insert_smem(sv, si, cur[8 * g + j], (uint32_t)(col0 + c * 32 + 8 * g + j));
+                    if (cur[8 * g + j] > theta) {
+                      const ThetaPos tp = topk_replace_min(sv, minpos, cur[8 * g + j], (uint32_t)(col0 + c * 32 + 8 * g + j));
+                      theta = tp.theta;
+                      minpos = tp.pos;
+                    }
                 }
               }
             }
@@ -372,15 +415,13 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           mbar_arrive(&bars->acc_empty[acs]);
           mbar_arrive(&bars->cs_empty[cs]);
         }
-        if (++acs == NUM_ACC_STAGES) { acs = 0; acph ^= 1; }
-        if (++cs == NUM_CS_STAGES) { cs = 0; cph ^= 1; }
       }
       if (qrow < P.q1) {
-        const int64_t o = ((qrow - P.q0) * P.nseg + sg) * KC;
+        const int64_t o = (((qrow - P.q0) * P.nseg + sg) * NUM_EPI_GROUPS + grp) * KC;
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
-          P.cand_idx[o + i] = si[i * TM];
-          P.cand_score[o + i] = sv[i * TM];
+          P.cand_idx[o + i] = lds_u32(sv + IDX_PLANE + i * SLOT_STRIDE);
+          P.cand_score[o + i] = lds_f32(sv + i * SLOT_STRIDE);
         }
       }
     }
@@ -433,6 +474,8 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dp, in
 }  // namespace
 
 int aps_k_knn_tc_supported(int Dp) { return Dp == 64 || Dp == 128; }
+int aps_k_knn_tc_lists() { return NUM_EPI_GROUPS; }
+static_assert(NUM_EPI_GROUPS == NUM_ACC_STAGES, "epilogue group g drains accumulator stage g");
 
 int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEvent_t ev0, cudaEvent_t ev1) {
   if (!aps_k_knn_tc_supported(p.Dp)) {
@@ -462,7 +505,7 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.dump = p.dump;
   // every (row, segment) slot is written by exactly one work unit (empty segments write empty slots)
   const size_t smem = 1024 + (size_t)NUM_A_STAGES * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
-                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)2 * KC * TM * 4 + sizeof(Barriers);
+                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)2 * NUM_EPI_GROUPS * KC * TM * 4 + sizeof(Barriers);
   const int64_t units = (int64_t)P.row_blocks * P.nseg;
   const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);
   if (ev0) APS_CUDA(cudaEventRecord(ev0, s));

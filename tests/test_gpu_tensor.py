@@ -15,6 +15,23 @@ def bf16_round(x):
     return r.astype(np.uint32).view(np.float32)
 
 
+def check_candidates(scores, cidx, csc, lo, hi):
+    """The two lists of a segment cover disjoint tile subsets: their union must contain the segment's
+    8 best columns (as the kernel's own epilogue values rank them) and carry the kernel's scores."""
+    seg = scores[:, lo:hi]
+    k8 = min(8, hi - lo)
+    best = np.argsort(-seg, axis=1, kind="stable")[:, :k8] + lo
+    for r in range(scores.shape[0]):
+        valid = cidx[r] != 0xFFFFFFFF
+        cand = cidx[r][valid].astype(np.int64)
+        assert len(set(cand.tolist())) == len(cand) and ((cand >= lo) & (cand < hi)).all(), r
+        kth = seg[r, best[r, -1] - lo]
+        need = set(np.flatnonzero(seg[r] > kth) + lo)      # strictly better than the 8th: must be present
+        assert need <= set(cand.tolist()), r
+        assert len(cand) >= k8, r
+        assert np.array_equal(csc[r][valid], scores[r, cand]), r
+
+
 def tc_scores(aps, Q, T, nseg=1, want_scores=True):
     ctx = aps._lib.default_context()
     L = aps._lib.lib()
@@ -22,8 +39,8 @@ def tc_scores(aps, Q, T, nseg=1, want_scores=True):
     T = np.ascontiguousarray(T, np.float32)
     nq, nt = Q.shape[0], T.shape[0]
     scores = np.zeros((nq, nt), np.float32) if want_scores else None
-    cidx = np.zeros((nq, nseg, 8), np.uint32)
-    csc = np.zeros((nq, nseg, 8), np.float32)
+    cidx = np.zeros((nq, nseg, 16), np.uint32)   # two lists of 8 per segment (one per epilogue warp group)
+    csc = np.zeros((nq, nseg, 16), np.float32)
     aps._lib.check(L.aps_debug_tc_scores(ctx.handle, Q.ctypes.data, nq, T.ctypes.data, nt, Q.shape[1], nseg,
                                          scores.ctypes.data if want_scores else None, cidx.ctypes.data, csc.ctypes.data))
     return scores, cidx, csc
@@ -42,11 +59,7 @@ def test_tc_raw_scores_match_bf16_matmul(aps, nq, nt, D):
     exp = Qb @ Tb.T - 0.5 * sq.astype(np.float64)[None, :]
     err = np.abs(got - exp).max()
     assert err < 2e-3, err          # fp32 accumulation of 128 products of magnitude ~1
-    # candidates = the 8 largest scores of each row, as the kernel's own epilogue values rank them
-    order = np.argsort(-got, axis=1, kind="stable")[:, :8]
-    k8 = min(8, nt)
-    assert np.array_equal(np.sort(cidx[:, 0, :k8], axis=1), np.sort(order[:, :k8].astype(np.uint32), axis=1))
-    assert np.allclose(np.sort(csc[:, 0, :k8], axis=1), np.sort(np.take_along_axis(got, order[:, :k8], 1), axis=1))
+    check_candidates(got, cidx[:, 0], csc[:, 0], 0, nt)
 
 
 def test_tc_integer_descriptors_are_exact(aps):
@@ -70,9 +83,7 @@ def test_tc_segments_partition_columns(aps, nseg):
     tps = -(-tiles // nseg)
     for s in range(nseg):
         lo, hi = s * tps * 256, min(5000, (s + 1) * tps * 256)
-        seg = got[:, lo:hi]
-        order = np.argsort(-seg, axis=1, kind="stable")[:, :8] + lo
-        assert np.array_equal(np.sort(cidx[:, s, :], axis=1), np.sort(order.astype(np.uint32), axis=1)), s
+        check_candidates(got, cidx[:, s], csc[:, s], lo, hi)
 
 
 @pytest.mark.parametrize("cid,n,kp", [(1, 6, 2048), (5, 6, 1500)])
