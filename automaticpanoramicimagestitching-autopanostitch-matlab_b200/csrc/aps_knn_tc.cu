@@ -40,7 +40,7 @@ constexpr int NUM_A_STAGES = 2;
 constexpr int NUM_ACC_STAGES = 2;
 constexpr int NUM_CS_STAGES = 4;
 constexpr int KC = 8;          // candidates per (row, segment)
-constexpr int NUM_EPI_GROUPS = 2;  // epilogue warp groups; group g owns the tiles with (tile counter & 1) == g
+constexpr int NUM_EPI_GROUPS = 2;  // epilogue warp groups; group g owns columns [g*128, (g+1)*128) of every tile
 constexpr int NUM_EPI_WARPS = 4 * NUM_EPI_GROUPS;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
@@ -176,36 +176,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // by score; addressed by 32-bit shared-window addresses (ld/st.shared, not generic).  Out of line
 // on purpose (code size); returns the new K'-th best score.
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 constexpr uint32_t SLOT_STRIDE = TM * 4;                  // bytes between consecutive slots of one row
-constexpr uint32_t IDX_PLANE = NUM_EPI_GROUPS * KC * TM * 4;  // bytes from the score plane to the index plane
-
-// The list is UNSORTED (aps_rerank.cu orders the candidates exactly anyway): a new candidate
-// overwrites the current minimum, then the new minimum and its slot are found with 8 independent
-// loads and a FMNMX tree -- ~40 instructions, no dependent shared-memory chain.
-struct ThetaPos {
-  float theta;  // smallest retained score == the row's K'-th best
-  int pos;      // its slot
-};
-__device__ __noinline__ ThetaPos topk_replace_min(uint32_t sv, int pos, float v, uint32_t col) {
-  sts_f32(sv + pos * SLOT_STRIDE, v);
-  sts_u32(sv + IDX_PLANE + pos * SLOT_STRIDE, col);
-  float x[KC];
-#pragma unroll
-  for (int i = 0; i < KC; ++i) x[i] = lds_f32(sv + i * SLOT_STRIDE);
-  float m = x[0];
-#pragma unroll
-  for (int i = 1; i < KC; ++i) m = fminf(m, x[i]);
-  int p = KC - 1;
-#pragma unroll
-  for (int i = KC - 2; i >= 0; --i) p = (x[i] == m) ? i : p;
-  ThetaPos r;
-  r.theta = m;
-  r.pos = p;
-  return r;
-}
 
 struct KParams {
   int64_t q0, q1, t0, t1;
@@ -232,8 +211,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   uint8_t* smem_a = smem;                                   // NUM_A_STAGES x a_bytes
   uint8_t* smem_b = smem_a + NUM_A_STAGES * a_bytes;        // NUM_B_STAGES x b_bytes
   float* smem_cs = (float*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x {TN scales, TN biases}
-  float* smem_topv = smem_cs + NUM_CS_STAGES * 2 * TN;                      // [groups][KC][TM] row-private top-K' scores
-  uint32_t* smem_topi = (uint32_t*)(smem_topv + NUM_EPI_GROUPS * KC * TM);  // [groups][KC][TM] and their train rows
+  uint32_t* smem_topi = (uint32_t*)(smem_cs + NUM_CS_STAGES * 2 * TN);  // [groups][KC][TM] train rows of the top-K'
   Barriers* bars = (Barriers*)(smem_topi + NUM_EPI_GROUPS * KC * TM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,8 +222,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   if (threadIdx.x == 0) {
     for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
     for (int i = 0; i < NUM_A_STAGES; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
-    for (int i = 0; i < NUM_ACC_STAGES; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
-    for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], 4); }
+    for (int i = 0; i < NUM_ACC_STAGES; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (2 accumulator stages x 256); one CTA per SM
@@ -321,52 +299,56 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     }
   } else {
     // ===================================== epilogue =========================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int grp = (warp - 2) >> 2;  // this warp's epilogue group
+    // Group g (4 warps, one per TMEM lane quadrant) owns columns [g*128, g*128+128) of EVERY tile, so
+    // both groups drain accumulator stage s while the tensor pipe fills stage s^1.
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;  // column half of the tile this warp scans
     const int row_in_tile = quad * 32 + lane;
-    const uint32_t sv = smem_u32(smem_topv + (grp * KC) * TM + row_in_tile);
-    uint32_t tcount = 0;  // tiles issued by this CTA so far (same sequence in the MMA warp)
+    const uint32_t si = smem_u32(smem_topi + (grp * KC) * TM + row_in_tile);  // this row's index slots
+    constexpr int CG = TN / NUM_EPI_GROUPS;                                   // columns per group per tile
+    uint32_t tcount = 0;  // tiles consumed so far (same sequence as the MMA warp's)
     for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int sg = (int)(u / P.row_blocks), rb = (int)(u % P.row_blocks);
       const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
       const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
       const int64_t qrow = P.q0 + (int64_t)rb * TM + row_in_tile;
+      // row-private top-KC (unsorted; aps_rerank.cu orders exactly): scores in registers, train rows in smem
+      float bv[KC];
 #pragma unroll
       for (int i = 0; i < KC; ++i) {
-        sts_f32(sv + i * SLOT_STRIDE, -CUDART_INF_F);
-        sts_u32(sv + IDX_PLANE + i * SLOT_STRIDE, 0xffffffffu);
+        bv[i] = -CUDART_INF_F;
+        sts_u32(si + i * SLOT_STRIDE, 0xffffffffu);
       }
-      float theta = -CUDART_INF_F;  // the row's current K'-th best score (within this group's tiles)
+      float theta = -CUDART_INF_F;  // min of bv == the row's K'-th best score so far
       int minpos = 0;               // slot holding it
       for (int64_t t = tl; t < th; ++t, ++tcount) {
-        if ((int)(tcount & 1) != grp) continue;
         const uint32_t acs = tcount & 1, acph = (tcount >> 1) & 1, cs = tcount & 3, cph = (tcount >> 2) & 1;
         mbar_wait(&bars->acc_full[acs], acph);
         mbar_wait(&bars->cs_full[cs], cph);
         tc_fence_after();
-        const float* cscale = smem_cs + cs * 2 * TN;
-        const int64_t col0 = t * TN;
-        const bool partial = (col0 < P.t0) || (col0 + TN > P.t1);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * TN;
+        const uint32_t cscale = smem_u32(smem_cs + cs * 2 * TN + grp * CG);
+        const int64_t col0 = t * TN + grp * CG;
+        const bool partial = (col0 < P.t0) || (col0 + CG > P.t1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * TN + grp * CG;
         float va[32], vb[32];
         tmem_ld32(taddr, va);
         tmem_wait_ld(va);
 #pragma unroll 1
-        for (int c2 = 0; c2 < TN / 64; ++c2) {
+        for (int c2 = 0; c2 < CG / 64; ++c2) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = 2 * c2 + h;
             float(&cur)[32] = h ? vb : va;
             float(&nxt)[32] = h ? va : vb;
-            if (c + 1 < TN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
+            if (c + 1 < CG / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
             float gm[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const float4 s0 = *reinterpret_cast<const float4*>(cscale + c * 32 + 8 * g);
-              const float4 s1 = *reinterpret_cast<const float4*>(cscale + c * 32 + 8 * g + 4);
+              const float4 s0 = lds_f32x4(cscale + (c * 32 + 8 * g) * 4);
+              const float4 s1 = lds_f32x4(cscale + (c * 32 + 8 * g + 4) * 4);
               if (BIAS) {
-                const float4 b0 = *reinterpret_cast<const float4*>(cscale + TN + c * 32 + 8 * g);
-                const float4 b1 = *reinterpret_cast<const float4*>(cscale + TN + c * 32 + 8 * g + 4);
+                const float4 b0 = lds_f32x4(cscale + (TN + c * 32 + 8 * g) * 4);
+                const float4 b1 = lds_f32x4(cscale + (TN + c * 32 + 8 * g + 4) * 4);
                 cur[8 * g + 0] = fmaf(cur[8 * g + 0], s0.x, b0.x); cur[8 * g + 1] = fmaf(cur[8 * g + 1], s0.y, b0.y);
                 cur[8 * g + 2] = fmaf(cur[8 * g + 2], s0.z, b0.z); cur[8 * g + 3] = fmaf(cur[8 * g + 3], s0.w, b0.w);
                 cur[8 * g + 4] = fmaf(cur[8 * g + 4], s1.x, b1.x); cur[8 * g + 5] = fmaf(cur[8 * g + 5], s1.y, b1.y);
@@ -395,18 +377,31 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
             if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) > theta) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                if (gm[g] > theta) {
+                // branch-free replace-min of the group's maximum; loops only if the same 8 columns hold
+                // a second candidate
+                while (gm[g] > theta) {
+                  int js = 7;
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (cur[8 * g + j] > theta) {
-                      const ThetaPos tp = topk_replace_min(sv, minpos, cur[8 * g + j], (uint32_t)(col0 + c * 32 + 8 * g + j));
-                      theta = tp.theta;
-                      minpos = tp.pos;
-                    }
+                  for (int j = 6; j >= 0; --j) js = (cur[8 * g + j] == gm[g]) ? j : js;
+                  sts_u32(si + minpos * SLOT_STRIDE, (uint32_t)(col0 + c * 32 + 8 * g + js));
+#pragma unroll
+                  for (int i = 0; i < KC; ++i) bv[i] = (i == minpos) ? gm[g] : bv[i];
+                  float m01 = fminf(fminf(bv[0], bv[1]), bv[2]);
+                  float m23 = fminf(fminf(bv[3], bv[4]), bv[5]);
+                  theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
+                  minpos = 7;
+#pragma unroll
+                  for (int i = 6; i >= 0; --i) minpos = (bv[i] == theta) ? i : minpos;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) cur[8 * g + j] = (j == js) ? -CUDART_INF_F : cur[8 * g + j];
+                  float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
+                  m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
+                  m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
+                  gm[g] = fmaxf(m, cur[8 * g + 7]);
                 }
               }
             }
-            if (c + 1 < TN / 32) tmem_wait_ld(nxt);
+            if (c + 1 < CG / 32) tmem_wait_ld(nxt);
           }
         }
         tc_fence_before();
@@ -420,8 +415,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         const int64_t o = (((qrow - P.q0) * P.nseg + sg) * NUM_EPI_GROUPS + grp) * KC;
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
-          P.cand_idx[o + i] = lds_u32(sv + IDX_PLANE + i * SLOT_STRIDE);
-          P.cand_score[o + i] = lds_f32(sv + i * SLOT_STRIDE);
+          P.cand_idx[o + i] = lds_u32(si + i * SLOT_STRIDE);
+          P.cand_score[o + i] = bv[i];
         }
       }
     }
@@ -475,7 +470,7 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dp, in
 
 int aps_k_knn_tc_supported(int Dp) { return Dp == 64 || Dp == 128; }
 int aps_k_knn_tc_lists() { return NUM_EPI_GROUPS; }
-static_assert(NUM_EPI_GROUPS == NUM_ACC_STAGES, "epilogue group g drains accumulator stage g");
+
 
 int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEvent_t ev0, cudaEvent_t ev1) {
   if (!aps_k_knn_tc_supported(p.Dp)) {
@@ -505,7 +500,7 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.dump = p.dump;
   // every (row, segment) slot is written by exactly one work unit (empty segments write empty slots)
   const size_t smem = 1024 + (size_t)NUM_A_STAGES * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
-                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)2 * NUM_EPI_GROUPS * KC * TM * 4 + sizeof(Barriers);
+                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)NUM_EPI_GROUPS * KC * TM * 4 + sizeof(Barriers);
   const int64_t units = (int64_t)P.row_blocks * P.nseg;
   const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);
   if (ev0) APS_CUDA(cudaEventRecord(ev0, s));
