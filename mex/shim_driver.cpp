@@ -1,0 +1,90 @@
+// shim_driver.cpp -- exercises one gateway (compiled together with it) under the mex shim.
+// Without a GPU only the argument validation is checked (it happens before any CUDA call and must
+// raise the reference's identifiers); with a GPU (argv[1] == "gpu") a small real call runs too.
+#include <cstdio>
+#include <cstring>
+
+#include "mex.h"
+
+static int expect_error(const char* want, int nlhs, int nrhs, const mxArray** in) {
+  mxArray* out[4] = {nullptr, nullptr, nullptr, nullptr};
+  try {
+    mexFunction(nlhs, out, nrhs, in);
+  } catch (const mexShimError& e) {
+    if (e.id == want) return 0;
+    std::printf("FAIL: expected %s, got %s (%s)\n", want, e.id.c_str(), e.what());
+    return 1;
+  }
+  std::printf("FAIL: expected %s, no error raised\n", want);
+  return 1;
+}
+
+int main(int argc, char** argv) {
+  const bool gpu = argc > 1 && !std::strcmp(argv[1], "gpu");
+  int bad = 0;
+#if defined(GATE_FLANN)
+  mxArray* T = mxCreateNumericMatrix(8, 4, mxSINGLE_CLASS, mxREAL);
+  mxArray* Td = mxCreateDoubleMatrix(8, 4, mxREAL);
+  mxArray* Q5 = mxCreateNumericMatrix(3, 5, mxSINGLE_CLASS, mxREAL);
+  mxArray *k0 = mxCreateDoubleScalar(0), *k2 = mxCreateDoubleScalar(2), *bf = mxCreateString("bf");
+  { const mxArray* in[] = {T}; bad += expect_error("flann_knn:args", 2, 1, in); }
+  { const mxArray* in[] = {Td, k2}; bad += expect_error("flann_knn:type", 2, 2, in); }
+  { const mxArray* in[] = {T, k0}; bad += expect_error("flann_knn:k", 2, 2, in); }
+  { const mxArray* in[] = {T, Q5, k2}; bad += expect_error("flann_knn:dim", 2, 3, in); }
+  if (gpu) {
+    { const mxArray* in[] = {T, k2, bf}; bad += expect_error("flann_knn:bf", 2, 3, in); }
+    float* t = (float*)mxGetData(T);
+    for (int i = 0; i < 32; ++i) t[i] = (float)((i * 7) % 11);
+    mxArray* out[2] = {nullptr, nullptr};
+    const mxArray* in[] = {T, k2};
+    mexFunction(2, out, 2, in);
+    const uint32_t* idx = (const uint32_t*)mxGetData(out[0]);
+    for (int r = 0; r < 8; ++r) bad += idx[r] != (uint32_t)(r + 1);  // nearest neighbour of a row is itself
+  } else {
+    const mxArray* in[] = {T, k2};
+    bad += expect_error("apsmatch:nogpu", 2, 2, in);  // no CPU fallback
+  }
+#elif defined(GATE_HAMMING)
+  mxArray* A = mxCreateNumericMatrix(4, 32, mxUINT8_CLASS, mxREAL);
+  mxArray* B = mxCreateNumericMatrix(5, 16, mxUINT8_CLASS, mxREAL);
+  mxArray* S = mxCreateNumericMatrix(4, 32, mxSINGLE_CLASS, mxREAL);
+  { const mxArray* in[] = {A}; bad += expect_error("hamm2nn:nrhs", 3, 1, in); }
+  { const mxArray* in[] = {A, S}; bad += expect_error("hamm2nn:type", 3, 2, in); }
+  { const mxArray* in[] = {A, B}; bad += expect_error("hamm2nn:cols", 3, 2, in); }
+  if (gpu) {
+    mxArray* out[3] = {nullptr, nullptr, nullptr};
+    const mxArray* in[] = {A, A};
+    mexFunction(3, out, 2, in);
+    bad += ((const float*)mxGetData(out[1]))[0] != 0.0f;
+  }
+#elif defined(GATE_BATCHED)
+  mxArray* cells = mxCreateCellMatrix(1, 2);
+  mxArray* n2 = mxCreateDoubleScalar(2);
+  { const mxArray* in[] = {n2, cells, n2}; bad += expect_error("apsmatch:args", 1, 3, in); }
+  {  // all-empty descriptors: cell(numImg) without touching the GPU
+    mxArray* out[1] = {nullptr};
+    mxArray* mode = mxCreateString("global");
+    mxArray *k = mxCreateDoubleScalar(4), *r = mxCreateDoubleScalar(0.6);
+    const mxArray* in[] = {mode, cells, n2, k, r};
+    mexFunction(1, out, 5, in);
+    bad += !(mxIsCell(out[0]) && mxGetM(out[0]) == 2 && mxGetN(out[0]) == 2 && mxGetCell(out[0], 2) == nullptr);
+  }
+  if (gpu) {
+    mxArray* a = mxCreateNumericMatrix(6, 8, mxSINGLE_CLASS, mxREAL);
+    mxArray* b = mxCreateNumericMatrix(6, 8, mxSINGLE_CLASS, mxREAL);
+    float *pa = (float*)mxGetData(a), *pb = (float*)mxGetData(b);
+    for (int i = 0; i < 48; ++i) { pa[i] = (float)((i * 13) % 17) - 8.f; pb[i] = pa[i] + ((i % 6) < 3 ? 0.001f : (float)((i * 5) % 7)); }
+    mxSetCell(cells, 0, a);
+    mxSetCell(cells, 1, b);
+    mxArray* out[1] = {nullptr};
+    mxArray* mode = mxCreateString("global");
+    mxArray *k = mxCreateDoubleScalar(4), *r = mxCreateDoubleScalar(0.5);
+    const mxArray* in[] = {mode, cells, n2, k, r};
+    mexFunction(1, out, 5, in);
+    const mxArray* c01 = mxGetCell(out[0], 2);  // cell (1,2) -> linear index 0 + 1*2
+    bad += !(c01 && mxIsDouble(c01) && mxGetN(c01) == 2 && mxGetM(c01) >= 3);
+  }
+#endif
+  std::printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
+  return bad ? 1 : 0;
+}

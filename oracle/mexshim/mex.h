@@ -2,7 +2,7 @@
  * mex.h -- minimal stand-in for MATLAB's MEX C API (TEST INFRASTRUCTURE ONLY).
  *
  * MATLAB is not installed in this image, so (a) the reference's own MEX sources under
- * /root/reference/Procedural Program/mex/*.cpp and (b) this repo's gateways in mex/ are
+ * /root/reference/Procedural Program/mex (its .cpp files) and (b) this repo's gateways in mex/ are
  * compiled against this header instead of MathWorks' <mex.h>.  It implements just enough of the
  * published API (column-major mxArray with class id, dims, data; cells; structs; char rows) for
  * those files to compile AND run under a plain C++ driver.  Written from the public MEX API
