@@ -20,4 +20,4 @@ from .host import (  # noqa: F401
     nearest2SSDExhaustive,
     selectImagePartners,
 )
-from . import synth  # noqa: F401
+from . import multigpu, synth  # noqa: F401

@@ -1,0 +1,56 @@
+"""Multi-GPU host logic of the global path: one process per GPU, torch.distributed for the plumbing.
+
+The reference's only parallelism is MATLAB `parfor` over independent work items with the descriptor cell
+broadcast to the workers (PP/featureMatching/featureMatchingPairwise.m:54-59, PP/main.m:39-47).  Here:
+  * every rank holds ALL descriptors (host upload on rank 0 + NCCL broadcast over NVLink, or its own
+    upload), so a query row's k nearest neighbours are complete on the rank that owns the row and no
+    cross-GPU top-k merge exists;
+  * query rows are sharded in contiguous blocks of 128-row tiles (`shard_bounds`);
+  * the only exchange on the data path is the per-query match records (8 bytes per query row:
+    int32 target image + uint32 partner index), each rank broadcasting its slice (`exchange_records`);
+  * compaction into the cell order is deterministic, so the lists are identical for every world size.
+Pure index arithmetic + collectives: testable on CPU with the gloo backend (tests/test_multigpu_cpu.py).
+"""
+from __future__ import annotations
+
+TILE_ROWS = 128
+
+
+def shard_bounds(F: int, world: int):
+    """[(q0, q1)] per rank: contiguous, disjoint, covering [0, F), aligned to 128-row tiles."""
+    blocks = (F + TILE_ROWS - 1) // TILE_ROWS
+    out = []
+    for r in range(world):
+        b0, b1 = r * blocks // world, (r + 1) * blocks // world
+        out.append((min(F, b0 * TILE_ROWS), min(F, b1 * TILE_ROWS)))
+    return out
+
+
+def exchange_records(rec, F: int, bounds, dist, group=None):
+    """rec: 1-D int32 tensor of 2*F entries (target[F] then partner[F], the layout of
+    aps_gplan_records_device).  After the call every rank holds every rank's slice."""
+    for r, (a, b) in enumerate(bounds):
+        if b > a:
+            dist.broadcast(rec[a:b], src=r, group=group)
+            dist.broadcast(rec[F + a:F + b], src=r, group=group)
+    return rec
+
+
+class CudaView:
+    """Exposes a raw device pointer to torch via __cuda_array_interface__ (zero-copy, for collectives)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def global_matching_step(plan, ratio, rank, world, dist=None, rec=None):
+    """One sharded pass of the global pipeline on an uploaded/broadcast plan (all ranks call it)."""
+    bounds = shard_bounds(plan.F, world)
+    q0, q1 = bounds[rank]
+    plan.prepare()
+    plan.knn(q0, q1)
+    plan.filter(ratio, q0, q1)
+    if world > 1:
+        exchange_records(rec, plan.F, bounds, dist)
+    plan.compact()

@@ -93,14 +93,6 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-class CudaView:
-    """Exposes a raw device pointer to torch via __cuda_array_interface__ (for NCCL collectives)."""
-
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 3, "strides": None}
-
-
 def cpu_reference_rate(desc, target_seconds, threads_note=True):
     """Times the oracle's exact float kNN (+ filter) on a bounded query sample against the full train set."""
     from oracle import oracle
@@ -195,29 +187,16 @@ def run_ours(args, rank, world, local_rank):
     plan = pkg.GlobalPlan(ctx, counts, D, False, KNN)
     plan.upload_pointers(host_ptrs)
 
-    # query-row shard of this rank (multiples of 128 rows)
-    blocks = (F + 127) // 128
-    b0, b1 = rank * blocks // world, (rank + 1) * blocks // world
-    q0, q1 = min(F, b0 * 128), min(F, b1 * 128)
-    bounds = [(min(F, (r * blocks // world) * 128), min(F, ((r + 1) * blocks // world) * 128)) for r in range(world)]
+    # query-row shard of this rank (contiguous blocks of 128-row tiles)
+    mg = pkg.multigpu
+    q0, q1 = mg.shard_bounds(F, world)[rank]
+    rec = desc_dev = None
     if world > 1:
-        rec = torch.as_tensor(CudaView(plan.records_device(), (2 * F,), "<i4"), device="cuda")
-        desc_dev = torch.as_tensor(CudaView(plan.desc_device(), (F * D,), "<f4"), device="cuda")
-
-    def exchange_records():
-        if world == 1:
-            return
-        for r, (a, b) in enumerate(bounds):       # target[F] then partner[F]; ranks own disjoint row slices
-            if b > a:
-                dist.broadcast(rec[a:b], src=r)
-                dist.broadcast(rec[F + a:F + b], src=r)
+        rec = torch.as_tensor(mg.CudaView(plan.records_device(), (2 * F,), "<i4"), device="cuda")
+        desc_dev = torch.as_tensor(mg.CudaView(plan.desc_device(), (F * D,), "<f4"), device="cuda")
 
     def step_device():
-        plan.prepare()
-        plan.knn(q0, q1)
-        plan.filter(RATIO, q0, q1)
-        exchange_records()
-        plan.compact()
+        mg.global_matching_step(plan, RATIO, rank, world, dist, rec)
 
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
