@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -270,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
         achieved = flops_per_launch / (tc_avg_ms / 1e3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and world == 1:   # captured by ncu --set full on exactly this workload (profiles/)
             traffic = json.load(open(tp)).get("k_knn_tc_dram_bytes_per_launch")
         peak = peaks["sustained"]
         line = {
