@@ -1134,10 +1134,11 @@ extern "C" int aps_select_partners(aps_ctx* c, const int64_t* counts, int n, int
 
 // ------------------------------------------------------------------------------------------------
 // diagnostics: run the tcgen05 candidate kernel alone and return what its epilogue saw
+extern "C" int aps_debug_tc_lists(void) { return aps_k_knn_tc_lists(); }
 extern "C" int aps_debug_tc_scores(aps_ctx* c, const float* Q, int64_t nq, const float* T, int64_t nt, int D,
                                    int nseg, float* scores, uint32_t* cand_idx, float* cand_score) {
   APS_CTX(c);
-  if (!Q || !T || nq <= 0 || nt <= 0 || D <= 0 || nseg < 1 || nseg > 4) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  if (!Q || !T || nq <= 0 || nt <= 0 || D <= 0 || nseg < 1 || nseg > 8) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
   const int lists = aps_k_knn_tc_lists();
   const int Dp = (D + 63) / 64 * 64;
   if (!aps_k_knn_tc_supported(Dp)) APS_FAIL(APS_ERR_DIM, "", "unsupported descriptor length %d", D);

@@ -23,6 +23,12 @@
 // Pipelines (all mbarrier based): B smem ring (2 x 64 KB) TMA<->MMA, A double buffer, TMEM
 // accumulator double buffer (2 x 256 columns = all 512) MMA<->epilogue, (scale,bias) ring.
 //
+// Measured alternatives (round 1, C2, same box): 4 epilogue groups x 64 columns, single-buffered TMEM
+// loads: 8.31 ms (more lists -> more insertions, ALU pipe 58 % busy); N=128 tiles with 4 TMEM stages and
+// 4 groups x 32 columns: 11.06 ms (per-tile barrier overhead per chunk doubles).  Kept: 2 groups x 128
+// columns, N=256, double-buffered tcgen05.ld: 8.23 ms.  The kernel is epilogue-issue bound (~138 warp
+// instructions per 32-column chunk, half of them the replace-min path), not MMA/L2 bound.
+//
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2*D per (query, train) pair.  HBM traffic is
 // negligible (operands stream from L2: every concurrently running CTA walks the same B tiles).
 #include <cuda.h>

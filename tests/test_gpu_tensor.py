@@ -39,8 +39,9 @@ def tc_scores(aps, Q, T, nseg=1, want_scores=True):
     T = np.ascontiguousarray(T, np.float32)
     nq, nt = Q.shape[0], T.shape[0]
     scores = np.zeros((nq, nt), np.float32) if want_scores else None
-    cidx = np.zeros((nq, nseg, 16), np.uint32)   # two lists of 8 per segment (one per epilogue warp group)
-    csc = np.zeros((nq, nseg, 16), np.float32)
+    slots = 8 * L.aps_debug_tc_lists()           # L lists of 8 per segment (one per epilogue warp group)
+    cidx = np.zeros((nq, nseg, slots), np.uint32)
+    csc = np.zeros((nq, nseg, slots), np.float32)
     aps._lib.check(L.aps_debug_tc_scores(ctx.handle, Q.ctypes.data, nq, T.ctypes.data, nt, Q.shape[1], nseg,
                                          scores.ctypes.data if want_scores else None, cidx.ctypes.data, csc.ctypes.data))
     return scores, cidx, csc
