@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(TJ) k_knn_exact(const float* __restrict__ Q, c
                                                    const int32_t* __restrict__ nrows_dev, int64_t q0, int64_t nq,
                                                    const float* __restrict__ T, const float* __restrict__ sqT,
                                                    int64_t t0, int64_t t1, int D, int k, int64_t out_row0,
-                                                   uint32_t* __restrict__ idx, float* __restrict__ dist) {
+                                                   uint32_t* __restrict__ idx, float* __restrict__ dist,
+                                                   int nsplit, int64_t split_cap, uint32_t* __restrict__ pidx,
+                                                   float* __restrict__ pdist) {
   extern __shared__ __align__(16) float smem[];
   const int Dpad = (D + DC - 1) / DC * DC;
   float* qs = smem;                       // [RQ][Dpad]
@@ -44,8 +46,15 @@ __global__ void __launch_bounds__(TJ) k_knn_exact(const float* __restrict__ Q, c
   const int64_t total = rows ? (int64_t)(*nrows_dev) : nq;
   const int64_t ngroups = (total + RQ - 1) / RQ;
   const int nfull = D / 4;  // full groups of four (FLANN functor), then a scalar tail
+  // few rows (the fallback list): split the train range over `ns` CTAs per row group, merge afterwards
+  const int ns = (nsplit > 1 && total <= split_cap) ? nsplit : 1;
+  const int64_t tiles_all = (t1 - t0 + TJ - 1) / TJ, tiles_per = (tiles_all + ns - 1) / ns;
 
-  for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  for (int64_t work = blockIdx.x; work < ngroups * ns; work += gridDim.x) {
+    const int64_t grp = work / ns;
+    const int sp = (int)(work - grp * ns);
+    const int64_t ts0 = t0 + (int64_t)sp * tiles_per * TJ;
+    const int64_t ts1 = min(t1, ts0 + tiles_per * TJ);
     __syncthreads();
     if (tid < RQ) {
       int64_t i = grp * RQ + tid;
@@ -65,7 +74,7 @@ __global__ void __launch_bounds__(TJ) k_knn_exact(const float* __restrict__ Q, c
 #pragma unroll
     for (int r = 0; r < RQ; ++r) a2[r] = (METRIC == 1 && s_row[r] >= 0) ? sqQ[s_row[r]] : 0.f;
 
-    for (int64_t j0 = t0; j0 < t1; j0 += TJ) {
+    for (int64_t j0 = ts0; j0 < ts1; j0 += TJ) {
       float acc[RQ];
 #pragma unroll
       for (int r = 0; r < RQ; ++r) acc[r] = 0.f;
@@ -171,10 +180,50 @@ __global__ void __launch_bounds__(TJ) k_knn_exact(const float* __restrict__ Q, c
     }
     __syncthreads();
     if (lane < k && s_row[warp] >= 0) {
-      int64_t o = (s_row[warp] - out_row0) * k + lane;
-      idx[o] = topi[warp * APS_MAX_K + lane];
-      dist[o] = topd[warp * APS_MAX_K + lane];
+      if (ns == 1) {
+        int64_t o = (s_row[warp] - out_row0) * k + lane;
+        idx[o] = topi[warp * APS_MAX_K + lane];
+        dist[o] = topd[warp * APS_MAX_K + lane];
+      } else {
+        int64_t o = ((grp * RQ + warp) * ns + sp) * k + lane;
+        pidx[o] = topi[warp * APS_MAX_K + lane];
+        pdist[o] = topd[warp * APS_MAX_K + lane];
+      }
     }
+  }
+}
+
+// merges the `ns` partial ascending lists of every row (ties -> lower index), one thread per row
+__global__ void k_knn_exact_merge(const int32_t* __restrict__ rows, const int32_t* __restrict__ nrows_dev, int64_t q0,
+                                  int64_t nq, int k, int nsplit, int64_t split_cap, const uint32_t* __restrict__ pidx,
+                                  const float* __restrict__ pdist, int64_t out_row0, uint32_t* __restrict__ idx,
+                                  float* __restrict__ dist) {
+  const int64_t total = rows ? (int64_t)(*nrows_dev) : nq;
+  if (!(nsplit > 1 && total <= split_cap)) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t row = rows ? (int64_t)rows[i] : q0 + i;
+  int head[64];
+  for (int s = 0; s < nsplit; ++s) head[s] = 0;
+  for (int c = 0; c < k; ++c) {
+    float bd = CUDART_INF_F;
+    uint32_t bi = 0;
+    int bs = -1;
+    for (int s = 0; s < nsplit; ++s) {
+      if (head[s] >= k) continue;
+      const int64_t o = (i * nsplit + s) * k + head[s];
+      const uint32_t ci = pidx[o];
+      if (ci == 0u) continue;
+      const float cd = pdist[o];
+      if (bs < 0 || cd < bd || (cd == bd && ci < bi)) {
+        bd = cd;
+        bi = ci;
+        bs = s;
+      }
+    }
+    if (bs >= 0) head[bs]++;
+    idx[(row - out_row0) * k + c] = bi;
+    dist[(row - out_row0) * k + c] = bs >= 0 ? bd : CUDART_INF_F;
   }
 }
 
@@ -191,14 +240,35 @@ int aps_k_knn_exact(cudaStream_t s, const float* Q, const float* sqQ, const int3
     return APS_ERR_DIM;
   }
   int64_t groups = aps_ceil_div(nq, RQ);
-  unsigned grid = (unsigned)(groups < 148 * 4 ? groups : 148 * 4);
+  // a row LIST (device-side count, usually tiny): let up to 32 CTAs share each row group's train range
+  const int64_t split_cap = 2048;
+  int nsplit = 1;
+  if (rows) {
+    const int64_t tiles = aps_ceil_div(t1 - t0, TJ);
+    nsplit = (int)(tiles < 32 ? (tiles < 1 ? 1 : tiles) : 32);
+  }
+  DevBuf<uint32_t> pidx;
+  DevBuf<float> pdist;
+  if (nsplit > 1) {
+    const int64_t prow = aps_min64(nq, split_cap) + RQ;
+    APS_TRY(pidx.alloc((size_t)prow * nsplit * k, s));
+    APS_TRY(pdist.alloc((size_t)prow * nsplit * k, s));
+  }
+  unsigned grid = (unsigned)(groups * nsplit < 148 * 4 ? groups * nsplit : 148 * 4);
   if (metric == 0) {
     APS_CUDA(cudaFuncSetAttribute(k_knn_exact<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_exact<0><<<grid, TJ, smem, s>>>(Q, sqQ, rows, nrows_dev, q0, nq, T, sqT, t0, t1, D, k, out_row0, idx, dist);
+    k_knn_exact<0><<<grid, TJ, smem, s>>>(Q, sqQ, rows, nrows_dev, q0, nq, T, sqT, t0, t1, D, k, out_row0, idx, dist,
+                                          nsplit, split_cap, pidx.p, pdist.p);
   } else {
     APS_CUDA(cudaFuncSetAttribute(k_knn_exact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_exact<1><<<grid, TJ, smem, s>>>(Q, sqQ, rows, nrows_dev, q0, nq, T, sqT, t0, t1, D, k, out_row0, idx, dist);
+    k_knn_exact<1><<<grid, TJ, smem, s>>>(Q, sqQ, rows, nrows_dev, q0, nq, T, sqT, t0, t1, D, k, out_row0, idx, dist,
+                                          nsplit, split_cap, pidx.p, pdist.p);
   }
   APS_LAUNCHED();
+  if (nsplit > 1) {
+    k_knn_exact_merge<<<(unsigned)aps_ceil_div(aps_min64(nq, split_cap), 128), 128, 0, s>>>(
+        rows, nrows_dev, q0, nq, k, nsplit, split_cap, pidx.p, pdist.p, out_row0, idx, dist);
+    APS_LAUNCHED();
+  }
   return APS_OK;
 }

@@ -131,3 +131,24 @@ def test_tensor_engine_pairwise_and_knn_entry(aps, orc):
     assert np.array_equal(m, om) and np.array_equal(met, omet) and len(m) > 100
     oi, od = orc.knn_l2(X, X[:1000], 4)
     assert np.array_equal(idx, oi) and np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+
+
+def test_tensor_engine_unprovable_rows_fall_back_to_exact_search(aps, orc):
+    """Rows whose candidate set cannot be proven complete (here: 40 identical descriptors, so the k-th
+    distance ties with the worst retained candidate) are re-searched by the exact kernel."""
+    ctx = aps._lib.default_context()
+    rng = np.random.default_rng(17)
+    X = rng.standard_normal((6000, 128)).astype(np.float32)
+    X[100:140] = X[100]                       # 40 exact duplicates
+    X[3000:3005] = X[100]
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    ctx.set_float_engine(2)
+    try:
+        idx, dist = aps.flann_knn_win(X, X, 4)
+        stats = ctx.last_stats()
+    finally:
+        ctx.set_float_engine(0)
+    oi, od = orc.knn_l2(X, X, 4)
+    assert stats["engine"] == "tcgen05" and stats["fallback_rows"] >= 40
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
