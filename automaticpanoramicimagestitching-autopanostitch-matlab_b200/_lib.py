@@ -103,7 +103,7 @@ def lib():
         "aps_gplan_download_knn": (i32, [vp, i64, i64, vp, vp]),
         "aps_gplan_download": (i32, [vp, pp]),
         "aps_gplan_pair_counts_device": (i32, [vp, pp]),
-        "aps_debug_tc_lists": (i32, []),
+        "aps_debug_tc_slots": (i32, [vp, i64, i64]),
         "aps_debug_tc_scores": (i32, [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -244,17 +244,12 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   c->stats[2] = 2;
   const int Dp = (D + 63) / 64 * 64;
   const int kcand = 8;
-  // column segments: enough (row block, segment) units to balance the persistent grid
-  const int64_t row_blocks = aps_ceil_div(nq, 128);
-  int nseg = 1;
-  const int64_t tiles = aps_ceil_div(t1 - t0, 256);
-  const int lists = aps_k_knn_tc_lists();
-  while (row_blocks * nseg < 4 * (int64_t)c->sm_count && nseg * 2 <= tiles && nseg * 2 * lists * kcand <= 32) nseg *= 2;
+  const int nslot = aps_k_knn_tc_slots(c->sm_count, nq, t0, t1);  // candidate lists per row (tail balancing)
   DevBuf<uint32_t> cidx;
   DevBuf<float> cscore;
   DevBuf<int32_t> fb;
-  APS_TRY(cidx.alloc((size_t)nq * nseg * lists * kcand, c->stream));
-  APS_TRY(cscore.alloc((size_t)nq * nseg * lists * kcand, c->stream));
+  APS_TRY(cidx.alloc((size_t)nq * nslot * kcand, c->stream));
+  APS_TRY(cscore.alloc((size_t)nq * nslot * kcand, c->stream));
   APS_TRY(fb.alloc((size_t)nq + 1, c->stream));
   APS_CUDA(cudaMemsetAsync(fb.p + nq, 0, sizeof(int32_t), c->stream));
   aps_tc_problem p;
@@ -270,7 +265,7 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   p.q1 = q1;
   p.t0 = t0;
   p.t1 = t1;
-  p.nseg = nseg;
+  p.nslot = nslot;
   p.kcand = kcand;
   p.cand_idx = cidx.p;
   p.cand_score = cscore.p;
@@ -285,7 +280,7 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
     c->tc_events.push_back(ev0);
     c->tc_events.push_back(ev1);
   }
-  APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nseg * lists, kcand, cidx.p,
+  APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nslot, kcand, cidx.p,
                        cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq));
   // rows that could not be proven complete: exact search (device-side count, no host round trip)
   APS_TRY(aps_k_knn_exact(c->stream, Q.xn, Q.sq, fb.p, fb.p + nq, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
@@ -1134,12 +1129,15 @@ extern "C" int aps_select_partners(aps_ctx* c, const int64_t* counts, int n, int
 
 // ------------------------------------------------------------------------------------------------
 // diagnostics: run the tcgen05 candidate kernel alone and return what its epilogue saw
-extern "C" int aps_debug_tc_lists(void) { return aps_k_knn_tc_lists(); }
+extern "C" int aps_debug_tc_slots(aps_ctx* c, int64_t nq, int64_t nt) {
+  return c ? aps_k_knn_tc_slots(c->sm_count, nq, 0, nt) : 0;
+}
 extern "C" int aps_debug_tc_scores(aps_ctx* c, const float* Q, int64_t nq, const float* T, int64_t nt, int D,
                                    int nseg, float* scores, uint32_t* cand_idx, float* cand_score) {
   APS_CTX(c);
-  if (!Q || !T || nq <= 0 || nt <= 0 || D <= 0 || nseg < 1 || nseg > 8) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
-  const int lists = aps_k_knn_tc_lists();
+  (void)nseg;
+  if (!Q || !T || nq <= 0 || nt <= 0 || D <= 0) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  const int nslot = aps_k_knn_tc_slots(c->sm_count, nq, 0, nt);
   const int Dp = (D + 63) / 64 * 64;
   if (!aps_k_knn_tc_supported(Dp)) APS_FAIL(APS_ERR_DIM, "", "unsupported descriptor length %d", D);
   FloatSet qs, ts;
@@ -1162,19 +1160,19 @@ extern "C" int aps_debug_tc_scores(aps_ctx* c, const float* Q, int64_t nq, const
   DevBuf<float> dump, cscore;
   DevBuf<uint32_t> cidx;
   if (scores) APS_TRY(dump.alloc((size_t)nq * nt, c->stream));
-  APS_TRY(cidx.alloc((size_t)nq * nseg * lists * 8, c->stream));
-  APS_TRY(cscore.alloc((size_t)nq * nseg * lists * 8, c->stream));
+  APS_TRY(cidx.alloc((size_t)nq * nslot * 8, c->stream));
+  APS_TRY(cscore.alloc((size_t)nq * nslot * 8, c->stream));
   aps_tc_problem p;
   p.Qb = qs.xb.p; p.Tb = ts.xb.p; p.colscale = ts.colscale.p; p.colbias = ts.colbias.p; p.bias = 1;
   p.Fq_total = nq; p.Ft_total = nt; p.Dp = Dp;
   p.q0 = 0; p.q1 = nq; p.t0 = 0; p.t1 = nt;
-  p.nseg = nseg; p.kcand = 8;
+  p.nslot = nslot; p.kcand = 8;
   p.cand_idx = cidx.p; p.cand_score = cscore.p;
   p.dump = scores ? dump.p : nullptr;
   APS_TRY(aps_k_knn_tc(c->stream, c->sm_count, p));
   if (scores) APS_CUDA(cudaMemcpyAsync(scores, dump.p, (size_t)nq * nt * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (cand_idx) APS_CUDA(cudaMemcpyAsync(cand_idx, cidx.p, (size_t)nq * nseg * lists * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (cand_score) APS_CUDA(cudaMemcpyAsync(cand_score, cscore.p, (size_t)nq * nseg * lists * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (cand_idx) APS_CUDA(cudaMemcpyAsync(cand_idx, cidx.p, (size_t)nq * nslot * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (cand_score) APS_CUDA(cudaMemcpyAsync(cand_score, cscore.p, (size_t)nq * nslot * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
   APS_CUDA(cudaStreamSynchronize(c->stream));
   return APS_OK;
 }

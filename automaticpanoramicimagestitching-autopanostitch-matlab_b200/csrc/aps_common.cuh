@@ -128,14 +128,14 @@ struct aps_tc_problem {
   int Dp;
   int64_t q0, q1;  // query rows to search
   int64_t t0, t1;  // train rows searched
-  int nseg;        // column segments per query row block
+  int nslot;       // candidate lists per row: aps_k_knn_tc_slots(...) for this problem
   int kcand;       // candidates kept per (row, segment): 8
-  uint32_t* cand_idx;   // [ (q1-q0) x nseg x lists x kcand ] global train row (0-based) or 0xFFFFFFFF
+  uint32_t* cand_idx;   // [ (q1-q0) x nslot x kcand ] global train row (0-based) or 0xFFFFFFFF
   float* cand_score;    // same shape: score (dot*scale+bias), -inf for empty slots
   float* dump;          // optional [ (q1-q0) x (t1-t0) ] raw scores (tests only), else nullptr
 };
 int aps_k_knn_tc_supported(int Dp);
-int aps_k_knn_tc_lists();  // candidate lists the kernel emits per (row, segment)
+int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1);  // candidate lists per row for this problem
 // ev0/ev1 (optional): recorded immediately before / after the candidate kernel itself
 int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEvent_t ev0 = nullptr,
                  cudaEvent_t ev1 = nullptr);

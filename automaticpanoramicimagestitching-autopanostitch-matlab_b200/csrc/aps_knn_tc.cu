@@ -3,31 +3,36 @@
 // Replaces the O(F^2 D) search behind  PP/mex/flann_knn.cpp:229-234 (global path) and the GEMM +
 // two min passes of  PP/featureMatching/matchFeaturesScratch.m:351-358 (pairwise path) with
 //     score(q, j) = (a_q . b_j) * scale_j + bias_j          (||a-b||^2 = ||a||^2 + ||b||^2 - 2 a.b)
-// evaluated as a dense bf16 contraction: tcgen05.mma (cta_group::1, M=128, N=256, K=16 per
+// evaluated as a dense bf16 contraction: tcgen05.mma (cta_group::1, M=128, N=128, K=16 per
 // instruction) with the accumulator in TMEM, operands staged in shared memory by TMA
 // (SWIZZLE_128B, K-major), and a fused top-K' selection in the epilogue: the distance matrix is
 // never written.  The K' = 8 best train rows per (query row, column segment) go to aps_rerank.cu,
 // which recomputes them exactly in FP32 and proves the top-k complete.
 //
-// CTA = 192 threads, persistent over work units (128-query-row block x column segment):
-//   warp 0   : TMA producer  (A tile once per unit, B tiles + per-column (scale,bias) per step)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
-//   warps 2-5: epilogue, thread == query row (tcgen05.ld 32x32b: lane i of the warp's TMEM
-//              quadrant).  Per 32-column chunk: score = acc*scale (+bias) with the per-column
-//              constants read as broadcast LDS.128, a FMNMX3 tree to four 8-column group maxima,
-//              one compare against the row's current K'-th best (theta, a register).  Only groups
-//              that contain a new candidate take the insertion path; the row's sorted top-K' list
-//              lives in shared memory and is updated by a small out-of-line routine, so the hot
-//              loop stays a few hundred instructions (an earlier fully unrolled register version
-//              was 348 KB of SASS and 69 % instruction-fetch stalled -- profiles/).
-// Pipelines (all mbarrier based): B smem ring (2 x 64 KB) TMA<->MMA, A double buffer, TMEM
-// accumulator double buffer (2 x 256 columns = all 512) MMA<->epilogue, (scale,bias) ring.
+// CTA = 352 threads, persistent over work units.  A unit = TWO 128-row query blocks (256 rows, both A
+// tiles resident in shared memory) x a range of 128-column train tiles; every B tile feeds two MMA
+// groups (one per row block), which halves the operand traffic per output and lets each query row be
+// owned by exactly ONE epilogue thread -- one top-K' list per row, half the insertions of a
+// column-split epilogue.
+//   warp 0   : TMA producer  (two A tiles per unit; per step one B tile + per-column (scale,bias))
+//   warps 1-2: one single-thread tcgen05.mma issuer per row block (warp 1 also owns the TMEM allocation);
+//              independent issuers remove head-of-line blocking between the two epilogue groups
+//   warps 3-6: epilogue group 0 = row block 0, warps 7-10: group 1 = row block 1 (thread == query row,
+//              tcgen05.ld 32x32b from the warp's TMEM lane quadrant).  Per 32-column chunk:
+//              score = acc*scale (+bias) with the constants read as broadcast LDS.128, a FMNMX3 tree to
+//              four 8-column group maxima, one compare with the row's K'-th best (theta, a register).
+//              Only groups that contain a candidate run the branch-free replace-min (scores in
+//              registers, train-row indices in shared memory).
+// TMEM: 4 accumulator slots of 128 columns = slot(tile parity, row block): the tensor pipe fills the
+// slots of tile t+1 while both groups drain tile t.  Pipelines (all mbarrier based): B ring (4 x 32 KB),
+// A pair (single buffered per unit), accumulator slots, (scale,bias) ring.
+// Scheduling: units that fill whole rounds of the grid span all train tiles; the units of the last,
+// partial round are split into up to 4 column segments so that the tail is balanced.
 //
-// Measured alternatives (round 1, C2, same box): 4 epilogue groups x 64 columns, single-buffered TMEM
-// loads: 8.31 ms (more lists -> more insertions, ALU pipe 58 % busy); N=128 tiles with 4 TMEM stages and
-// 4 groups x 32 columns: 11.06 ms (per-tile barrier overhead per chunk doubles).  Kept: 2 groups x 128
-// columns, N=256, double-buffered tcgen05.ld: 8.23 ms.  The kernel is epilogue-issue bound (~138 warp
-// instructions per 32-column chunk, half of them the replace-min path), not MMA/L2 bound.
+// Measured alternatives (round 1, C2, same box): one row block per unit with the epilogue split by
+// columns (two lists per row): 8.23 ms; the same with 4 groups x 64 columns: 8.31 ms; a fully unrolled
+// register-resident sorted top-K: 348 KB of SASS, 69 % instruction-fetch stalls, 109 ms
+// (profiles/r1_ncu_history.txt).  The kernel is epilogue-issue bound, not MMA/L2 bound.
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2*D per (query, train) pair.  HBM traffic is
 // negligible (operands stream from L2: every concurrently running CTA walks the same B tiles).
@@ -38,28 +43,24 @@
 
 namespace {
 
-constexpr int TM = 128;        // query rows per CTA tile (UMMA M)
-constexpr int TN = 256;        // train rows per step (UMMA N)
+constexpr int TM = 128;        // query rows per MMA (UMMA M); a unit holds RB of these row blocks
+constexpr int RB = 2;          // row blocks per unit == epilogue groups
+constexpr int TN = 128;        // train rows per step (UMMA N)
 constexpr int KSLAB = 64;      // bf16 elements per 128-byte swizzle row
-constexpr int NUM_B_STAGES = 2;
-constexpr int NUM_A_STAGES = 2;
-constexpr int NUM_ACC_STAGES = 2;
-constexpr int NUM_CS_STAGES = 4;
+constexpr int NUM_B_STAGES = 4;
+constexpr int NUM_ACC_SLOTS = 2 * RB;  // slot = (tile parity) * RB + row block ; 4 x 128 columns = all of TMEM
+constexpr int NUM_CS_STAGES = 8;
 constexpr int KC = 8;          // candidates per (row, segment)
-constexpr int NUM_EPI_GROUPS = 2;  // epilogue warp groups; group g owns columns [g*128, (g+1)*128) of every tile
-constexpr int NUM_EPI_WARPS = 4 * NUM_EPI_GROUPS;
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-
-struct SmemLayout {
-  // operand buffers first: 1024-byte alignment required by SWIZZLE_128B
-  static constexpr int a_bytes(int dp) { return TM * dp * 2; }
-  static constexpr int b_bytes(int dp) { return TN * dp * 2; }
-};
+constexpr int MAX_SEG = 4;     // column segments of a tail unit == candidate lists a row can have
+constexpr int NUM_EPI_WARPS = 4 * RB;
+constexpr int FIRST_EPI_WARP = 1 + RB;  // warp 0 producer, warps 1..RB MMA issuers (one per row block)
+constexpr int NUM_THREADS = 32 * (FIRST_EPI_WARP + NUM_EPI_WARPS);
+static_assert(NUM_ACC_SLOTS * TN == 512, "TMEM budget");
 
 struct Barriers {
   uint64_t b_full[NUM_B_STAGES], b_empty[NUM_B_STAGES];
-  uint64_t a_full[NUM_A_STAGES], a_empty[NUM_A_STAGES];
-  uint64_t acc_full[NUM_ACC_STAGES], acc_empty[NUM_ACC_STAGES];
+  uint64_t a_full, a_empty;
+  uint64_t acc_full[NUM_ACC_SLOTS], acc_empty[NUM_ACC_SLOTS];
   uint64_t cs_full[NUM_CS_STAGES], cs_empty[NUM_CS_STAGES];
   uint32_t tmem_base;
   uint32_t pad;
@@ -194,18 +195,41 @@ constexpr uint32_t SLOT_STRIDE = TM * 4;                  // bytes between conse
 
 struct KParams {
   int64_t q0, q1, t0, t1;
-  int dp;              // padded descriptor length (64 or 128)
-  int nseg;
-  int row_blocks;      // ceil((q1-q0)/128)
-  int64_t tile_lo;     // first 256-column tile (global tile grid)
-  int64_t tile_hi;     // one past the last tile
-  int tiles_per_seg;
+  int dp;               // padded descriptor length (64 or 128)
+  int nslot;            // candidate lists allocated per row (1..MAX_SEG)
+  int units_full;       // units that span all tiles (list 0 only)
+  int tail_units;       // row-block pairs of the last partial round ...
+  int tail_seg;         // ... each split into this many column segments
+  int64_t tile_lo;      // first TN-column tile (global tile grid)
+  int64_t tile_hi;      // one past the last tile
+  int tiles_per_seg;    // tiles per segment of a tail unit
   const float* colscale;  // [Ft_total + 256] per train row
   const float* colbias;   // [Ft_total + 256] per train row (read only by the BIAS variant)
   uint32_t* cand_idx;
   float* cand_score;
   float* dump;
 };
+
+struct Unit {
+  int64_t rb2;     // index of the 256-row query block pair
+  int64_t tl, th;  // tile range
+  int seg;         // candidate list this unit fills
+  bool full;       // spans all tiles: also clears the row's unused lists
+};
+__device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
+  Unit x;
+  if (u < P.units_full) {
+    x.rb2 = u; x.tl = P.tile_lo; x.th = P.tile_hi; x.seg = 0; x.full = true;
+  } else {
+    const int64_t v = u - P.units_full;
+    x.seg = (int)(v / P.tail_units);                 // segment-major: neighbours share B tiles in L2
+    x.rb2 = P.units_full + (v % P.tail_units);
+    x.tl = P.tile_lo + (int64_t)x.seg * P.tiles_per_seg;
+    x.th = min(P.tile_hi, x.tl + P.tiles_per_seg);
+    x.full = false;
+  }
+  return x;
+}
 
 template <bool BIAS, bool DUMP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -214,25 +238,26 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   // dynamic smem base is only guaranteed 16-byte aligned: align by hand
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int a_bytes = TM * P.dp * 2, b_bytes = TN * P.dp * 2;
-  uint8_t* smem_a = smem;                                   // NUM_A_STAGES x a_bytes
-  uint8_t* smem_b = smem_a + NUM_A_STAGES * a_bytes;        // NUM_B_STAGES x b_bytes
+  uint8_t* smem_a = smem;                                      // RB x a_bytes (both row blocks of the unit)
+  uint8_t* smem_b = smem_a + RB * a_bytes;                     // NUM_B_STAGES x b_bytes
   float* smem_cs = (float*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x {TN scales, TN biases}
-  uint32_t* smem_topi = (uint32_t*)(smem_cs + NUM_CS_STAGES * 2 * TN);  // [groups][KC][TM] train rows of the top-K'
-  Barriers* bars = (Barriers*)(smem_topi + NUM_EPI_GROUPS * KC * TM);
+  uint32_t* smem_topi = (uint32_t*)(smem_cs + NUM_CS_STAGES * 2 * TN);  // [RB][KC][TM] train rows of the top-K'
+  Barriers* bars = (Barriers*)(smem_topi + RB * KC * TM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksl = P.dp / KSLAB;   // 128-byte K slabs per operand row
   const int kst = P.dp / 16;      // UMMA K steps per tile
-  const int64_t num_units = (int64_t)P.row_blocks * P.nseg;
+  const int64_t num_units = (int64_t)P.units_full + (int64_t)P.tail_units * P.tail_seg;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
-    for (int i = 0; i < NUM_A_STAGES; ++i) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
-    for (int i = 0; i < NUM_ACC_STAGES; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], RB); }
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, RB);
+    for (int i = 0; i < NUM_ACC_SLOTS; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
     for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: all 512 columns (2 accumulator stages x 256); one CTA per SM
+  if (warp == 1) {  // TMEM: all 512 columns (NUM_ACC_SLOTS x TN); one CTA per SM
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -244,18 +269,18 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      uint32_t bs = 0, bph = 0, as = 0, aph = 0, cs = 0, cph = 0;
+      uint32_t bs = 0, bph = 0, aph = 0, cs = 0, cph = 0;
       for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
-        const int sg = (int)(u / P.row_blocks), rb = (int)(u % P.row_blocks);  // segment-major: neighbours share B tiles in L2
-        const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
-        const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
-        if (tl >= th) continue;
-        mbar_wait_backoff(&bars->a_empty[as], aph ^ 1);
-        mbar_arrive_expect_tx(&bars->a_full[as], (uint32_t)a_bytes);
-        for (int s = 0; s < ksl; ++s)
-          tma_load_2d(smem_a + as * a_bytes + s * (TM * 128), &map_q, s * KSLAB, (int)(P.q0 + (int64_t)rb * TM), &bars->a_full[as]);
-        if (++as == NUM_A_STAGES) { as = 0; aph ^= 1; }
-        for (int64_t t = tl; t < th; ++t) {
+        const Unit x = get_unit(P, u);
+        if (x.tl >= x.th) continue;
+        mbar_wait_backoff(&bars->a_empty, aph ^ 1);   // every MMA of the previous unit has read its A tiles
+        mbar_arrive_expect_tx(&bars->a_full, (uint32_t)(RB * a_bytes));
+        for (int r = 0; r < RB; ++r)
+          for (int s = 0; s < ksl; ++s)
+            tma_load_2d(smem_a + r * a_bytes + s * (TM * 128), &map_q, s * KSLAB,
+                        (int)(P.q0 + (x.rb2 * RB + r) * TM), &bars->a_full);
+        aph ^= 1;
+        for (int64_t t = x.tl; t < x.th; ++t) {
           mbar_wait_backoff(&bars->cs_empty[cs], cph ^ 1);
           mbar_arrive_expect_tx(&bars->cs_full[cs], (BIAS ? 2u : 1u) * TN * (uint32_t)sizeof(float));
           bulk_load_1d(smem_cs + cs * 2 * TN, P.colscale + t * TN, TN * (uint32_t)sizeof(float), &bars->cs_full[cs]);
@@ -270,54 +295,51 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
+  } else if (warp <= RB) {
+    // ===================================== MMA issuers =======================================
+    // One issuing thread per row block: each waits only for ITS epilogue group's accumulator slot, so a
+    // slow group (insertion-heavy tile) does not stall the other group's MMAs (no head-of-line blocking).
     if (lane == 0) {
+      const int r = warp - 1;
       const uint32_t idesc = make_idesc_bf16(TM, TN);
-      uint32_t bs = 0, bph = 0, as = 0, aph = 0, acs = 0, acph = 0;
+      const uint32_t a_addr = smem_u32(smem_a + r * a_bytes);
+      uint32_t bs = 0, bph = 0, aph = 0, tcount = 0;
       for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
-        const int sg = (int)(u / P.row_blocks);
-        const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
-        const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
-        if (tl >= th) continue;
-        mbar_wait_backoff(&bars->a_full[as], aph);
-        const uint32_t a_addr = smem_u32(smem_a + as * a_bytes);
-        for (int64_t t = tl; t < th; ++t) {
-          mbar_wait_backoff(&bars->acc_empty[acs], acph ^ 1);
-          mbar_wait_backoff(&bars->b_full[bs], bph);
+        const Unit x = get_unit(P, u);
+        if (x.tl >= x.th) continue;
+        mbar_wait(&bars->a_full, aph);
+        aph ^= 1;
+        for (int64_t t = x.tl; t < x.th; ++t, ++tcount) {
+          const uint32_t slot = (tcount & 1) * RB + r, acph = (tcount >> 1) & 1;
+          mbar_wait(&bars->acc_empty[slot], acph ^ 1);
+          mbar_wait(&bars->b_full[bs], bph);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(smem_b + bs * b_bytes);
-          const uint32_t d_tmem = tmem_base + acs * TN;
+          const uint32_t d_tmem = tmem_base + slot * TN;
           for (int k = 0; k < kst; ++k) {
             const int slab = k >> 2, kin = k & 3;  // 4 K steps (32 B each) per 128-byte swizzle row
             const uint64_t adesc = make_kmajor_sw128_desc(a_addr + slab * (TM * 128) + kin * 32);
             const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + slab * (TN * 128) + kin * 32);
             umma_bf16(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
           }
-          tc_commit(&bars->b_empty[bs]);     // smem slot reusable once these MMAs have read it
-          tc_commit(&bars->acc_full[acs]);   // accumulator ready for the epilogue
+          tc_commit(&bars->acc_full[slot]);  // this row block's accumulator is ready for its epilogue group
+          tc_commit(&bars->b_empty[bs]);     // B stage reusable once BOTH issuers' MMAs have read it (count RB)
           if (++bs == NUM_B_STAGES) { bs = 0; bph ^= 1; }
-          if (++acs == NUM_ACC_STAGES) { acs = 0; acph ^= 1; }
         }
-        tc_commit(&bars->a_empty[as]);
-        if (++as == NUM_A_STAGES) { as = 0; aph ^= 1; }
+        tc_commit(&bars->a_empty);
       }
     }
   } else {
     // ===================================== epilogue =========================================
-    // Group g (4 warps, one per TMEM lane quadrant) owns columns [g*128, g*128+128) of EVERY tile, so
-    // both groups drain accumulator stage s while the tensor pipe fills stage s^1.
+    // Group g (4 warps, one per TMEM lane quadrant) owns row block g of the unit: thread == query row.
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
-    const int grp = (warp - 2) >> 2;  // column half of the tile this warp scans
+    const int grp = (warp - FIRST_EPI_WARP) >> 2;  // row block of the unit
     const int row_in_tile = quad * 32 + lane;
     const uint32_t si = smem_u32(smem_topi + (grp * KC) * TM + row_in_tile);  // this row's index slots
-    constexpr int CG = TN / NUM_EPI_GROUPS;                                   // columns per group per tile
     uint32_t tcount = 0;  // tiles consumed so far (same sequence as the MMA warp's)
     for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
-      const int sg = (int)(u / P.row_blocks), rb = (int)(u % P.row_blocks);
-      const int64_t tl = P.tile_lo + (int64_t)sg * P.tiles_per_seg;
-      const int64_t th = min(P.tile_hi, tl + P.tiles_per_seg);
-      const int64_t qrow = P.q0 + (int64_t)rb * TM + row_in_tile;
+      const Unit x = get_unit(P, u);
+      const int64_t qrow = P.q0 + (x.rb2 * RB + grp) * TM + row_in_tile;
       // row-private top-KC (unsorted; aps_rerank.cu orders exactly): scores in registers, train rows in smem
       float bv[KC];
 #pragma unroll
@@ -327,26 +349,27 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       }
       float theta = -CUDART_INF_F;  // min of bv == the row's K'-th best score so far
       int minpos = 0;               // slot holding it
-      for (int64_t t = tl; t < th; ++t, ++tcount) {
-        const uint32_t acs = tcount & 1, acph = (tcount >> 1) & 1, cs = tcount & 3, cph = (tcount >> 2) & 1;
-        mbar_wait(&bars->acc_full[acs], acph);
+      for (int64_t t = x.tl; t < x.th; ++t, ++tcount) {
+        const uint32_t slot = (tcount & 1) * RB + grp, acph = (tcount >> 1) & 1;
+        const uint32_t cs = tcount % NUM_CS_STAGES, cph = (tcount / NUM_CS_STAGES) & 1;
+        mbar_wait(&bars->acc_full[slot], acph);
         mbar_wait(&bars->cs_full[cs], cph);
         tc_fence_after();
-        const uint32_t cscale = smem_u32(smem_cs + cs * 2 * TN + grp * CG);
-        const int64_t col0 = t * TN + grp * CG;
-        const bool partial = (col0 < P.t0) || (col0 + CG > P.t1);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acs * TN + grp * CG;
+        const uint32_t cscale = smem_u32(smem_cs + cs * 2 * TN);
+        const int64_t col0 = t * TN;
+        const bool partial = (col0 < P.t0) || (col0 + TN > P.t1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * TN;
         float va[32], vb[32];
         tmem_ld32(taddr, va);
         tmem_wait_ld(va);
 #pragma unroll 1
-        for (int c2 = 0; c2 < CG / 64; ++c2) {
+        for (int c2 = 0; c2 < TN / 64; ++c2) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = 2 * c2 + h;
             float(&cur)[32] = h ? vb : va;
             float(&nxt)[32] = h ? va : vb;
-            if (c + 1 < CG / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
+            if (c + 1 < TN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
             float gm[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -407,23 +430,29 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                 }
               }
             }
-            if (c + 1 < CG / 32) tmem_wait_ld(nxt);
+            if (c + 1 < TN / 32) tmem_wait_ld(nxt);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&bars->acc_empty[acs]);
+          mbar_arrive(&bars->acc_empty[slot]);
           mbar_arrive(&bars->cs_empty[cs]);
         }
       }
       if (qrow < P.q1) {
-        const int64_t o = (((qrow - P.q0) * P.nseg + sg) * NUM_EPI_GROUPS + grp) * KC;
+        const int64_t o = ((qrow - P.q0) * P.nslot + x.seg) * KC;
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
           P.cand_idx[o + i] = lds_u32(si + i * SLOT_STRIDE);
           P.cand_score[o + i] = bv[i];
         }
+        if (x.full)  // rows of full-width units have one list: mark the others empty
+          for (int sl = 1; sl < P.nslot; ++sl)
+            for (int i = 0; i < KC; ++i) {
+              P.cand_idx[o + sl * KC + i] = 0xffffffffu;
+              P.cand_score[o + sl * KC + i] = -CUDART_INF_F;
+            }
       }
     }
   }
@@ -475,8 +504,36 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dp, in
 }  // namespace
 
 int aps_k_knn_tc_supported(int Dp) { return Dp == 64 || Dp == 128; }
-int aps_k_knn_tc_lists() { return NUM_EPI_GROUPS; }
 
+// Work decomposition shared by the launcher and by callers that size the candidate buffers.
+struct TcSchedule {
+  int units_full, tail_units, tail_seg, nslot, tiles_per_seg;
+  int64_t tile_lo, tile_hi;
+};
+static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1) {
+  TcSchedule sc;
+  sc.tile_lo = t0 / TN;
+  sc.tile_hi = aps_ceil_div(t1, TN);
+  const int64_t tiles = sc.tile_hi - sc.tile_lo;
+  const int64_t pairs = aps_ceil_div(nq, (int64_t)RB * TM);  // 256-row query block pairs
+  const int64_t grid = sm_count;  // fewer pairs than SMs: every unit is a (segmented) tail unit
+  sc.units_full = (int)((pairs / grid) * grid);
+  sc.tail_units = (int)(pairs - sc.units_full);
+  sc.tail_seg = 1;
+  if (sc.tail_units > 0) {
+    int64_t seg = grid / sc.tail_units;  // fill the last round
+    if (seg > MAX_SEG) seg = MAX_SEG;
+    if (seg > tiles) seg = tiles;
+    if (seg < 1) seg = 1;
+    sc.tail_seg = (int)seg;
+  }
+  sc.nslot = sc.tail_units > 0 ? sc.tail_seg : 1;
+  sc.tiles_per_seg = (int)aps_ceil_div(tiles, sc.tail_seg);
+  return sc;
+}
+int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1) {
+  return make_schedule(sm_count, nq, t0, t1).nslot;
+}
 
 int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEvent_t ev0, cudaEvent_t ev1) {
   if (!aps_k_knn_tc_supported(p.Dp)) {
@@ -488,26 +545,33 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
     return APS_ERR_ARGS;
   }
   if (p.q1 <= p.q0 || p.t1 <= p.t0) return APS_OK;
+  const TcSchedule sc = make_schedule(sm_count, p.q1 - p.q0, p.t0, p.t1);
+  if (p.nslot != sc.nslot) {
+    aps_set_error(APS_ERR_ARGS, "", "candidate buffers must be sized with aps_k_knn_tc_slots (%d != %d)", p.nslot, sc.nslot);
+    return APS_ERR_ARGS;
+  }
   CUtensorMap map_q, map_t;
   APS_TRY(make_map(&map_q, p.Qb, p.Fq_total, p.Dp, TM));
   APS_TRY(make_map(&map_t, p.Tb, p.Ft_total, p.Dp, TN));
   KParams P;
   P.q0 = p.q0; P.q1 = p.q1; P.t0 = p.t0; P.t1 = p.t1;
   P.dp = p.Dp;
-  P.nseg = p.nseg;
-  P.row_blocks = (int)aps_ceil_div(p.q1 - p.q0, TM);
-  P.tile_lo = p.t0 / TN;
-  P.tile_hi = aps_ceil_div(p.t1, TN);
-  P.tiles_per_seg = (int)aps_ceil_div(P.tile_hi - P.tile_lo, p.nseg);
+  P.nslot = sc.nslot;
+  P.units_full = sc.units_full;
+  P.tail_units = sc.tail_units;
+  P.tail_seg = sc.tail_seg;
+  P.tile_lo = sc.tile_lo;
+  P.tile_hi = sc.tile_hi;
+  P.tiles_per_seg = sc.tiles_per_seg;
   P.colscale = p.colscale;
   P.colbias = p.colbias;
   P.cand_idx = p.cand_idx;
   P.cand_score = p.cand_score;
   P.dump = p.dump;
-  // every (row, segment) slot is written by exactly one work unit (empty segments write empty slots)
-  const size_t smem = 1024 + (size_t)NUM_A_STAGES * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
-                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)NUM_EPI_GROUPS * KC * TM * 4 + sizeof(Barriers);
-  const int64_t units = (int64_t)P.row_blocks * P.nseg;
+  // every (row, list) slot is written by exactly one work unit (full-width units clear the unused lists)
+  const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
+                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * KC * TM * 4 + sizeof(Barriers);
+  const int64_t units = (int64_t)sc.units_full + (int64_t)sc.tail_units * sc.tail_seg;
   const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);
   if (ev0) APS_CUDA(cudaEventRecord(ev0, s));
   auto launch = [&](auto kern) -> int {

@@ -176,10 +176,10 @@ int aps_gplan_pair_counts_device(aps_gplan* p, void** counts_i64); /* n*n int64,
 /* ---- diagnostics (tests only): raw output of the tcgen05 candidate kernel -----------------------
  * Q [nq x D], T [nt x D] ROW-major float (used as given, no normalisation).  scores [nq x nt]
  * receives (bf16(q).bf16(t))*scale_t + bias_t as the kernel's epilogue computes it (scale = 1,
- * bias = -|t|^2/2); cand_idx / cand_score [nq x nseg x L x 8], L = aps_debug_tc_lists(): per column
- * segment the kernel keeps L lists of 8 (one per epilogue warp group, over disjoint column subsets) of
- * 0-based train rows, 0xFFFFFFFF = empty.  Any of the three outputs may be NULL. */
-int aps_debug_tc_lists(void);
+ * bias = -|t|^2/2); cand_idx / cand_score [nq x S x 8], S = aps_debug_tc_slots(ctx, nq, nt): the
+ * candidate lists the kernel keeps per query row (one per column segment its work unit was split
+ * into; 0-based train rows, 0xFFFFFFFF = empty).  Any of the three outputs may be NULL; nseg is ignored. */
+int aps_debug_tc_slots(aps_ctx* ctx, int64_t nq, int64_t nt);
 int aps_debug_tc_scores(aps_ctx* ctx, const float* Q, int64_t nq, const float* T, int64_t nt, int D, int nseg,
                         float* scores, uint32_t* cand_idx, float* cand_score);
 
