@@ -29,10 +29,19 @@
 // Scheduling: units that fill whole rounds of the grid span all train tiles; the units of the last,
 // partial round are split into up to 4 column segments so that the tail is balanced.
 //
-// Measured alternatives (round 1, C2, same box): one row block per unit with the epilogue split by
-// columns (two lists per row): 8.23 ms; the same with 4 groups x 64 columns: 8.31 ms; a fully unrolled
-// register-resident sorted top-K: 348 KB of SASS, 69 % instruction-fetch stalls, 109 ms
-// (profiles/r1_ncu_history.txt).  The kernel is epilogue-issue bound, not MMA/L2 bound.
+// What bounds it (round 1 measurements, C2 = 163840^2 pairs, D = 128, same box, profiles/r1_ncu_history.txt):
+//   * with the selection skipped (accumulators never read) the TMA + MMA pipeline alone takes 3.99 ms
+//     = 1723 TFLOP/s;
+//   * with the selection: 6.6-6.7 ms = 1025-1040 TFLOP/s, unchanged by doubling the epilogue warps
+//     (CSPLIT = 2: 7.24 ms) or by cheaper polling -- every fp32 accumulator must cross TMEM -> registers,
+//     and tcgen05.ld moves ~64 B/clk/SM (B300_MICROARCH.md "TMEM-read 64 B/cyc"): 128 rows x 128 columns
+//     x 4 B x 2 row blocks = 128 KB per step = 2048 clk, measured 2380 clk per step.  16 outputs/clk/SM
+//     x 2*D FLOP = 1.19 PFLOP/s at D = 128 is the ceiling of any epilogue that inspects every distance
+//     in fp32; the kernel runs at 87 % of it.  (fp16 accumulators would halve the TMEM traffic but their
+//     rounding breaks the completeness proof on SIFT-like data: median d8-d4 gap 0.016.)
+//   * earlier designs: one row block per unit, epilogue split by columns (two lists per row, single MMA
+//     issuer): 8.23 ms; fully unrolled register-resident sorted top-K: 348 KB of SASS, 69 % instruction-
+//     fetch stalls, 109 ms.
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2*D per (query, train) pair.  HBM traffic is
 // negligible (operands stream from L2: every concurrently running CTA walks the same B tiles).
@@ -51,8 +60,9 @@ constexpr int NUM_B_STAGES = 4;
 constexpr int NUM_ACC_SLOTS = 2 * RB;  // slot = (tile parity) * RB + row block ; 4 x 128 columns = all of TMEM
 constexpr int NUM_CS_STAGES = 8;
 constexpr int KC = 8;          // candidates per (row, segment)
-constexpr int MAX_SEG = 4;     // column segments of a tail unit == candidate lists a row can have
-constexpr int NUM_EPI_WARPS = 4 * RB;
+constexpr int CSPLIT = 1;      // epilogue groups per row block (each scans TN/CSPLIT columns of every tile, own list)
+constexpr int MAX_SEG = 4 / CSPLIT;  // column segments of a tail unit; a row has MAX_SEG*CSPLIT <= 4 candidate lists
+constexpr int NUM_EPI_WARPS = 4 * RB * CSPLIT;
 constexpr int FIRST_EPI_WARP = 1 + RB;  // warp 0 producer, warps 1..RB MMA issuers (one per row block)
 constexpr int NUM_THREADS = 32 * (FIRST_EPI_WARP + NUM_EPI_WARPS);
 static_assert(NUM_ACC_SLOTS * TN == 512, "TMEM budget");
@@ -78,16 +88,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the hint (ns) elapses: the
+// polling loops of the producer / MMA lanes then cost almost no issue slots (they were 21 % of all
+// executed instructions with the default time limit -- profiles/r1_ncu_history.txt)
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(kSuspendHintNs)
         : "memory");
   } while (!done);
 }
@@ -99,10 +113,10 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(kSuspendHintNs)
         : "memory");
     if (done) break;
     __nanosleep(40);
@@ -241,8 +255,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   uint8_t* smem_a = smem;                                      // RB x a_bytes (both row blocks of the unit)
   uint8_t* smem_b = smem_a + RB * a_bytes;                     // NUM_B_STAGES x b_bytes
   float* smem_cs = (float*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x {TN scales, TN biases}
-  uint32_t* smem_topi = (uint32_t*)(smem_cs + NUM_CS_STAGES * 2 * TN);  // [RB][KC][TM] train rows of the top-K'
-  Barriers* bars = (Barriers*)(smem_topi + RB * KC * TM);
+  uint32_t* smem_topi = (uint32_t*)(smem_cs + NUM_CS_STAGES * 2 * TN);  // [RB*CSPLIT][KC][TM] train rows of the top-K'
+  Barriers* bars = (Barriers*)(smem_topi + RB * CSPLIT * KC * TM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksl = P.dp / KSLAB;   // 128-byte K slabs per operand row
@@ -253,7 +267,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], RB); }
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, RB);
-    for (int i = 0; i < NUM_ACC_SLOTS; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
+    for (int i = 0; i < NUM_ACC_SLOTS; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4 * CSPLIT); }
     for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -333,9 +347,12 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     // ===================================== epilogue =========================================
     // Group g (4 warps, one per TMEM lane quadrant) owns row block g of the unit: thread == query row.
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
-    const int grp = (warp - FIRST_EPI_WARP) >> 2;  // row block of the unit
+    const int egrp = (warp - FIRST_EPI_WARP) >> 2;
+    const int grp = egrp / CSPLIT;  // row block of the unit
+    const int ch = egrp % CSPLIT;   // column part of every tile this warp scans
+    constexpr int CG = TN / CSPLIT;
     const int row_in_tile = quad * 32 + lane;
-    const uint32_t si = smem_u32(smem_topi + (grp * KC) * TM + row_in_tile);  // this row's index slots
+    const uint32_t si = smem_u32(smem_topi + (egrp * KC) * TM + row_in_tile);  // this row's index slots
     uint32_t tcount = 0;  // tiles consumed so far (same sequence as the MMA warp's)
     for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
       const Unit x = get_unit(P, u);
@@ -355,21 +372,28 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         mbar_wait(&bars->acc_full[slot], acph);
         mbar_wait(&bars->cs_full[cs], cph);
         tc_fence_after();
-        const uint32_t cscale = smem_u32(smem_cs + cs * 2 * TN);
-        const int64_t col0 = t * TN;
-        const bool partial = (col0 < P.t0) || (col0 + TN > P.t1);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * TN;
+        const uint32_t cscale = smem_u32(smem_cs + cs * 2 * TN + ch * CG);
+        const int64_t col0 = t * TN + ch * CG;
+        const bool partial = (col0 < P.t0) || (col0 + CG > P.t1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * TN + ch * CG;
         float va[32], vb[32];
-        tmem_ld32(taddr, va);
-        tmem_wait_ld(va);
+        if (CSPLIT == 1) {  // two warps per sub-partition: double-buffer the TMEM loads
+          tmem_ld32(taddr, va);
+          tmem_wait_ld(va);
+        }
 #pragma unroll 1
-        for (int c2 = 0; c2 < TN / 64; ++c2) {
+        for (int c2 = 0; c2 < CG / 64 + (CG % 64 ? 1 : 0); ++c2) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < (CG >= 64 ? 2 : 1); ++h) {
             const int c = 2 * c2 + h;
-            float(&cur)[32] = h ? vb : va;
-            float(&nxt)[32] = h ? va : vb;
-            if (c + 1 < TN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
+            float(&cur)[32] = (CSPLIT == 1 && h) ? vb : va;
+            float(&nxt)[32] = (CSPLIT == 1 && h) ? va : vb;
+            if (CSPLIT == 1) {
+              if (c + 1 < CG / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
+            } else {  // four warps per sub-partition hide the load latency of each other: single buffer
+              tmem_ld32(taddr + c * 32, cur);
+              tmem_wait_ld(cur);
+            }
             float gm[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -430,7 +454,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                 }
               }
             }
-            if (c + 1 < TN / 32) tmem_wait_ld(nxt);
+            if (CSPLIT == 1 && c + 1 < CG / 32) tmem_wait_ld(nxt);
           }
         }
         tc_fence_before();
@@ -441,14 +465,14 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         }
       }
       if (qrow < P.q1) {
-        const int64_t o = ((qrow - P.q0) * P.nslot + x.seg) * KC;
+        const int64_t o = ((qrow - P.q0) * P.nslot + x.seg * CSPLIT + ch) * KC;
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
           P.cand_idx[o + i] = lds_u32(si + i * SLOT_STRIDE);
           P.cand_score[o + i] = bv[i];
         }
-        if (x.full)  // rows of full-width units have one list: mark the others empty
-          for (int sl = 1; sl < P.nslot; ++sl)
+        if (x.full && ch == 0)  // rows of full-width units use the first CSPLIT lists: mark the others empty
+          for (int sl = CSPLIT; sl < P.nslot; ++sl)
             for (int i = 0; i < KC; ++i) {
               P.cand_idx[o + sl * KC + i] = 0xffffffffu;
               P.cand_score[o + sl * KC + i] = -CUDART_INF_F;
@@ -527,7 +551,7 @@ static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1
     if (seg < 1) seg = 1;
     sc.tail_seg = (int)seg;
   }
-  sc.nslot = sc.tail_units > 0 ? sc.tail_seg : 1;
+  sc.nslot = (sc.tail_units > 0 ? sc.tail_seg : 1) * CSPLIT;
   sc.tiles_per_seg = (int)aps_ceil_div(tiles, sc.tail_seg);
   return sc;
 }
@@ -570,7 +594,7 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.dump = p.dump;
   // every (row, list) slot is written by exactly one work unit (full-width units clear the unused lists)
   const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
-                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * KC * TM * 4 + sizeof(Barriers);
+                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * CSPLIT * KC * TM * 4 + sizeof(Barriers);
   const int64_t units = (int64_t)sc.units_full + (int64_t)sc.tail_units * sc.tail_seg;
   const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);
   if (ev0) APS_CUDA(cudaEventRecord(ev0, s));
