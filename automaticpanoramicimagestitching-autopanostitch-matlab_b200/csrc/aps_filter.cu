@@ -97,6 +97,57 @@ __global__ void k_rank_per_image(const int32_t* __restrict__ target, const int64
   for (int t = lane; t < n; t += 32) dir_counts[(int64_t)i * n + t] = cnt[t];
 }
 
+// Same result with 8 warps per image (n <= 1024 targets): pass 1 counts per (warp sub-range, target), a
+// prefix over the sub-ranges gives every warp its starting rank, pass 2 hands the ranks out.
+constexpr int RPI_WARPS = 8;
+__global__ void __launch_bounds__(32 * RPI_WARPS) k_rank_per_image_mw(const int32_t* __restrict__ target,
+                                                                       const int64_t* __restrict__ img_off, int n,
+                                                                       int64_t* __restrict__ dir_counts,
+                                                                       int64_t* __restrict__ rank) {
+  extern __shared__ int cnt[];  // [RPI_WARPS][n]
+  const int i = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int t = threadIdx.x; t < RPI_WARPS * n; t += blockDim.x) cnt[t] = 0;
+  __syncthreads();
+  const int64_t b = img_off[i], e = img_off[i + 1];
+  const int64_t per = (((e - b) + RPI_WARPS - 1) / RPI_WARPS + 31) / 32 * 32;
+  const int64_t wb = min(e, b + w * per), we = min(e, wb + per);
+  int* mine = cnt + w * n;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int64_t base = wb; base < we; base += 32) {
+      const int64_t q = base + lane;
+      const int t = (q < we) ? target[q] : 0;
+      const bool active = t > 0;
+      const unsigned amask = __ballot_sync(0xffffffffu, active);
+      int myrank = 0, cbase = 0;
+      unsigned peers = 0;
+      if (active) {
+        peers = __match_any_sync(amask, t);
+        cbase = mine[t - 1];
+        myrank = __popc(peers & ((1u << lane) - 1u));
+      }
+      __syncwarp();
+      if (active) {
+        if (pass == 1) rank[q] = (int64_t)cbase + myrank;
+        if (myrank == 0) mine[t - 1] = cbase + __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (pass == 0) {  // counts -> exclusive prefix over the warp sub-ranges; totals out
+      for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        int run = 0;
+        for (int ww = 0; ww < RPI_WARPS; ++ww) {
+          int v = cnt[ww * n + t];
+          cnt[ww * n + t] = run;
+          run += v;
+        }
+        dir_counts[(int64_t)i * n + t] = run;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // pair_counts (column-major cell index a + b*n) and its exclusive scan; single block.
 __global__ void k_pair_counts_scan(const int64_t* __restrict__ dir_counts, int n, int64_t* __restrict__ pair_counts,
                                    int64_t* __restrict__ pair_ptr) {
@@ -170,7 +221,10 @@ int aps_k_global_compact(cudaStream_t s, const int32_t* target, const uint32_t* 
                           const int32_t* img_of_row, const int64_t* img_off, int n, int64_t F, int64_t* dir_counts,
                           int64_t* pair_counts, int64_t* pair_ptr, int64_t* rank, uint32_t* rows) {
   if (n == 0) return APS_OK;
-  k_rank_per_image<<<n, 32, (size_t)n * sizeof(int), s>>>(target, img_off, n, dir_counts, rank);
+  if (n <= 1024)
+    k_rank_per_image_mw<<<n, 32 * RPI_WARPS, (size_t)RPI_WARPS * n * sizeof(int), s>>>(target, img_off, n, dir_counts, rank);
+  else
+    k_rank_per_image<<<n, 32, (size_t)n * sizeof(int), s>>>(target, img_off, n, dir_counts, rank);
   APS_LAUNCHED();
   k_pair_counts_scan<<<1, 1024, 0, s>>>(dir_counts, n, pair_counts, pair_ptr);
   APS_LAUNCHED();

@@ -61,6 +61,8 @@ __device__ __forceinline__ float eps_bound(const int32_t* __restrict__ flags, in
   return bias_mode ? (slop + bf) : (slop + bf + dev);     // normalised rows: |sq_b - 1| <= dev is ignored by the score
 }
 
+// G lanes per query row (G = 8, 16 or 32 >= number of candidates): 32/G rows per warp.
+template <int G>
 __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, const float* __restrict__ sqQ,
                                                 const float* __restrict__ invnQ, const float* __restrict__ T,
                                                 const float* __restrict__ sqT, int D, int metric, int64_t q0,
@@ -71,10 +73,12 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
                                                 int64_t out_row0, uint32_t* __restrict__ idx,
                                                 float* __restrict__ dist, int32_t* __restrict__ fb_rows,
                                                 int32_t* __restrict__ fb_count) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= nq) return;
-  const int64_t q = q0 + r;
+  constexpr int RPW = 32 / G;  // rows per warp
+  const int lane = threadIdx.x & 31, sub = lane / G, sl = lane % G;
+  const unsigned segmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
+  const int64_t r = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool row_ok = r < nq;
+  const int64_t q = q0 + (row_ok ? r : 0);
   const int ncand = nseg * kcand;
   const float eps = eps_bound(flags, bias_mode);
   const bool exact = flags[0] != 0;
@@ -85,26 +89,26 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
 
   uint32_t ci = 0xffffffffu;
   float sc = -CUDART_INF_F;
-  if (lane < ncand) {
-    ci = cand_idx[r * ncand + lane];
-    sc = cand_score[r * ncand + lane];
+  if (row_ok && sl < ncand) {
+    ci = cand_idx[r * ncand + sl];
+    sc = cand_score[r * ncand + sl];
   }
   const bool valid = ci != 0xffffffffu;
   const float sapx = valid ? fmaf(beta, sc, alpha) : CUDART_INF_F;  // monotone in sc; its own rounding is inside eps
 
-  // W = min over segments of the worst (largest) retained approx distance
+  // W = min over lists of the worst (largest) retained approx distance
   float W = CUDART_INF_F;
   for (int s = 0; s < nseg; ++s) {
-    float m = (lane >= s * kcand && lane < (s + 1) * kcand) ? sapx : -CUDART_INF_F;
+    float m = (sl >= s * kcand && sl < (s + 1) * kcand) ? sapx : -CUDART_INF_F;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o, G));
     W = fminf(W, m);
   }
   // prune: lanes whose lower bound exceeds the k-th smallest upper bound cannot be in the top-k
   const float ub = sapx + eps, lb = sapx - eps;
   int below = 0;
-  for (int l = 0; l < 32; ++l) {
-    float o = __shfl_sync(0xffffffffu, ub, l);
+  for (int l = 0; l < G; ++l) {
+    float o = __shfl_sync(0xffffffffu, ub, l, G);
     below += (o < lb);
   }
   const bool need = valid && below < k;
@@ -114,30 +118,30 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
     const float* b = T + (int64_t)ci * D;
     d = (metric == 0) ? l2sq_flann(a, b, D) : ssd_seq(a, b, D, a2, sqT[ci]);
   }
-  const bool nan_seen = __any_sync(0xffffffffu, need && !(d == d));
+  const bool nan_seen = (__ballot_sync(0xffffffffu, need && !(d == d)) & segmask) != 0u;
   // rank by (distance, index)
   int rank = 0;
-  for (int l = 0; l < 32; ++l) {
-    float od = __shfl_sync(0xffffffffu, d, l);
-    uint32_t oi = __shfl_sync(0xffffffffu, ci, l);
-    bool oneed = __shfl_sync(0xffffffffu, (int)need, l);
+  for (int l = 0; l < G; ++l) {
+    float od = __shfl_sync(0xffffffffu, d, l, G);
+    uint32_t oi = __shfl_sync(0xffffffffu, ci, l, G);
+    bool oneed = __shfl_sync(0xffffffffu, (int)need, l, G);
     rank += oneed && (od < d || (od == d && oi < ci));
   }
-  const int nvalid = __popc(__ballot_sync(0xffffffffu, need));
+  const int nvalid = __popc(__ballot_sync(0xffffffffu, need) & segmask);
   if (need && rank < k) {
     idx[(q - out_row0) * k + rank] = (uint32_t)((int64_t)ci - t0 + 1);
     dist[(q - out_row0) * k + rank] = d;
   }
-  if (lane >= nvalid && lane < k) {  // fewer than k neighbours exist: flann_knn.cpp:216-219
-    idx[(q - out_row0) * k + lane] = 0u;
-    dist[(q - out_row0) * k + lane] = CUDART_INF_F;
+  if (row_ok && sl >= nvalid && sl < k) {  // fewer than k neighbours exist: flann_knn.cpp:216-219
+    idx[(q - out_row0) * k + sl] = 0u;
+    dist[(q - out_row0) * k + sl] = CUDART_INF_F;
   }
   // completeness proof
   float dk = -CUDART_INF_F;  // k-th smallest exact distance (or -inf when fewer than k candidates)
   {
     float mine = (need && rank == k - 1) ? d : -CUDART_INF_F;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+    for (int o = G / 2; o > 0; o >>= 1) mine = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, o, G));
     dk = mine;
   }
   bool proven;
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   else
     proven = (W == CUDART_INF_F);  // every train row was a candidate
   if (nan_seen) proven = false;
-  if (!proven && lane == 0) {
+  if (row_ok && !proven && sl == 0) {
     int pos = atomicAdd(fb_count, 1);
     fb_rows[pos] = (int32_t)q;
   }
@@ -165,9 +169,20 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
     aps_set_error(APS_ERR_ARGS, "", "rerank: nseg*kcand must be <= 32");
     return APS_ERR_ARGS;
   }
-  k_rerank<<<(unsigned)aps_ceil_div(nq, 8), 256, 0, s>>>(Q, sqQ, invnQ, T, sqT, D, metric, q0, nq, t0, nseg, kcand,
-                                                        cand_idx, cand_score, flags, bias_mode, k, out_row0, idx,
-                                                        dist, fb_rows, fb_count);
+  const int ncand = nseg * kcand;
+  if (k > 8 || k > ncand) {
+    aps_set_error(APS_ERR_ARGS, "", "rerank: k must be <= min(8, candidates)");
+    return APS_ERR_ARGS;
+  }
+#define APS_RERANK(G)                                                                                              \
+  k_rerank<G><<<(unsigned)aps_ceil_div(nq, 8 * (32 / G)), 256, 0, s>>>(Q, sqQ, invnQ, T, sqT, D, metric, q0, nq, t0, \
+                                                                       nseg, kcand, cand_idx, cand_score, flags,     \
+                                                                       bias_mode, k, out_row0, idx, dist, fb_rows,  \
+                                                                       fb_count)
+  if (ncand <= 8) APS_RERANK(8);
+  else if (ncand <= 16) APS_RERANK(16);
+  else APS_RERANK(32);
+#undef APS_RERANK
   APS_LAUNCHED();
   return APS_OK;
 }
