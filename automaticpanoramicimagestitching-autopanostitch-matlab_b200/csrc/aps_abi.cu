@@ -182,10 +182,6 @@ static int pad_rows(cudaStream_t s, const uint8_t* src, int64_t N, int nb, int n
   return APS_OK;
 }
 
-__global__ void k_add_offset_u32(uint32_t* idx, int64_t n, uint32_t off) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && idx[i] != 0u) idx[i] += off;
-}
 
 static int copy_out_matrix(aps_ctx* c, const uint32_t* idx_rm, const float* dist_rm, int64_t N, int k, int layout,
                            uint32_t* h_idx, float* h_dist) {
@@ -221,8 +217,10 @@ struct FloatSide {          // one prepared descriptor set
   int64_t N = 0;
 };
 
-static bool tc_wanted(const aps_ctx* c, int D, int64_t nq, int64_t nt) {
+static bool tc_wanted(const aps_ctx* c, int D, int64_t nq, int64_t nt, int k) {
   if (c->float_engine == 1) return false;
+  // the completeness proof needs the K'-th candidate (K' = 8) strictly beyond the k-th neighbour
+  if (k > 5) return false;
   int Dp = (D + 63) / 64 * 64;
   if (!aps_k_knn_tc_supported(Dp)) return false;
   if (c->float_engine == 2) return true;
@@ -392,7 +390,7 @@ extern "C" int aps_flann_knn(aps_ctx* c, const void* train, int64_t Ft, const vo
     return copy_out_matrix(c, didx.p, ddist.p, Fq, k, layout, idx, dist);
   }
   // float: the caller passes what featureMatchingGlobal.m:80-84 already normalised -> no normalisation here
-  const bool tc = tc_wanted(c, D, Fq, Ft);
+  const bool tc = tc_wanted(c, D, Fq, Ft, k);
   FloatSet T, Q;
   APS_TRY(floatset_alloc(c, T, Ft, D));
   APS_TRY(floatset_reset_flags(c, T));
@@ -500,7 +498,7 @@ extern "C" int aps_nearest2_ssd(aps_ctx* c, const float* A, int64_t N1, const fl
   if (D <= 0) APS_FAIL(APS_ERR_DIM, "", "descriptor dimension must be positive");
   if (N1 == 0) return APS_OK;
   c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
-  const bool tc = tc_wanted(c, D, N1, N2);
+  const bool tc = tc_wanted(c, D, N1, N2, 2);
   FloatSet QA, TB;
   DevBuf<uint8_t> tmp;
   APS_TRY(floatset_alloc(c, QA, N1, D));
@@ -619,7 +617,7 @@ extern "C" int aps_gplan_create(aps_ctx* c, const int64_t* counts, int n, int D,
   int rc = APS_OK;
   auto A = [&](int r) { if (rc == APS_OK) rc = r; };
   if (dtype == APS_F32) {
-    p->tensor = tc_wanted(c, D, F, F);
+    p->tensor = tc_wanted(c, D, F, F, k);
     A(floatset_alloc(c, p->fs, F, D));
   } else {
     p->nb16 = (D + 15) / 16 * 16;
@@ -969,7 +967,7 @@ extern "C" int aps_match_features(aps_ctx* c, const void* F1, int64_t N1, const 
   c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
   const void* desc[2] = {F1, F2};
   const int64_t counts[2] = {N1, N2};
-  const bool tensor = dtype == APS_F32 && tc_wanted(c, D, N1, N2);
+  const bool tensor = dtype == APS_F32 && tc_wanted(c, D, N1, N2, 2);
   PairwiseSets ps;
   APS_TRY(pairwise_prepare(c, ps, desc, counts, 2, D, dtype, layout, tensor));
   DevBuf<uint32_t> dm;
@@ -1030,7 +1028,7 @@ extern "C" int aps_feature_matching_pairwise(aps_ctx* c, const void* const* desc
   }
   int rc = APS_OK;
   {
-    const bool tensor = dtype == APS_F32 && tc_wanted(c, D, maxc, maxc);
+    const bool tensor = dtype == APS_F32 && tc_wanted(c, D, maxc, maxc, 2);
     PairwiseSets ps;
     // pair list in column-major cell order (featureMatchingPairwise.m:48): j outer, i < j inner
     std::vector<int> pi, pj;

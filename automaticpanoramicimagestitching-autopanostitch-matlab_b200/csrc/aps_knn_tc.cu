@@ -196,14 +196,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // The row's top-KC list lives in shared memory, slot-major ([slot][row], conflict-free), descending
 // by score; addressed by 32-bit shared-window addresses (ld/st.shared, not generic).  Out of line
 // on purpose (code size); returns the new K'-th best score.
-__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 constexpr uint32_t SLOT_STRIDE = TM * 4;                  // bytes between consecutive slots of one row
 

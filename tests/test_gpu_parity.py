@@ -243,3 +243,24 @@ def test_select_partners_vs_oracle_random(aps, orc):
         cand, pairs = aps.selectImagePartners(C, m)
         oc, op = orc.select_partners(C, m)
         assert (cand == oc).all() and np.array_equal(pairs, op + 1)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 6, 8])
+def test_flann_knn_float_k_sweep(aps, orc, k):
+    """every supported k (reference uses 4 and 2); k > 5 runs on the exact engine by design."""
+    rng = np.random.default_rng(k)
+    X = rng.standard_normal((5000, 128)).astype(np.float32)
+    X[10:14] = X[10]
+    idx, dist = aps.flann_knn_win(X, X[:900].copy(), k)
+    oi, od = orc.knn_l2(X, X[:900], k)
+    assert np.array_equal(idx, oi) and np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+
+
+def test_flann_knn_binary_k_sweep_and_widths(aps, orc):
+    rng = np.random.default_rng(3)
+    for nb in (16, 32, 48, 64):
+        T = rng.integers(0, 256, (2000, nb), dtype=np.uint8)
+        for k in (1, 2, 4, 7):
+            idx, dist = aps.flann_knn_win(T, T[:300].copy(), k, "bf")
+            oi, od = orc.knn_hamming(T, T[:300], k)
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nb, k)
