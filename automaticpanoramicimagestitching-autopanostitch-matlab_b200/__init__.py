@@ -15,6 +15,7 @@ from .host import (  # noqa: F401
     featureMatchingPairwise,
     flann_knn_win,
     matchFeaturesScratch,
+    merge_pairwise_shards,
     nearest2HammingExhaustiveMEX,
     nearest2HammingExhaustiveOMPMEX,
     nearest2SSDExhaustive,

@@ -81,6 +81,7 @@ def lib():
         "aps_match_features": (i32, [vp, vp, i64, vp, i64, i32, i32, i32, dbl, dbl, i32, vp, vp, C.POINTER(i64)]),
         "aps_feature_matching_global": (i32, [vp, pp, C.POINTER(i64), i32, i32, i32, i32, i32, dbl, i32, pp]),
         "aps_feature_matching_pairwise": (i32, [vp, pp, C.POINTER(i64), i32, i32, i32, i32, dbl, dbl, pp]),
+        "aps_feature_matching_pairwise_shard": (i32, [vp, pp, C.POINTER(i64), i32, i32, i32, i32, dbl, dbl, i32, i32, pp]),
         "aps_matchlist_n": (i32, [vp]),
         "aps_matchlist_total": (i64, [vp]),
         "aps_matchlist_pair_ptr": (C.POINTER(i64), [vp]),

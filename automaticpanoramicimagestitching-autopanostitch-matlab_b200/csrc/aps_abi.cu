@@ -990,6 +990,7 @@ extern "C" int aps_match_features(aps_ctx* c, const void* F1, int64_t N1, const 
   return APS_OK;
 }
 
+
 __global__ void k_gather_pairs(const uint32_t* __restrict__ src_m, const double* __restrict__ src_d,
                                const int64_t* __restrict__ region_off, const int64_t* __restrict__ out_off,
                                uint32_t* __restrict__ rows, double* __restrict__ metric) {
@@ -1002,13 +1003,155 @@ __global__ void k_gather_pairs(const uint32_t* __restrict__ src_m, const double*
   }
 }
 
-extern "C" int aps_feature_matching_pairwise(aps_ctx* c, const void* const* desc, const int64_t* counts, int n,
-                                             int D, int dtype, int layout, double match_threshold, double max_ratio,
-                                             aps_matchlist** out) {
+// One batch of pairs (all using the same descriptor view) through the batched pipeline; results are
+// appended to the host vectors in the order of `pairs`.
+struct PairRef {
+  int i, j;
+  size_t ordinal;  // position in the full pair list (cell order)
+};
+
+static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRef>& pairs, const int64_t* counts, int D,
+                          int dtype, bool norm, bool tensor, double match_threshold, double max_ratio,
+                          std::vector<int32_t>& out_count, std::vector<std::vector<uint32_t>>& out_rows,
+                          std::vector<std::vector<double>>& out_metric) {
+  const int np = (int)pairs.size();
+  if (np == 0) return APS_OK;
+  cudaStream_t s = c->stream;
+  std::vector<int64_t> eoff(np + 1, 0), boff(np + 1, 0);
+  std::vector<int32_t> qoff(np), toff(np), tcnt(np);
+  for (int p = 0; p < np; ++p) {
+    eoff[p + 1] = eoff[p] + counts[pairs[p].i];
+    boff[p + 1] = boff[p] + counts[pairs[p].j];
+    qoff[p] = (int32_t)ps.off[pairs[p].i];
+    toff[p] = (int32_t)ps.off[pairs[p].j];
+    tcnt[p] = (int32_t)counts[pairs[p].j];
+  }
+  const int64_t E = eoff[np], B = boff[np];
+  DevBuf<int64_t> d_eoff, d_boff;
+  DevBuf<int32_t> d_qoff, d_toff, d_tcnt, d_count, fb;
+  DevBuf<uint32_t> i2, idx2, matches;
+  DevBuf<float> dd, d1, d2;
+  DevBuf<unsigned long long> best, keys, winners;
+  DevBuf<double> metric;
+  APS_TRY(d_eoff.alloc(np + 1, s));
+  APS_TRY(d_boff.alloc(np + 1, s));
+  APS_TRY(d_qoff.alloc(np, s));
+  APS_TRY(d_toff.alloc(np, s));
+  APS_TRY(d_tcnt.alloc(np, s));
+  APS_TRY(d_count.alloc(np, s));
+  APS_TRY(i2.alloc((size_t)E * 2, s));
+  APS_TRY(dd.alloc((size_t)E * 2, s));
+  APS_TRY(idx2.alloc((size_t)E, s));
+  APS_TRY(d1.alloc((size_t)E, s));
+  APS_TRY(d2.alloc((size_t)E, s));
+  APS_TRY(best.alloc((size_t)B, s));
+  APS_TRY(keys.alloc((size_t)E, s));
+  APS_TRY(winners.alloc((size_t)E, s));
+  APS_TRY(matches.alloc((size_t)E * 2, s));
+  APS_TRY(metric.alloc((size_t)E, s));
+  APS_CUDA(cudaMemcpyAsync(d_eoff.p, eoff.data(), (np + 1) * 8, cudaMemcpyHostToDevice, s));
+  APS_CUDA(cudaMemcpyAsync(d_boff.p, boff.data(), (np + 1) * 8, cudaMemcpyHostToDevice, s));
+  APS_CUDA(cudaMemcpyAsync(d_qoff.p, qoff.data(), np * 4, cudaMemcpyHostToDevice, s));
+  APS_CUDA(cudaMemcpyAsync(d_toff.p, toff.data(), np * 4, cudaMemcpyHostToDevice, s));
+  APS_CUDA(cudaMemcpyAsync(d_tcnt.p, tcnt.data(), np * 4, cudaMemcpyHostToDevice, s));
+  aps_pair_tables pt;
+  pt.eoff = d_eoff.p; pt.qoff = d_qoff.p; pt.toff = d_toff.p; pt.tcnt = d_tcnt.p; pt.boff = d_boff.p; pt.npairs = np;
+
+  if (dtype == APS_U8) {
+    APS_TRY(aps_k_pairs_hamming2(s, ps.u8pad.p, ps.nb16, eoff, qoff, toff, tcnt, i2.p, dd.p));
+    APS_TRY(aps_k_pairs_k2_to_nn(s, pt, E, 1, D, i2.p, dd.p, idx2.p, d1.p, d2.p));
+    APS_TRY(aps_k_pairs_filter_unique(s, pt, E, B, idx2.p, d1.p, d2.p, 1, D * 8, match_threshold, max_ratio, best.p,
+                                      keys.p, winners.p, d_count.p, matches.p, metric.p));
+  } else {
+    FloatSet& S = norm ? ps.normset : ps.rawset;
+    const FloatSide side = S.side();
+    const int bias_mode = norm ? 0 : 1;
+    c->stats[0] += E;
+    if (tensor) {
+      c->stats[2] = 2;
+      std::vector<aps_tc_unit> units;
+      for (int p = 0; p < np; ++p) {
+        const int64_t nq = eoff[p + 1] - eoff[p];
+        for (int64_t b0 = 0; b0 < nq; b0 += 256) {
+          aps_tc_unit u;
+          u.qrow0 = (int32_t)(qoff[p] + b0);
+          u.qend = (int32_t)(qoff[p] + nq);
+          u.t0 = toff[p];
+          u.t1 = toff[p] + tcnt[p];
+          u.out_row = eoff[p] + b0;
+          units.push_back(u);
+        }
+      }
+      DevBuf<aps_tc_unit> d_units;
+      DevBuf<uint32_t> cidx;
+      DevBuf<float> cscore;
+      APS_TRY(d_units.alloc(units.size(), s));
+      APS_TRY(cidx.alloc((size_t)E * 8, s));
+      APS_TRY(cscore.alloc((size_t)E * 8, s));
+      APS_TRY(fb.alloc((size_t)E + 1, s));
+      APS_CUDA(cudaMemsetAsync(fb.p + E, 0, sizeof(int32_t), s));
+      APS_CUDA(cudaMemcpyAsync(d_units.p, units.data(), units.size() * sizeof(aps_tc_unit), cudaMemcpyHostToDevice, s));
+      APS_CUDA(cudaStreamSynchronize(s));  // host tables are pageable
+      aps_tc_problem tp;
+      tp.Qb = side.xb; tp.Tb = side.xb; tp.colscale = side.colscale; tp.colbias = side.colbias; tp.bias = bias_mode;
+      tp.Fq_total = side.N; tp.Ft_total = side.N; tp.Dp = (D + 63) / 64 * 64;
+      tp.q0 = 0; tp.q1 = 0; tp.t0 = 0; tp.t1 = 0; tp.nslot = 1; tp.kcand = 8;
+      tp.cand_idx = cidx.p; tp.cand_score = cscore.p; tp.dump = nullptr;
+      APS_TRY(aps_k_knn_tc_units(s, c->sm_count, tp, d_units.p, (int64_t)units.size()));
+      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, /*metric*/ 1, 0, E, 0, 1, 8, cidx.p,
+                           cscore.p, S.flags.p, bias_mode, S.flags.p, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &pt));
+      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, 1, pt, fb.p, fb.p + E, E, i2.p, dd.p));
+      APS_CUDA(cudaMemcpyAsync(c->h_flags + 33, fb.p + E, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    } else {
+      c->stats[2] = 1;
+      APS_CUDA(cudaStreamSynchronize(s));
+      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, 1, pt, nullptr, nullptr, E, i2.p, dd.p));
+    }
+    APS_TRY(aps_k_pairs_k2_to_nn(s, pt, E, 0, 0, i2.p, dd.p, idx2.p, d1.p, d2.p));
+    APS_TRY(aps_k_pairs_filter_unique(s, pt, E, B, idx2.p, d1.p, d2.p, 0, 0, match_threshold, max_ratio, best.p, keys.p,
+                                      winners.p, d_count.p, matches.p, metric.p));
+  }
+  // results -> host (regions are compacted on the device first)
+  std::vector<int32_t> hc(np);
+  APS_CUDA(cudaMemcpyAsync(hc.data(), d_count.p, np * 4, cudaMemcpyDeviceToHost, s));
+  APS_CUDA(cudaStreamSynchronize(s));
+  if (tensor && dtype == APS_F32) c->stats[1] += c->h_flags[33];
+  std::vector<int64_t> outoff(np + 1, 0);
+  for (int p = 0; p < np; ++p) outoff[p + 1] = outoff[p] + hc[p];
+  const int64_t M = outoff[np];
+  std::vector<uint32_t> hrows((size_t)M * 2);
+  std::vector<double> hmet((size_t)M);
+  if (M > 0) {
+    DevBuf<uint32_t> rows;
+    DevBuf<double> met;
+    DevBuf<int64_t> d_outoff;
+    APS_TRY(rows.alloc((size_t)M * 2, s));
+    APS_TRY(met.alloc((size_t)M, s));
+    APS_TRY(d_outoff.alloc(np + 1, s));
+    APS_CUDA(cudaMemcpyAsync(d_outoff.p, outoff.data(), (np + 1) * 8, cudaMemcpyHostToDevice, s));
+    k_gather_pairs<<<(unsigned)np, 128, 0, s>>>(matches.p, metric.p, d_eoff.p, d_outoff.p, rows.p, met.p);
+    APS_LAUNCHED();
+    APS_CUDA(cudaMemcpyAsync(hrows.data(), rows.p, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+    APS_CUDA(cudaMemcpyAsync(hmet.data(), met.p, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+    APS_CUDA(cudaStreamSynchronize(s));
+  }
+  for (int p = 0; p < np; ++p) {
+    const size_t o = pairs[p].ordinal;
+    out_count[o] = hc[p];
+    out_rows[o].assign(hrows.begin() + 2 * outoff[p], hrows.begin() + 2 * outoff[p + 1]);
+    out_metric[o].assign(hmet.begin() + outoff[p], hmet.begin() + outoff[p + 1]);
+  }
+  return APS_OK;
+}
+
+static int feature_matching_pairwise_impl(aps_ctx* c, const void* const* desc, const int64_t* counts, int n, int D,
+                                          int dtype, int layout, double match_threshold, double max_ratio,
+                                          int pair_first, int pair_stride, aps_matchlist** out) {
   APS_CTX(c);
   if (!out) APS_FAIL(APS_ERR_ARGS, "", "out is NULL");
   *out = nullptr;
-  if (n < 0 || (n > 0 && !counts)) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  if (n < 0 || (n > 0 && !counts) || pair_stride < 1 || pair_first < 0 || pair_first >= pair_stride)
+    APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
   if (dtype != APS_F32 && dtype != APS_U8) APS_FAIL(APS_ERR_TYPE, "", "descriptors must be single or uint8");
   c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
   aps_matchlist* m = new (std::nothrow) aps_matchlist();
@@ -1026,69 +1169,61 @@ extern "C" int aps_feature_matching_pairwise(aps_ctx* c, const void* const* desc
     *out = m;
     return APS_OK;
   }
+  if (F >= ((int64_t)1 << 31) - 512) {
+    delete m;
+    APS_FAIL(APS_ERR_ARGS, "", "more than 2^31 descriptors are not supported");
+  }
   int rc = APS_OK;
   {
-    const bool tensor = dtype == APS_F32 && tc_wanted(c, D, maxc, maxc, 2);
+    const bool tensor = dtype == APS_F32 && tc_wanted(c, D, maxc, maxc * (int64_t)n, 2);
     PairwiseSets ps;
-    // pair list in column-major cell order (featureMatchingPairwise.m:48): j outer, i < j inner
-    std::vector<int> pi, pj;
-    std::vector<int64_t> region(1, 0);
+    rc = pairwise_prepare(c, ps, desc, counts, n, D, dtype, layout, tensor);
+    // pair list in column-major cell order (featureMatchingPairwise.m:48): j outer, i < j inner; this rank's
+    // share = every pair_stride-th pair (the reference's parfor distributes the same list over workers)
+    std::vector<PairRef> all, mine_raw, mine_norm;
     for (int j = 0; j < n; ++j)
-      for (int i = 0; i < j; ++i) {
-        pi.push_back(i);
-        pj.push_back(j);
-        region.push_back(region.back() + counts[i]);
-      }
-    const size_t NP = pi.size();
-    DevBuf<uint32_t> dm, rows;
-    DevBuf<double> dmet, met;
-    DevBuf<int32_t> cnt;
-    DevBuf<int64_t> d_region, d_outoff;
-    auto A = [&](int r) { if (rc == APS_OK) rc = r; };
-    A(pairwise_prepare(c, ps, desc, counts, n, D, dtype, layout, tensor));
-    A(dm.alloc((size_t)region.back() * 2, c->stream));
-    A(dmet.alloc((size_t)region.back(), c->stream));
-    A(cnt.alloc(NP, c->stream));
-    for (size_t p = 0; p < NP && rc == APS_OK; ++p)
-      rc = pair_device(c, ps, pi[p], pj[p], counts, D, dtype, match_threshold, max_ratio, 1, tensor,
-                       dm.p + 2 * region[p], dmet.p + region[p], cnt.p + p);
-    std::vector<int32_t> hc(NP, 0);
-    if (rc == APS_OK && cudaMemcpyAsync(hc.data(), cnt.p, NP * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = APS_ERR_CUDA;
-    if (rc == APS_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = APS_ERR_CUDA;
-    if (rc == APS_OK) {
-      std::vector<int64_t> outoff(NP + 1, 0);
-      for (size_t p = 0; p < NP; ++p) outoff[p + 1] = outoff[p] + hc[p];
-      m->total = outoff[NP];
-      // CSR over all n*n cells
-      size_t p = 0;
-      for (int j = 0; j < n; ++j)
-        for (int i = 0; i < n; ++i) {
-          size_t cell = (size_t)i + (size_t)j * n;
-          int64_t add = 0;
-          if (i < j) add = hc[p++];
-          m->pair_ptr[cell + 1] = m->pair_ptr[cell] + add;
-        }
-      m->rows.resize((size_t)m->total * 2);
-      m->metric.resize((size_t)m->total);
-      if (m->total > 0) {
-        A(rows.alloc((size_t)m->total * 2, c->stream));
-        A(met.alloc((size_t)m->total, c->stream));
-        A(d_region.alloc(NP + 1, c->stream));
-        A(d_outoff.alloc(NP + 1, c->stream));
-        if (rc == APS_OK) {
-          cudaMemcpyAsync(d_region.p, region.data(), (NP + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-          cudaMemcpyAsync(d_outoff.p, outoff.data(), (NP + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-          k_gather_pairs<<<(unsigned)NP, 128, 0, c->stream>>>(dm.p, dmet.p, d_region.p, d_outoff.p, rows.p, met.p);
-          cudaMemcpyAsync(m->rows.data(), rows.p, (size_t)m->total * 8, cudaMemcpyDeviceToHost, c->stream);
-          cudaMemcpyAsync(m->metric.data(), met.p, (size_t)m->total * 8, cudaMemcpyDeviceToHost, c->stream);
-          if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-            aps_set_error(APS_ERR_CUDA, "", "pairwise gather failed");
-            rc = APS_ERR_CUDA;
-          }
-        }
+      for (int i = 0; i < j; ++i) all.push_back(PairRef{i, j, all.size()});
+    const size_t NP = all.size();
+    for (size_t o = 0; o < NP; ++o) {
+      if ((int)(o % (size_t)pair_stride) != pair_first) continue;
+      const PairRef& pr = all[o];
+      if (counts[pr.i] == 0 || counts[pr.j] == 0) continue;  // matchFeaturesScratch.m:84-88
+      const bool norm = dtype == APS_F32 && (ps.big[pr.i] || ps.big[pr.j]);  // :105-110 is a per-pair decision
+      (norm ? mine_norm : mine_raw).push_back(pr);
+    }
+    std::vector<int32_t> cnt(NP, 0);
+    std::vector<std::vector<uint32_t>> prow(NP);
+    std::vector<std::vector<double>> pmet(NP);
+    const int64_t ENTRY_BUDGET = (int64_t)1 << 25;  // entries per batch: bounds the candidate buffers to ~2 GB
+    for (int g = 0; g < 2 && rc == APS_OK; ++g) {
+      const std::vector<PairRef>& grp = g ? mine_norm : mine_raw;
+      size_t a = 0;
+      while (a < grp.size() && rc == APS_OK) {
+        size_t b = a;
+        int64_t e = 0;
+        while (b < grp.size() && (b == a || e + counts[grp[b].i] <= ENTRY_BUDGET)) e += counts[grp[b++].i];
+        std::vector<PairRef> batch(grp.begin() + a, grp.begin() + b);
+        rc = pairwise_batch(c, ps, batch, counts, D, dtype, g == 1, tensor, match_threshold, max_ratio, cnt, prow, pmet);
+        a = b;
       }
     }
-    c->stats[1] = c->h_flags[32];
+    if (rc == APS_OK) {
+      size_t o = 0;
+      for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+          const size_t cell = (size_t)i + (size_t)j * n;
+          int64_t add = 0;
+          if (i < j) add = cnt[o++];
+          m->pair_ptr[cell + 1] = m->pair_ptr[cell] + add;
+        }
+      m->total = m->pair_ptr[cells];
+      m->rows.reserve((size_t)m->total * 2);
+      m->metric.reserve((size_t)m->total);
+      for (size_t q = 0; q < NP; ++q) {
+        m->rows.insert(m->rows.end(), prow[q].begin(), prow[q].end());
+        m->metric.insert(m->metric.end(), pmet[q].begin(), pmet[q].end());
+      }
+    }
   }
   if (rc != APS_OK) {
     delete m;
@@ -1096,6 +1231,20 @@ extern "C" int aps_feature_matching_pairwise(aps_ctx* c, const void* const* desc
   }
   *out = m;
   return APS_OK;
+}
+
+extern "C" int aps_feature_matching_pairwise(aps_ctx* c, const void* const* desc, const int64_t* counts, int n,
+                                             int D, int dtype, int layout, double match_threshold, double max_ratio,
+                                             aps_matchlist** out) {
+  return feature_matching_pairwise_impl(c, desc, counts, n, D, dtype, layout, match_threshold, max_ratio, 0, 1, out);
+}
+
+extern "C" int aps_feature_matching_pairwise_shard(aps_ctx* c, const void* const* desc, const int64_t* counts, int n,
+                                                   int D, int dtype, int layout, double match_threshold,
+                                                   double max_ratio, int pair_first, int pair_stride,
+                                                   aps_matchlist** out) {
+  return feature_matching_pairwise_impl(c, desc, counts, n, D, dtype, layout, match_threshold, max_ratio, pair_first,
+                                        pair_stride, out);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -118,6 +118,12 @@ int aps_k_knn_hamming(cudaStream_t s, const uint8_t* Q, int64_t q0, int64_t nq, 
                       int64_t t1, int nb, int k, int64_t out_row0, uint32_t* idx, float* dist);
 
 // K2 aps_knn_tc.cu : tcgen05 candidate search.  See the file header.
+struct aps_tc_unit {  // explicit work unit of the batched launch
+  int32_t qrow0;    // first query row (global) of a block of up to 256 rows
+  int32_t qend;     // one past the last query row that belongs to the unit
+  int32_t t0, t1;   // train rows searched
+  int64_t out_row;  // row of qrow0 in the candidate buffers
+};
 struct aps_tc_problem {
   const __nv_bfloat16* Qb;  // [Fq_total x Dp] query operands
   const __nv_bfloat16* Tb;  // [Ft_total x Dp] train operands
@@ -135,10 +141,23 @@ struct aps_tc_problem {
   float* dump;          // optional [ (q1-q0) x (t1-t0) ] raw scores (tests only), else nullptr
 };
 int aps_k_knn_tc_supported(int Dp);
+int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, const aps_tc_unit* d_units,
+                       int64_t n_units);
 int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1);  // candidate lists per row for this problem
 // ev0/ev1 (optional): recorded immediately before / after the candidate kernel itself
 int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEvent_t ev0 = nullptr,
                  cudaEvent_t ev1 = nullptr);
+
+// batched pairwise bookkeeping: entry e of pair p (eoff[p] <= e < eoff[p+1]) is query row qoff[p] + e - eoff[p]
+// searched in train rows [toff[p], toff[p] + tcnt[p])
+struct aps_pair_tables {
+  const int64_t* eoff;   // [npairs + 1] entry offsets
+  const int32_t* qoff;   // [npairs] first global row of the query image
+  const int32_t* toff;   // [npairs] first global row of the train image
+  const int32_t* tcnt;   // [npairs] rows of the train image
+  const int64_t* boff;   // [npairs + 1] offsets into per-train-row scratch (sum of tcnt)
+  int npairs;
+};
 
 // K3 aps_rerank.cu : exact FP32 re-rank of the candidates + completeness proof.
 //   approx distance of a score: alpha[row] + beta[row]*score ; row proven iff
@@ -148,7 +167,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const float* sqT, int D, int metric, int64_t q0, int64_t nq, int64_t t0, int nseg, int kcand,
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
-                 int32_t* fb_count);
+                 int32_t* fb_count, const aps_pair_tables* pairs = nullptr);
 
 // K5 aps_filter.cu
 int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, int k, int64_t q0, int64_t q1,
@@ -172,3 +191,17 @@ int aps_k_pair_filter_unique(cudaStream_t s, const uint32_t* idx2, const float* 
 
 // K6 aps_select.cu
 int aps_k_select_partners(cudaStream_t s, const int64_t* counts_cm, int n, int m, uint8_t* cand_cm);
+
+// aps_pairwise.cu : batched pairwise stages (see the file header)
+int aps_k_pair_exact2(cudaStream_t s, const float* X, const float* sq, int D, int metric, const aps_pair_tables& pt,
+                      const int32_t* rows, const int32_t* nrows_dev, int64_t n_entries, uint32_t* idx, float* dist);
+int aps_k_pairs_hamming2(cudaStream_t s, const uint8_t* Xpad, int nb16, const std::vector<int64_t>& eoff,
+                         const std::vector<int32_t>& qoff, const std::vector<int32_t>& toff,
+                         const std::vector<int32_t>& tcnt, uint32_t* idx, float* dist);
+int aps_k_pairs_k2_to_nn(cudaStream_t s, const aps_pair_tables& pt, int64_t E, int is_binary, int nb, const uint32_t* i2,
+                         const float* dd, uint32_t* idx2, float* d1, float* d2);
+int aps_k_pairs_filter_unique(cudaStream_t s, const aps_pair_tables& pt, int64_t E, int64_t Btotal,
+                              const uint32_t* idx2, const float* d1, const float* d2, int is_binary, int nbits,
+                              double match_threshold, double max_ratio, unsigned long long* best,
+                              unsigned long long* keys, unsigned long long* winners, int32_t* count, uint32_t* matches,
+                              double* metric);

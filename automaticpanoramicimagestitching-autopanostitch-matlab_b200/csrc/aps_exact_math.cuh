@@ -1,0 +1,50 @@
+// aps_exact_math.cuh -- the oracle's float operation orders as device functions (explicit _rn
+// intrinsics: no FMA contraction), shared by the re-rank and the pairwise fallback kernels.
+#pragma once
+#include <math_constants.h>
+
+#include "aps_common.cuh"
+
+__device__ __forceinline__ float l2sq_flann(const float* __restrict__ a, const float* __restrict__ b, int D) {
+  float result = 0.f;
+  int d = 0;
+  for (; d + 3 < D; d += 4) {
+    float4 x, y;
+    if ((D & 3) == 0) {
+      x = *reinterpret_cast<const float4*>(a + d);
+      y = *reinterpret_cast<const float4*>(b + d);
+    } else {
+      x = make_float4(a[d], a[d + 1], a[d + 2], a[d + 3]);
+      y = make_float4(b[d], b[d + 1], b[d + 2], b[d + 3]);
+    }
+    float e0 = __fsub_rn(x.x, y.x), e1 = __fsub_rn(x.y, y.y), e2 = __fsub_rn(x.z, y.z), e3 = __fsub_rn(x.w, y.w);
+    float s = __fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1));
+    s = __fadd_rn(s, __fmul_rn(e2, e2));
+    s = __fadd_rn(s, __fmul_rn(e3, e3));
+    result = __fadd_rn(result, s);
+  }
+  for (; d < D; ++d) {
+    float e0 = __fsub_rn(a[d], b[d]);
+    result = __fadd_rn(result, __fmul_rn(e0, e0));
+  }
+  return result;
+}
+
+__device__ __forceinline__ float ssd_seq(const float* __restrict__ a, const float* __restrict__ b, int D, float a2,
+                                         float b2) {
+  float g = 0.f;
+  for (int d = 0; d < D; ++d) g = __fadd_rn(g, __fmul_rn(a[d], b[d]));
+  return __fsub_rn(__fadd_rn(a2, b2), __fmul_rn(2.0f, g));
+}
+
+// error bound of the approximate distance; flags: [0] operands exact in bf16, [1] bits of max|sq-1|,
+// [2] bits of max sq.  See DESIGN.md "Exactness of the tensor-core search".
+__device__ __forceinline__ float eps_bound(const int32_t* __restrict__ flags, int bias_mode) {
+  const bool exact = flags[0] != 0;
+  const float dev = __int_as_float(flags[1]);
+  const float maxsq = fmaxf(__int_as_float(flags[2]), 1.0f);
+  const float slop = 1.0e-4f * maxsq;                     // fp32 evaluation-order differences
+  const float bf = exact ? 0.0f : 7.9e-3f * maxsq;        // 2 * 2^-8 * (1+2^-9)^2 * |a||b|
+  return bias_mode ? (slop + bf) : (slop + bf + dev);     // normalised rows: |sq_b - 1| <= dev is ignored by the score
+}
+

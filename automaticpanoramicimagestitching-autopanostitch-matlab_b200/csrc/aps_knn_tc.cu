@@ -220,26 +220,39 @@ struct KParams {
   uint32_t* cand_idx;
   float* cand_score;
   float* dump;
+  const aps_tc_unit* unit_table;  // batched (pairwise) mode: explicit units, one list per row; else nullptr
+  int64_t n_table_units;
 };
 
 struct Unit {
-  int64_t rb2;     // index of the 256-row query block pair
-  int64_t tl, th;  // tile range
-  int seg;         // candidate list this unit fills
-  bool full;       // spans all tiles: also clears the row's unused lists
+  int64_t qrow0;     // first query row (global) of the unit's 256-row block pair
+  int64_t qend;      // rows >= qend are not the unit's (next image / end of range): computed, not stored
+  int64_t t0, t1;    // train rows searched (columns outside are masked)
+  int64_t out_row;   // candidate-buffer row of qrow0
+  int64_t tl, th;    // tile range
+  int seg;           // candidate list this unit fills
+  bool full;         // spans all tiles: also clears the row's unused lists
 };
 __device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
   Unit x;
+  if (P.unit_table) {
+    const aps_tc_unit t = P.unit_table[u];
+    x.qrow0 = t.qrow0; x.qend = t.qend; x.t0 = t.t0; x.t1 = t.t1; x.out_row = t.out_row;
+    x.tl = t.t0 / TN; x.th = (t.t1 + TN - 1) / TN; x.seg = 0; x.full = true;
+    return x;
+  }
+  int64_t rb2;
   if (u < P.units_full) {
-    x.rb2 = u; x.tl = P.tile_lo; x.th = P.tile_hi; x.seg = 0; x.full = true;
+    rb2 = u; x.tl = P.tile_lo; x.th = P.tile_hi; x.seg = 0; x.full = true;
   } else {
     const int64_t v = u - P.units_full;
     x.seg = (int)(v / P.tail_units);                 // segment-major: neighbours share B tiles in L2
-    x.rb2 = P.units_full + (v % P.tail_units);
+    rb2 = P.units_full + (v % P.tail_units);
     x.tl = P.tile_lo + (int64_t)x.seg * P.tiles_per_seg;
     x.th = min(P.tile_hi, x.tl + P.tiles_per_seg);
     x.full = false;
   }
+  x.qrow0 = P.q0 + rb2 * RB * TM; x.qend = P.q1; x.t0 = P.t0; x.t1 = P.t1; x.out_row = rb2 * RB * TM;
   return x;
 }
 
@@ -259,7 +272,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksl = P.dp / KSLAB;   // 128-byte K slabs per operand row
   const int kst = P.dp / 16;      // UMMA K steps per tile
-  const int64_t num_units = (int64_t)P.units_full + (int64_t)P.tail_units * P.tail_seg;
+  const int64_t num_units = P.unit_table ? P.n_table_units : (int64_t)P.units_full + (int64_t)P.tail_units * P.tail_seg;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], RB); }
@@ -290,7 +303,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         for (int r = 0; r < RB; ++r)
           for (int s = 0; s < ksl; ++s)
             tma_load_2d(smem_a + r * a_bytes + s * (TM * 128), &map_q, s * KSLAB,
-                        (int)(P.q0 + (x.rb2 * RB + r) * TM), &bars->a_full);
+                        (int)(x.qrow0 + r * TM), &bars->a_full);
         aph ^= 1;
         for (int64_t t = x.tl; t < x.th; ++t) {
           mbar_wait_backoff(&bars->cs_empty[cs], cph ^ 1);
@@ -354,7 +367,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     uint32_t tcount = 0;  // tiles consumed so far (same sequence as the MMA warp's)
     for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
       const Unit x = get_unit(P, u);
-      const int64_t qrow = P.q0 + (x.rb2 * RB + grp) * TM + row_in_tile;
+      const int64_t qrow = x.qrow0 + grp * TM + row_in_tile;
       // row-private top-KC (unsorted; aps_rerank.cu orders exactly): scores in registers, train rows in smem
       float bv[KC];
 #pragma unroll
@@ -372,7 +385,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         tc_fence_after();
         const uint32_t cscale = smem_u32(smem_cs + cs * 2 * TN + ch * CG);
         const int64_t col0 = t * TN + ch * CG;
-        const bool partial = (col0 < P.t0) || (col0 + CG > P.t1);
+        const bool partial = (col0 < x.t0) || (col0 + CG > x.t1);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * TN + ch * CG;
         float va[32], vb[32];
         if (CSPLIT == 1) {  // two warps per sub-partition: double-buffer the TMEM loads
@@ -413,7 +426,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int64_t col = col0 + c * 32 + j;
-                const bool ok = col >= P.t0 && col < P.t1;
+                const bool ok = col >= x.t0 && col < x.t1;
                 if (DUMP && ok && qrow < P.q1) P.dump[(qrow - P.q0) * (P.t1 - P.t0) + (col - P.t0)] = cur[j];
                 if (!ok) cur[j] = -CUDART_INF_F;
               }
@@ -462,8 +475,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           mbar_arrive(&bars->cs_empty[cs]);
         }
       }
-      if (qrow < P.q1) {
-        const int64_t o = ((qrow - P.q0) * P.nslot + x.seg * CSPLIT + ch) * KC;
+      if (qrow < x.qend) {
+        const int64_t o = ((x.out_row + grp * TM + row_in_tile) * P.nslot + x.seg * CSPLIT + ch) * KC;
 #pragma unroll
         for (int i = 0; i < KC; ++i) {
           P.cand_idx[o + i] = lds_u32(si + i * SLOT_STRIDE);
@@ -590,6 +603,8 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.cand_idx = p.cand_idx;
   P.cand_score = p.cand_score;
   P.dump = p.dump;
+  P.unit_table = nullptr;
+  P.n_table_units = 0;
   // every (row, list) slot is written by exactly one work unit (full-width units clear the unused lists)
   const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
                       (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * CSPLIT * KC * TM * 4 + sizeof(Barriers);
@@ -607,5 +622,41 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
     APS_TRY(p.bias ? launch(k_knn_tc<true, false>) : launch(k_knn_tc<false, false>));
   APS_LAUNCHED();
   if (ev1) APS_CUDA(cudaEventRecord(ev1, s));
+  return APS_OK;
+}
+
+// Batched (pairwise) launch: explicit work units, e.g. one per (256-row block of image i, image j).
+// One candidate list of 8 per row at candidate-buffer row (unit.out_row + row offset).
+int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, const aps_tc_unit* d_units,
+                       int64_t n_units) {
+  if (!aps_k_knn_tc_supported(p.Dp)) {
+    aps_set_error(APS_ERR_DIM, "", "tcgen05 path supports padded descriptor lengths 64 and 128 (got %d)", p.Dp);
+    return APS_ERR_DIM;
+  }
+  if (n_units <= 0) return APS_OK;
+  CUtensorMap map_q, map_t;
+  APS_TRY(make_map(&map_q, p.Qb, p.Fq_total, p.Dp, TM));
+  APS_TRY(make_map(&map_t, p.Tb, p.Ft_total, p.Dp, TN));
+  KParams P;
+  memset(&P, 0, sizeof P);
+  P.dp = p.Dp;
+  P.nslot = 1;
+  P.colscale = p.colscale;
+  P.colbias = p.colbias;
+  P.cand_idx = p.cand_idx;
+  P.cand_score = p.cand_score;
+  P.dump = nullptr;
+  P.unit_table = d_units;
+  P.n_table_units = n_units;
+  const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
+                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * CSPLIT * KC * TM * 4 + sizeof(Barriers);
+  const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
+  auto launch = [&](auto kern) -> int {
+    APS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
+    return APS_OK;
+  };
+  APS_TRY(p.bias ? launch(k_knn_tc<true, false>) : launch(k_knn_tc<false, false>));
+  APS_LAUNCHED();
   return APS_OK;
 }

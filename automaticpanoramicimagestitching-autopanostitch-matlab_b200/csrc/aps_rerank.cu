@@ -15,51 +15,9 @@
 #include <math_constants.h>
 
 #include "aps_common.cuh"
+#include "aps_exact_math.cuh"
 
 namespace {
-
-__device__ __forceinline__ float l2sq_flann(const float* __restrict__ a, const float* __restrict__ b, int D) {
-  float result = 0.f;
-  int d = 0;
-  for (; d + 3 < D; d += 4) {
-    float4 x, y;
-    if ((D & 3) == 0) {
-      x = *reinterpret_cast<const float4*>(a + d);
-      y = *reinterpret_cast<const float4*>(b + d);
-    } else {
-      x = make_float4(a[d], a[d + 1], a[d + 2], a[d + 3]);
-      y = make_float4(b[d], b[d + 1], b[d + 2], b[d + 3]);
-    }
-    float e0 = __fsub_rn(x.x, y.x), e1 = __fsub_rn(x.y, y.y), e2 = __fsub_rn(x.z, y.z), e3 = __fsub_rn(x.w, y.w);
-    float s = __fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1));
-    s = __fadd_rn(s, __fmul_rn(e2, e2));
-    s = __fadd_rn(s, __fmul_rn(e3, e3));
-    result = __fadd_rn(result, s);
-  }
-  for (; d < D; ++d) {
-    float e0 = __fsub_rn(a[d], b[d]);
-    result = __fadd_rn(result, __fmul_rn(e0, e0));
-  }
-  return result;
-}
-
-__device__ __forceinline__ float ssd_seq(const float* __restrict__ a, const float* __restrict__ b, int D, float a2,
-                                         float b2) {
-  float g = 0.f;
-  for (int d = 0; d < D; ++d) g = __fadd_rn(g, __fmul_rn(a[d], b[d]));
-  return __fsub_rn(__fadd_rn(a2, b2), __fmul_rn(2.0f, g));
-}
-
-// error bound of the approximate distance; flags: [0] operands exact in bf16, [1] bits of max|sq-1|,
-// [2] bits of max sq.  See DESIGN.md "Exactness of the tensor-core search".
-__device__ __forceinline__ float eps_bound(const int32_t* __restrict__ flags, int bias_mode) {
-  const bool exact = flags[0] != 0;
-  const float dev = __int_as_float(flags[1]);
-  const float maxsq = fmaxf(__int_as_float(flags[2]), 1.0f);
-  const float slop = 1.0e-4f * maxsq;                     // fp32 evaluation-order differences
-  const float bf = exact ? 0.0f : 7.9e-3f * maxsq;        // 2 * 2^-8 * (1+2^-9)^2 * |a||b|
-  return bias_mode ? (slop + bf) : (slop + bf + dev);     // normalised rows: |sq_b - 1| <= dev is ignored by the score
-}
 
 // G lanes per query row (G = 8, 16 or 32 >= number of candidates): 32/G rows per warp.
 template <int G>
@@ -72,13 +30,25 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
                                                 const int32_t* __restrict__ flags, int bias_mode, int k,
                                                 int64_t out_row0, uint32_t* __restrict__ idx,
                                                 float* __restrict__ dist, int32_t* __restrict__ fb_rows,
-                                                int32_t* __restrict__ fb_count) {
+                                                int32_t* __restrict__ fb_count, aps_pair_tables pt) {
   constexpr int RPW = 32 / G;  // rows per warp
   const int lane = threadIdx.x & 31, sub = lane / G, sl = lane % G;
   const unsigned segmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
   const int64_t r = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
   const bool row_ok = r < nq;
-  const int64_t q = q0 + (row_ok ? r : 0);
+  int64_t q = q0 + (row_ok ? r : 0);
+  int64_t orow = q - out_row0;  // output row
+  if (pt.eoff) {  // batched pairwise: candidate row r is entry r of pair p: query off_i + (r - eoff[p]), train image j
+    const int64_t e = row_ok ? r : 0;
+    int lo = 0, hi = pt.npairs;  // last p with eoff[p] <= e
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (pt.eoff[mid] <= e) lo = mid; else hi = mid;
+    }
+    q = (int64_t)pt.qoff[lo] + (e - pt.eoff[lo]);
+    t0 = pt.toff[lo];
+    orow = e;
+  }
   const int ncand = nseg * kcand;
   const float eps = eps_bound(flags, bias_mode);
   const bool exact = flags[0] != 0;
@@ -129,12 +99,12 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   }
   const int nvalid = __popc(__ballot_sync(0xffffffffu, need) & segmask);
   if (need && rank < k) {
-    idx[(q - out_row0) * k + rank] = (uint32_t)((int64_t)ci - t0 + 1);
-    dist[(q - out_row0) * k + rank] = d;
+    idx[orow * k + rank] = (uint32_t)((int64_t)ci - t0 + 1);
+    dist[orow * k + rank] = d;
   }
   if (row_ok && sl >= nvalid && sl < k) {  // fewer than k neighbours exist: flann_knn.cpp:216-219
-    idx[(q - out_row0) * k + sl] = 0u;
-    dist[(q - out_row0) * k + sl] = CUDART_INF_F;
+    idx[orow * k + sl] = 0u;
+    dist[orow * k + sl] = CUDART_INF_F;
   }
   // completeness proof
   float dk = -CUDART_INF_F;  // k-th smallest exact distance (or -inf when fewer than k candidates)
@@ -152,7 +122,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   if (nan_seen) proven = false;
   if (row_ok && !proven && sl == 0) {
     int pos = atomicAdd(fb_count, 1);
-    fb_rows[pos] = (int32_t)q;
+    fb_rows[pos] = (int32_t)(pt.eoff ? orow : q);
   }
 }
 
@@ -162,13 +132,16 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const float* sqT, int D, int metric, int64_t q0, int64_t nq, int64_t t0, int nseg, int kcand,
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
-                 int32_t* fb_count) {
+                 int32_t* fb_count, const aps_pair_tables* pairs) {
   (void)exact_flag;
   if (nq == 0) return APS_OK;
   if (nseg * kcand > 32) {
     aps_set_error(APS_ERR_ARGS, "", "rerank: nseg*kcand must be <= 32");
     return APS_ERR_ARGS;
   }
+  aps_pair_tables pt;
+  memset(&pt, 0, sizeof pt);
+  if (pairs) pt = *pairs;
   const int ncand = nseg * kcand;
   if (k > 8 || k > ncand) {
     aps_set_error(APS_ERR_ARGS, "", "rerank: k must be <= min(8, candidates)");
@@ -178,7 +151,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
   k_rerank<G><<<(unsigned)aps_ceil_div(nq, 8 * (32 / G)), 256, 0, s>>>(Q, sqQ, invnQ, T, sqT, D, metric, q0, nq, t0, \
                                                                        nseg, kcand, cand_idx, cand_score, flags,     \
                                                                        bias_mode, k, out_row0, idx, dist, fb_rows,  \
-                                                                       fb_count)
+                                                                       fb_count, pt)
   if (ncand <= 8) APS_RERANK(8);
   else if (ncand <= 16) APS_RERANK(16);
   else APS_RERANK(32);

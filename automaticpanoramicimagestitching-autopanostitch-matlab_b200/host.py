@@ -167,12 +167,14 @@ def featureMatchingGlobal(input, allDescriptors, numImg, ctx=None):
     return matches
 
 
-def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metric=False):
+def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metric=False, shard=None):
     """matches = featureMatchingPairwise(input, allDescriptors, numImg)  (featureMatchingPairwise.m:1-63)
 
     Runs getMatches' matchFeaturesScratch branch (:108-117) with Method 'Exhaustive' and Unique=true
     for every i<j.  The MathWorks matchFeatures branch (input.useMATLABFeatureMatch=1) is closed
-    source and the approximate modes are out of scope: both raise."""
+    source and the approximate modes are out of scope: both raise.
+    shard=(first, stride): compute only every stride-th pair of the column-major pair list (one share
+    per GPU rank); cells of other shares come back empty and are merged by `merge_pairwise_shards`."""
     ctx = ctx or default_context()
     if not (np.isscalar(numImg) and np.isfinite(numImg) and numImg > 0):
         raise ValueError("numImg must be a positive finite scalar")
@@ -187,8 +189,9 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
         return (m, [[None] * n for _ in range(n)]) if return_metric else m
     ptrs, cnt, layout, keep = _desc_args(mats, counts)
     h = C.c_void_p()
-    check(lib().aps_feature_matching_pairwise(ctx.handle, ptrs, cnt, n, int(D), APS_U8 if is_binary else APS_F32,
-                                              layout, thr, ratio, C.byref(h)))
+    first, stride = shard if shard is not None else (0, 1)
+    check(lib().aps_feature_matching_pairwise_shard(ctx.handle, ptrs, cnt, n, int(D), APS_U8 if is_binary else APS_F32,
+                                                    layout, thr, ratio, int(first), int(stride), C.byref(h)))
     try:
         matches, metrics, _, _ = _cells_from_matchlist(h, n, want_metric=True)
     finally:
@@ -199,6 +202,20 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
             if matches[i][j].size == 0:
                 matches[i][j] = np.zeros((0, 2))
     return (matches, metrics) if return_metric else matches
+
+
+def merge_pairwise_shards(shards):
+    """Merges the per-rank results of featureMatchingPairwise(..., shard=(r, world)): every pair was computed
+    by exactly one rank, so the merge takes each cell from the rank that owns it (ordinal % world)."""
+    world = len(shards)
+    n = len(shards[0])
+    out = [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]
+    o = 0
+    for j in range(n):
+        for i in range(j):
+            out[i][j] = shards[o % world][i][j]
+            o += 1
+    return out
 
 
 def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRatio=0.6, Unique=True, ctx=None, **nv):

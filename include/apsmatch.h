@@ -128,6 +128,13 @@ int aps_feature_matching_pairwise(aps_ctx* ctx, const void* const* desc, const i
                                   int dtype, int layout, double match_threshold, double max_ratio,
                                   aps_matchlist** out);
 
+/* Multi-GPU building block of the pairwise path: computes only the image pairs whose ordinal in the
+ * column-major strict-upper-triangle list (featureMatchingPairwise.m:48) is congruent to pair_first modulo
+ * pair_stride (one share per rank, like the reference's parfor over the same list); other cells stay empty. */
+int aps_feature_matching_pairwise_shard(aps_ctx* ctx, const void* const* desc, const int64_t* counts, int n, int D,
+                                        int dtype, int layout, double match_threshold, double max_ratio,
+                                        int pair_first, int pair_stride, aps_matchlist** out);
+
 /* ---- match list: the n x n cell in CSR form ---------------------------------------------------
  * cell (i,j) (0-based, i<j) is linear index c = i + j*n (MATLAB's column-major cell index);
  * its rows are rows[2*pair_ptr[c] .. 2*pair_ptr[c+1]) interleaved (col1,col2) = (index into image i,

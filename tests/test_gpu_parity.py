@@ -264,3 +264,57 @@ def test_flann_knn_binary_k_sweep_and_widths(aps, orc):
             idx, dist = aps.flann_knn_win(T, T[:300].copy(), k, "bf")
             oi, od = orc.knn_hamming(T, T[:300], k)
             assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nb, k)
+
+
+def test_pairwise_shards_merge_to_the_full_result(aps, orc):
+    """multi-GPU pairwise: every rank computes every world-th pair; merged cells == single-GPU == oracle."""
+    desc, c = aps.synth.make_config(5, n=6, kp=500)
+    inp = {"Matchingmethod": "Exhaustive", "Matchingthreshold": 1.5, "Ratiothreshold": 0.6}
+    full = aps.featureMatchingPairwise(inp, desc, len(desc))
+    shards = [aps.featureMatchingPairwise(inp, desc, len(desc), shard=(r, 3)) for r in range(3)]
+    merged = aps.merge_pairwise_shards(shards)
+    ref = orc.feature_matching_pairwise(desc, 1.5, 0.6)
+    for j in range(6):
+        for i in range(j):
+            assert np.array_equal(full[i][j], merged[i][j])
+            exp = ref["cells"].get((i, j))
+            assert (exp is None and full[i][j].shape[0] == 0) or np.array_equal(full[i][j], exp.astype(np.float64))
+
+
+def test_pairwise_mixed_magnitudes_and_empty_images(aps, orc):
+    """matchFeaturesScratch.m:105-110 normalises a pair iff max|A|>2 or max|B|>2: a per-PAIR decision."""
+    rng = np.random.default_rng(8)
+    small = [rng.standard_normal((300, 32)).astype(np.float32) * 0.3 for _ in range(2)]
+    small = [np.clip(x, -1.9, 1.9) for x in small]
+    small[1][:100] = small[0][:100] + 0.001
+    big = [x * 50 for x in small[:1]] + [np.zeros((0, 32), np.float32)]
+    desc = [small[0], big[0], small[1], big[1]]
+    ref = orc.feature_matching_pairwise(desc, 1.5, 0.7)
+    got = aps.featureMatchingPairwise({"Matchingthreshold": 1.5, "Ratiothreshold": 0.7}, desc, 4)
+    for j in range(4):
+        for i in range(j):
+            exp = ref["cells"].get((i, j))
+            if exp is None:
+                assert got[i][j].shape == (0, 2)
+            else:
+                assert np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
+
+
+def test_pairwise_tensor_engine_large(aps, orc):
+    ctx = aps._lib.default_context()
+    desc, c = aps.synth.make_config(5, n=5, kp=3000)
+    ctx.set_float_engine(2)
+    try:
+        got = aps.featureMatchingPairwise({"Matchingthreshold": 1.5, "Ratiothreshold": 0.7}, desc, 5)
+        stats = ctx.last_stats()
+    finally:
+        ctx.set_float_engine(0)
+    assert stats["engine"] == "tcgen05"
+    ref = orc.feature_matching_pairwise(desc, 1.5, 0.7)
+    rows = 0
+    for j in range(5):
+        for i in range(j):
+            exp = ref["cells"].get((i, j))
+            assert exp is not None and np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
+            rows += len(exp)
+    assert rows > 3000
