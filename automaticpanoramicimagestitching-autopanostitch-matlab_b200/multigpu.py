@@ -54,3 +54,16 @@ def global_matching_step(plan, ratio, rank, world, dist=None, rec=None):
     if world > 1:
         exchange_records(rec, plan.F, bounds, dist)
     plan.compact()
+
+
+def pairwise_matching_sharded(host, input, allDescriptors, numImg, rank, world, dist=None, ctx=None):
+    """featureMatchingPairwise across `world` ranks: rank r computes every world-th image pair of the
+    column-major pair list (block-cyclic, like the reference's parfor over the same list,
+    featureMatchingPairwise.m:48-59), the per-pair lists are exchanged and every rank returns the merged cell.
+    `host` is the package's host module (featureMatchingPairwise / merge_pairwise_shards)."""
+    mine = host.featureMatchingPairwise(input, allDescriptors, numImg, ctx=ctx, shard=(rank, world))
+    if world == 1:
+        return mine
+    shards = [None] * world
+    dist.all_gather_object(shards, mine)  # match lists are small next to the descriptors (8-16 B per match)
+    return host.merge_pairwise_shards(shards)
