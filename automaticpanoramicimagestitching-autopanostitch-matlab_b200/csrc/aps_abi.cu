@@ -280,10 +280,45 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   }
   APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nslot, kcand, cidx.p,
                        cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq));
-  // rows that could not be proven complete: exact search (device-side count, no host round trip)
-  APS_TRY(aps_k_knn_exact(c->stream, Q.xn, Q.sq, fb.p, fb.p + nq, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
-                          out_row0, idx, dist));
-  APS_CUDA(cudaMemcpyAsync(c->h_flags + 32, fb.p + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  // Rows that could not be proven complete (device-side list, no host round trip) get a SECOND tensor pass with
+  // 4 column segments = 32 candidates per row: with inexact (non bf16-representable) operands the error bound
+  // is ~0.016 in squared distance and 8 candidates often do not reach beyond it; 32 usually do.
+  const int nslot2 = aps_k_knn_tc_slots(c->sm_count, nq, t0, t1, /*all_segmented*/ 1);
+  DevBuf<int32_t> fb2;
+  APS_TRY(fb2.alloc((size_t)nq + 1, c->stream));
+  APS_CUDA(cudaMemsetAsync(fb2.p + nq, 0, sizeof(int32_t), c->stream));
+  if (nslot2 > nslot) {
+    DevBuf<__nv_bfloat16> qb2;
+    DevBuf<uint32_t> cidx2;
+    DevBuf<float> cscore2;
+    APS_TRY(qb2.alloc((size_t)nq * Dp, c->stream));
+    APS_TRY(cidx2.alloc((size_t)nq * nslot2 * kcand, c->stream));
+    APS_TRY(cscore2.alloc((size_t)nq * nslot2 * kcand, c->stream));
+    APS_TRY(aps_k_gather_rows(c->stream, Q.xb, Dp, fb.p, fb.p + nq, nq, qb2.p));
+    aps_tc_problem p2 = p;
+    p2.Qb = qb2.p;
+    p2.Fq_total = nq;
+    p2.q0 = 0;
+    p2.q1 = nq;
+    p2.nslot = nslot2;
+    p2.cand_idx = cidx2.p;
+    p2.cand_score = cscore2.p;
+    p2.nrows_dev = fb.p + nq;
+    APS_TRY(aps_k_knn_tc(c->stream, c->sm_count, p2, nullptr, nullptr));
+    APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nslot2, kcand, cidx2.p,
+                         cscore2.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb2.p, fb2.p + nq, nullptr,
+                         fb.p, fb.p + nq));
+    // still unproven: exact CUDA-core search
+    APS_TRY(aps_k_knn_exact(c->stream, Q.xn, Q.sq, fb2.p, fb2.p + nq, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
+                            out_row0, idx, dist));
+    APS_CUDA(cudaMemcpyAsync(c->h_flags + 32, fb2.p + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    APS_CUDA(cudaMemcpyAsync(c->h_flags + 34, fb.p + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    APS_TRY(aps_k_knn_exact(c->stream, Q.xn, Q.sq, fb.p, fb.p + nq, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
+                            out_row0, idx, dist));
+    APS_CUDA(cudaMemcpyAsync(c->h_flags + 32, fb.p + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    APS_CUDA(cudaMemcpyAsync(c->h_flags + 34, fb.p + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
   return APS_OK;
 }
 

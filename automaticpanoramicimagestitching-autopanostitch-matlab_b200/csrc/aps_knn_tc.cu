@@ -222,6 +222,8 @@ struct KParams {
   float* dump;
   const aps_tc_unit* unit_table;  // batched (pairwise) mode: explicit units, one list per row; else nullptr
   int64_t n_table_units;
+  const int32_t* nrows_dev;       // second-pass mode: the query matrix holds *nrows_dev gathered rows (device-side
+                                  // count); every unit is split into tail_seg column segments
 };
 
 struct Unit {
@@ -258,11 +260,11 @@ __device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
 
 template <bool BIAS, bool DUMP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const KParams P) {
+k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const KParams Pin) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16-byte aligned: align by hand
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int a_bytes = TM * P.dp * 2, b_bytes = TN * P.dp * 2;
+  const int a_bytes = TM * Pin.dp * 2, b_bytes = TN * Pin.dp * 2;
   uint8_t* smem_a = smem;                                      // RB x a_bytes (both row blocks of the unit)
   uint8_t* smem_b = smem_a + RB * a_bytes;                     // NUM_B_STAGES x b_bytes
   float* smem_cs = (float*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x {TN scales, TN biases}
@@ -270,8 +272,15 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   Barriers* bars = (Barriers*)(smem_topi + RB * CSPLIT * KC * TM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ksl = P.dp / KSLAB;   // 128-byte K slabs per operand row
-  const int kst = P.dp / 16;      // UMMA K steps per tile
+  const int ksl = Pin.dp / KSLAB;   // 128-byte K slabs per operand row
+  const int kst = Pin.dp / 16;      // UMMA K steps per tile
+  KParams P = Pin;
+  if (P.nrows_dev) {  // device-side row count (rows gathered by aps_k_gather_rows): all units segmented
+    const int64_t n = *P.nrows_dev;
+    P.q1 = P.q0 + n;
+    P.units_full = 0;
+    P.tail_units = (int)((n + RB * TM - 1) / (RB * TM));
+  }
   const int64_t num_units = P.unit_table ? P.n_table_units : (int64_t)P.units_full + (int64_t)P.tail_units * P.tail_seg;
 
   if (threadIdx.x == 0) {
@@ -545,8 +554,19 @@ struct TcSchedule {
   int units_full, tail_units, tail_seg, nslot, tiles_per_seg;
   int64_t tile_lo, tile_hi;
 };
-static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1) {
+static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1, bool all_segmented = false) {
   TcSchedule sc;
+  if (all_segmented) {
+    sc.tile_lo = t0 / TN;
+    sc.tile_hi = aps_ceil_div(t1, TN);
+    const int64_t tiles = sc.tile_hi - sc.tile_lo;
+    sc.units_full = 0;
+    sc.tail_units = (int)aps_ceil_div(nq, (int64_t)RB * TM);
+    sc.tail_seg = (int)(tiles < MAX_SEG ? (tiles < 1 ? 1 : tiles) : MAX_SEG);
+    sc.nslot = sc.tail_seg * CSPLIT;
+    sc.tiles_per_seg = (int)aps_ceil_div(tiles, sc.tail_seg);
+    return sc;
+  }
   sc.tile_lo = t0 / TN;
   sc.tile_hi = aps_ceil_div(t1, TN);
   const int64_t tiles = sc.tile_hi - sc.tile_lo;
@@ -566,8 +586,8 @@ static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1
   sc.tiles_per_seg = (int)aps_ceil_div(tiles, sc.tail_seg);
   return sc;
 }
-int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1) {
-  return make_schedule(sm_count, nq, t0, t1).nslot;
+int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1, int all_segmented) {
+  return make_schedule(sm_count, nq, t0, t1, all_segmented != 0).nslot;
 }
 
 int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEvent_t ev0, cudaEvent_t ev1) {
@@ -580,7 +600,7 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
     return APS_ERR_ARGS;
   }
   if (p.q1 <= p.q0 || p.t1 <= p.t0) return APS_OK;
-  const TcSchedule sc = make_schedule(sm_count, p.q1 - p.q0, p.t0, p.t1);
+  const TcSchedule sc = make_schedule(sm_count, p.q1 - p.q0, p.t0, p.t1, p.nrows_dev != nullptr);
   if (p.nslot != sc.nslot) {
     aps_set_error(APS_ERR_ARGS, "", "candidate buffers must be sized with aps_k_knn_tc_slots (%d != %d)", p.nslot, sc.nslot);
     return APS_ERR_ARGS;
@@ -605,11 +625,18 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.dump = p.dump;
   P.unit_table = nullptr;
   P.n_table_units = 0;
+  P.nrows_dev = p.nrows_dev;
+  if (p.nrows_dev) {  // second pass: every unit in MAX_SEG column segments (more candidate lists per row)
+    P.units_full = 0;
+    P.tail_units = (int)aps_ceil_div(p.q1 - p.q0, (int64_t)RB * TM);
+    P.tail_seg = sc.tail_seg;
+    P.tiles_per_seg = sc.tiles_per_seg;
+  }
   // every (row, list) slot is written by exactly one work unit (full-width units clear the unused lists)
   const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
                       (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * CSPLIT * KC * TM * 4 + sizeof(Barriers);
   const int64_t units = (int64_t)sc.units_full + (int64_t)sc.tail_units * sc.tail_seg;
-  const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);
+  const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);  // upper bound in second-pass mode
   if (ev0) APS_CUDA(cudaEventRecord(ev0, s));
   auto launch = [&](auto kern) -> int {
     APS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -622,6 +649,26 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
     APS_TRY(p.bias ? launch(k_knn_tc<true, false>) : launch(k_knn_tc<false, false>));
   APS_LAUNCHED();
   if (ev1) APS_CUDA(cudaEventRecord(ev1, s));
+  return APS_OK;
+}
+
+// gathers the bf16 operand rows listed in rows[0 .. *nrows_dev) into a compact matrix (second-pass queries)
+__global__ void k_gather_rows(const uint4* __restrict__ src, const int32_t* __restrict__ rows,
+                              const int32_t* __restrict__ nrows_dev, int chunks, uint4* __restrict__ dst) {
+  const int64_t total = (int64_t)(*nrows_dev) * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / chunks;
+    const int c = (int)(i - r * chunks);
+    dst[i] = src[(int64_t)rows[r] * chunks + c];
+  }
+}
+int aps_k_gather_rows(cudaStream_t s, const __nv_bfloat16* src, int Dp, const int32_t* rows, const int32_t* nrows_dev,
+                      int64_t max_rows, __nv_bfloat16* dst) {
+  if (max_rows == 0) return APS_OK;
+  const int chunks = Dp * 2 / 16;
+  const unsigned grid = (unsigned)aps_min64(aps_ceil_div(max_rows * chunks, 256), 148 * 8);
+  k_gather_rows<<<grid, 256, 0, s>>>((const uint4*)src, rows, nrows_dev, chunks, (uint4*)dst);
+  APS_LAUNCHED();
   return APS_OK;
 }
 
@@ -639,6 +686,7 @@ int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, co
   APS_TRY(make_map(&map_t, p.Tb, p.Ft_total, p.Dp, TN));
   KParams P;
   memset(&P, 0, sizeof P);
+  P.nrows_dev = nullptr;
   P.dp = p.Dp;
   P.nslot = 1;
   P.colscale = p.colscale;

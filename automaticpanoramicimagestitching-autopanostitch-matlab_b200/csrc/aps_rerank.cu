@@ -30,13 +30,16 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
                                                 const int32_t* __restrict__ flags, int bias_mode, int k,
                                                 int64_t out_row0, uint32_t* __restrict__ idx,
                                                 float* __restrict__ dist, int32_t* __restrict__ fb_rows,
-                                                int32_t* __restrict__ fb_count, aps_pair_tables pt) {
+                                                int32_t* __restrict__ fb_count, aps_pair_tables pt,
+                                                const int32_t* __restrict__ row_map,
+                                                const int32_t* __restrict__ nrows_dev) {
   constexpr int RPW = 32 / G;  // rows per warp
   const int lane = threadIdx.x & 31, sub = lane / G, sl = lane % G;
   const unsigned segmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
   const int64_t r = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
-  const bool row_ok = r < nq;
+  const bool row_ok = r < (nrows_dev ? (int64_t)(*nrows_dev) : nq);
   int64_t q = q0 + (row_ok ? r : 0);
+  if (row_map) q = row_ok ? (int64_t)row_map[r] : q0;  // second pass: candidate row r belongs to query row_map[r]
   int64_t orow = q - out_row0;  // output row
   if (pt.eoff) {  // batched pairwise: candidate row r is entry r of pair p: query off_i + (r - eoff[p]), train image j
     const int64_t e = row_ok ? r : 0;
@@ -132,7 +135,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const float* sqT, int D, int metric, int64_t q0, int64_t nq, int64_t t0, int nseg, int kcand,
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
-                 int32_t* fb_count, const aps_pair_tables* pairs) {
+                 int32_t* fb_count, const aps_pair_tables* pairs, const int32_t* row_map, const int32_t* nrows_dev) {
   (void)exact_flag;
   if (nq == 0) return APS_OK;
   if (nseg * kcand > 32) {
@@ -151,7 +154,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
   k_rerank<G><<<(unsigned)aps_ceil_div(nq, 8 * (32 / G)), 256, 0, s>>>(Q, sqQ, invnQ, T, sqT, D, metric, q0, nq, t0, \
                                                                        nseg, kcand, cand_idx, cand_score, flags,     \
                                                                        bias_mode, k, out_row0, idx, dist, fb_rows,  \
-                                                                       fb_count, pt)
+                                                                       fb_count, pt, row_map, nrows_dev)
   if (ncand <= 8) APS_RERANK(8);
   else if (ncand <= 16) APS_RERANK(16);
   else APS_RERANK(32);

@@ -28,6 +28,9 @@ CONFIGS = {
             name="C4: 50 img x 20000 kp ORB-256bit, BF Hamming k=4"),
     5: dict(kind="kaze", n=300, kp=4096, D=64, ring=30, empty=(), k=4, ratio=0.8, m=4,
             name="C5: 300 img x 4096 kp KAZE-64 f32, pairwise blocks"),
+    # not a BASELINE config: C2 with REAL-valued SIFT-like descriptors (stress test of the bf16 error bound)
+    6: dict(kind="siftf", n=20, kp=8192, D=128, ring=20, empty=(), k=4, ratio=0.8, m=4,
+            name="C2f: 20 img x 8192 kp real-valued SIFT-128 f32, global k=4"),
 }
 
 
@@ -35,11 +38,13 @@ def _unit(x):
     return x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
 
 
-def _sift_quantise(v):
+def _sift_quantise(v, integer=True):
     v = np.clip(v, 0.0, None)
     v = _unit(v)
     v = np.minimum(v, 0.2)
     v = _unit(v)
+    if not integer:   # "siftf": the same descriptor left real-valued (unit norm), as MATLAB's extractFeatures returns it
+        return v.astype(np.float32)
     return np.minimum(np.rint(512.0 * v), 255.0).astype(np.float32)
 
 
@@ -55,7 +60,7 @@ def synth_descriptors(kind, n, kp, D, seed, ring=None, empty=(), duplicates=8):
     for i in live:
         if kind == "orb":
             base[i] = rng.integers(0, 256, size=(kp, D), dtype=np.uint8)
-        elif kind == "sift":
+        elif kind in ("sift", "siftf"):
             base[i] = _unit(np.abs(rng.standard_normal((kp, D), dtype=np.float32)))
         else:
             base[i] = _unit(rng.standard_normal((kp, D), dtype=np.float32))
@@ -85,8 +90,8 @@ def synth_descriptors(kind, n, kp, D, seed, ring=None, empty=(), duplicates=8):
             out.append(np.zeros((0, D), np.uint8 if kind == "orb" else np.float32))
         elif kind == "orb":
             out.append(base[i])
-        elif kind == "sift":
-            out.append(_sift_quantise(base[i]))
+        elif kind in ("sift", "siftf"):
+            out.append(_sift_quantise(base[i], integer=(kind == "sift")))
         else:
             out.append(_unit(base[i]).astype(np.float32))
     # exact duplicates: across two images, and inside one image

@@ -158,3 +158,30 @@ def test_tensor_engine_unprovable_rows_fall_back_to_exact_search(aps, orc):
     assert stats["engine"] == "tcgen05" and stats["fallback_rows"] >= 40
     assert np.array_equal(idx, oi)
     assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+
+
+def test_tensor_engine_real_valued_sift_second_pass(aps, orc):
+    """Real-valued SIFT-like descriptors (not exact in bf16, neighbour distances tightly packed): many rows
+    cannot be proven with 8 candidates and take the second tensor pass (32 candidates), a few the exact
+    kernel; the result must still be the oracle's, bit for bit."""
+    ctx = aps._lib.default_context()
+    desc, c = aps.synth.make_config(6, n=8, kp=2048)
+    ref = orc.feature_matching_global(desc, 4, c["ratio"], return_knn=True)
+    ctx.set_float_engine(2)
+    try:
+        plan = aps.GlobalPlan(ctx, [d.shape[0] for d in desc], 128, False, 4)
+        plan.upload(desc)
+        plan.prepare()
+        plan.knn()
+        plan.filter(c["ratio"])
+        plan.compact()
+        _, _, pair_ptr, rows = plan.download()
+        idx, dist = plan.download_knn()
+        stats = ctx.last_stats()
+        plan.close()
+    finally:
+        ctx.set_float_engine(0)
+    assert stats["engine"] == "tcgen05" and not stats["bf16_exact_operands"]
+    assert np.array_equal(idx, ref["knn_idx"])
+    assert np.array_equal(dist.view(np.uint32), ref["knn_dist"].view(np.uint32))
+    assert np.array_equal(pair_ptr, ref["pair_ptr"]) and np.array_equal(rows, ref["rows"])
