@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
                                                 const int32_t* __restrict__ row_map,
                                                 const int32_t* __restrict__ nrows_dev) {
   constexpr int RPW = 32 / G;  // rows per warp
+  if (nrows_dev && (int64_t)blockIdx.x * (blockDim.x >> 5) * RPW >= (int64_t)(*nrows_dev)) return;  // second pass: short list
   const int lane = threadIdx.x & 31, sub = lane / G, sl = lane % G;
   const unsigned segmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
   const int64_t r = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
