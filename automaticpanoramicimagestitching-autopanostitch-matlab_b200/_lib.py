@@ -79,6 +79,7 @@ def lib():
         "aps_nearest2_hamming": (i32, [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
         "aps_nearest2_ssd": (i32, [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
         "aps_match_features": (i32, [vp, vp, i64, vp, i64, i32, i32, i32, dbl, dbl, i32, vp, vp, C.POINTER(i64)]),
+        "aps_match_features_bits": (i32, [vp, vp, i64, vp, i64, i32, i32, dbl, dbl, i32, vp, vp, C.POINTER(i64)]),
         "aps_feature_matching_global": (i32, [vp, pp, C.POINTER(i64), i32, i32, i32, i32, i32, dbl, i32, pp]),
         "aps_feature_matching_pairwise": (i32, [vp, pp, C.POINTER(i64), i32, i32, i32, i32, dbl, dbl, pp]),
         "aps_feature_matching_pairwise_shard": (i32, [vp, pp, C.POINTER(i64), i32, i32, i32, i32, dbl, dbl, i32, i32, pp]),

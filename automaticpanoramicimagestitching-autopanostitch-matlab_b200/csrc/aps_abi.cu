@@ -1026,6 +1026,71 @@ extern "C" int aps_match_features(aps_ctx* c, const void* F1, int64_t N1, const 
 }
 
 
+// packBits (matchFeaturesScratch.m:617-646): [N x Dbits] 0/1 bytes -> [N x ceil(Dbits/8)] bytes, MSB first
+__global__ void k_pack_bits01(const uint8_t* __restrict__ bits, int64_t N, int Dbits, int nb, uint8_t* __restrict__ packed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * nb) return;
+  const int64_t r = i / nb;
+  const int byte = (int)(i - r * nb);
+  unsigned v = 0;
+  for (int b = 0; b < 8; ++b) {
+    const int col = byte * 8 + b;
+    if (col < Dbits && bits[r * Dbits + col]) v |= 1u << (7 - b);
+  }
+  packed[i] = (uint8_t)v;
+}
+
+extern "C" int aps_match_features_bits(aps_ctx* c, const uint8_t* F1, int64_t N1, const uint8_t* F2, int64_t N2,
+                                       int Dbits, int layout, double match_threshold, double max_ratio, int unique,
+                                       uint32_t* matches, double* metric, int64_t* K) {
+  APS_CTX(c);
+  if (!K) APS_FAIL(APS_ERR_ARGS, "", "K is NULL");
+  *K = 0;
+  if (N1 == 0 || N2 == 0) return APS_OK;  // matchFeaturesScratch.m:84-88
+  if (!F1 || !F2 || !matches || !metric) APS_FAIL(APS_ERR_ARGS, "", "null pointer argument");
+  if (Dbits <= 0) APS_FAIL(APS_ERR_DIM, "", "descriptor width must be positive");
+  cudaStream_t s = c->stream;
+  const int nb = (Dbits + 7) / 8, nb16 = (nb + 15) / 16 * 16;
+  DevBuf<uint8_t> bits[2], packed[2], padded[2], tmp;
+  const uint8_t* src[2] = {F1, F2};
+  const int64_t cnt[2] = {N1, N2};
+  for (int i = 0; i < 2; ++i) {
+    APS_TRY(bits[i].alloc((size_t)cnt[i] * Dbits, s));
+    APS_TRY(packed[i].alloc((size_t)cnt[i] * nb, s));
+    APS_TRY(padded[i].alloc((size_t)cnt[i] * nb16, s));
+    APS_TRY(stage_matrix(c, src[i], cnt[i], Dbits, 1, layout, bits[i].p, tmp));
+    k_pack_bits01<<<(unsigned)aps_ceil_div(cnt[i] * nb, 256), 256, 0, s>>>(bits[i].p, cnt[i], Dbits, nb, packed[i].p);
+    APS_LAUNCHED();
+    APS_TRY(pad_rows(s, packed[i].p, cnt[i], nb, nb16, padded[i].p));
+  }
+  DevBuf<uint32_t> idx2, dm;
+  DevBuf<float> d1, d2;
+  DevBuf<unsigned long long> best, keys;
+  DevBuf<double> dmet;
+  DevBuf<int32_t> count;
+  APS_TRY(idx2.alloc((size_t)N1, s));
+  APS_TRY(d1.alloc((size_t)N1, s));
+  APS_TRY(d2.alloc((size_t)N1, s));
+  APS_TRY(best.alloc((size_t)N2, s));
+  APS_TRY(keys.alloc((size_t)N1 * 2, s));
+  APS_TRY(dm.alloc((size_t)N1 * 2, s));
+  APS_TRY(dmet.alloc((size_t)N1, s));
+  APS_TRY(count.alloc(1, s));
+  APS_TRY(hamming2_device(c, padded[0].p, 0, N1, padded[1].p, 0, N2, nb, nb16, idx2.p, d1.p, d2.p));
+  APS_TRY(aps_k_pair_filter_unique(s, idx2.p, d1.p, d2.p, N1, N2, 1, /*nBits*/ Dbits, match_threshold, max_ratio, unique,
+                                   best.p, keys.p, count.p, dm.p, dmet.p));
+  int32_t hk = 0;
+  APS_CUDA(cudaMemcpyAsync(&hk, count.p, 4, cudaMemcpyDeviceToHost, s));
+  APS_CUDA(cudaStreamSynchronize(s));
+  if (hk > 0) {
+    APS_CUDA(cudaMemcpyAsync(matches, dm.p, (size_t)hk * 8, cudaMemcpyDeviceToHost, s));
+    APS_CUDA(cudaMemcpyAsync(metric, dmet.p, (size_t)hk * 8, cudaMemcpyDeviceToHost, s));
+    APS_CUDA(cudaStreamSynchronize(s));
+  }
+  *K = hk;
+  return APS_OK;
+}
+
 __global__ void k_gather_pairs(const uint32_t* __restrict__ src_m, const double* __restrict__ src_d,
                                const int64_t* __restrict__ region_off, const int64_t* __restrict__ out_off,
                                uint32_t* __restrict__ rows, double* __restrict__ metric) {

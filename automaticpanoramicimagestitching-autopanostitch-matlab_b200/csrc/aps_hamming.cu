@@ -10,11 +10,12 @@
 // loads; every thread reads the same train row (shared-memory broadcast), XOR + __popc, and keeps
 // an ascending top-K in registers (scan order is ascending train index, strict '<' => ties keep the
 // lower index, as BFMatcher and the MEX do).  Integer work on CUDA cores -- deliberately not
-// reshaped into a GEMM.  Bound: the POPC pipe (8 popc per 256-bit pair); operand bytes come from
+// reshaped into a GEMM.  Bound: POPC + LOP3 issue (carry-save adders: 5 popc + 14 lop3 per 256-bit pair); operand bytes come from
 // shared memory, HBM sees each train row once per CTA (L2-resident for F <= ~10^6 rows).
 #include <math_constants.h>
 
 #include "aps_common.cuh"
+#include "aps_hamming.cuh"
 
 namespace {
 
@@ -47,12 +48,7 @@ __global__ void __launch_bounds__(HQ) k_knn_hamming(const uint4* __restrict__ Q,
     __syncthreads();
 #pragma unroll 4
     for (int j = 0; j < nj; ++j) {
-      int h = 0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const uint4 b = ts[j * NW + w];
-        h += __popc(a[w].x ^ b.x) + __popc(a[w].y ^ b.y) + __popc(a[w].z ^ b.z) + __popc(a[w].w ^ b.w);
-      }
+      const int h = hamming_words<NW>(a, ts + j * NW);
       if (h < bd[KT - 1]) {
         bd[KT - 1] = h;
         bi[KT - 1] = (uint32_t)(j0 + j - t0 + 1);

@@ -15,6 +15,7 @@
 
 #include "aps_common.cuh"
 #include "aps_exact_math.cuh"
+#include "aps_hamming.cuh"
 
 namespace {
 
@@ -97,12 +98,7 @@ __global__ void __launch_bounds__(HQ) k_knn_hamming_tab(const uint4* __restrict_
     __syncthreads();
 #pragma unroll 4
     for (int j = 0; j < nj; ++j) {
-      int h = 0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const uint4 b = ts[j * NW + w];
-        h += __popc(a[w].x ^ b.x) + __popc(a[w].y ^ b.y) + __popc(a[w].z ^ b.z) + __popc(a[w].w ^ b.w);
-      }
+      const int h = hamming_words<NW>(a, ts + j * NW);
       if (h < b1) {  // ascending scan + strict '<' : first index attaining the minimum, second with multiplicity
         const uint32_t id = (uint32_t)(j0 + j - hb.t0 + 1);
         if (h < b0) { b1 = b0; i1 = i0; b0 = h; i0 = id; }

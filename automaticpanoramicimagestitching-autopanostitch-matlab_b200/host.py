@@ -239,11 +239,21 @@ def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRat
         if isbin(a) and isbin(b):
             if a.size == 0 or b.size == 0:
                 return np.zeros((0, 2), np.uint32), np.zeros((0,), np.float32)
-            A = np.packbits(a.astype(np.uint8), axis=1)  # packBits :617-646 (MSB first)
-            B = np.packbits(b.astype(np.uint8), axis=1)
-            is_binary = True
-            if a.shape[1] % 8:
-                raise NotImplementedError("unpacked bit widths that are not a multiple of 8")
+            if a.shape[1] != b.shape[1]:
+                raise ValueError("Descriptor dimensions must match.")
+            # unpacked 0/1 bits: packed MSB-first ON THE DEVICE (packBits :617-646), nBits = Dbits
+            A, la = _as_matrix(a.astype(np.uint8), np.uint8)
+            B, lb = _as_matrix(b.astype(np.uint8), np.uint8)
+            if la != lb:
+                A, B, la = np.ascontiguousarray(A), np.ascontiguousarray(B), APS_ROW_MAJOR
+            N1 = A.shape[0]
+            m = np.zeros((max(N1, 1), 2), np.uint32)
+            met = np.zeros(max(N1, 1), np.float64)
+            K = C.c_int64(0)
+            check(lib().aps_match_features_bits(ctx.handle, _ptr(A), N1, _ptr(B), B.shape[0], int(A.shape[1]), la,
+                                                float(MatchThreshold), float(MaxRatio), int(bool(Unique)), _ptr(m),
+                                                _ptr(met), C.byref(K)))
+            return m[:K.value].copy(), met[:K.value].copy()
         else:
             A, B, is_binary = a, b, False
     A, la = _as_matrix(A, np.uint8 if is_binary else np.float32)

@@ -114,6 +114,12 @@ int aps_match_features(aps_ctx* ctx, const void* F1, int64_t N1, const void* F2,
                        int layout, double match_threshold, double max_ratio, int unique, uint32_t* matches,
                        double* metric, int64_t* K);
 
+/* Same for UNPACKED binary descriptors (logical / 0-1 uint8 matrices [N x Dbits], matchFeaturesScratch.m:259-275):
+ * the bits are packed MSB-first on the device (packBits, :617-646) and nBits = Dbits enters the percent metric. */
+int aps_match_features_bits(aps_ctx* ctx, const uint8_t* F1, int64_t N1, const uint8_t* F2, int64_t N2, int Dbits,
+                            int layout, double match_threshold, double max_ratio, int unique, uint32_t* matches,
+                            double* metric, int64_t* K);
+
 /* ---- matches = featureMatchingGlobal(input, allDescriptors, numImg) --------------------------
  * PP/featureMatching/featureMatchingGlobal.m:1-163.  desc[i] -> image i's [counts[i] x D] matrix
  * (may be NULL when counts[i]==0).  k = input.k, ratio = input.Ratiothreshold.  use_bf is accepted

@@ -318,3 +318,21 @@ def test_pairwise_tensor_engine_large(aps, orc):
             assert exp is not None and np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
             rows += len(exp)
     assert rows > 3000
+
+
+def test_match_features_unpacked_bits_packed_on_device(aps, orc):
+    """logical / 0-1 uint8 inputs (matchFeaturesScratch.m:259-275): MSB-first packing on the GPU, nBits = Dbits
+    in the percent metric -- also for widths that are not a multiple of 8."""
+    rng = np.random.default_rng(12)
+    for Dbits in (256, 100):
+        a = (rng.random((400, Dbits)) < 0.5).astype(np.uint8)
+        b = (rng.random((500, Dbits)) < 0.5).astype(np.uint8)
+        b[:150] = a[:150] ^ (rng.random((150, Dbits)) < 0.03)
+        m, met = aps.matchFeaturesScratch(a.astype(bool), b, MatchThreshold=20.0, MaxRatio=0.8)
+        A, B = orc.pack_bits(a), orc.pack_bits(b)
+        from oracle import oracle as O
+        idx2, d1, d2 = O.nearest2_hamming(A, B)
+        om = np.zeros((400, 2), np.uint32)
+        omet = np.zeros(400)
+        K = O.lib().orc_filter_unique(idx2, d1, d2, 400, 500, 1, Dbits, 20.0, 0.8, 1, om.reshape(-1), omet)
+        assert K > 100 and np.array_equal(m, om[:K]) and np.array_equal(met, omet[:K]), Dbits
