@@ -179,8 +179,11 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
     if not (np.isscalar(numImg) and np.isfinite(numImg) and numImg > 0):
         raise ValueError("numImg must be a positive finite scalar")
     method = str(_field(input, "Matchingmethod", "Exhaustive")).lower()
-    if method != "exhaustive":
-        raise NotImplementedError("Matchingmethod='Approximate' is outside the exhaustive hot path")
+    if method not in ("exhaustive", "approximate"):
+        raise ValueError(f"Unknown Method: {method}")  # matchFeaturesScratch.m:164-165
+    # 'Approximate' (the reference's inputs.m default): binary descriptors already run the exhaustive OMP MEX
+    # there (matchFeaturesScratch.m:611, the "LSH" is a stub); for float descriptors the PCA / KD-tree /
+    # random-subset searches (:128-163) approximate exactly what the exhaustive engine returns, so it serves both.
     thr = float(_field(input, "Matchingthreshold", required=True))
     ratio = float(_field(input, "Ratiothreshold", required=True))
     n, first, mats, counts, D, is_binary = _describe(allDescriptors, numImg)
@@ -223,8 +226,8 @@ def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRat
 
     matches: [K x 2] uint32 (1-based rows of F1 / F2); matchMetric: [K x 1] (SSD, or percent Hamming)."""
     ctx = ctx or default_context()
-    if str(Method).lower() != "exhaustive":
-        raise NotImplementedError("Method='Approximate' is outside the exhaustive hot path")
+    if str(Method).lower() not in ("exhaustive", "approximate"):
+        raise ValueError(f"Unknown Method: {Method}")  # :164-165 ; 'Approximate' is served by the exact engine
     if not (MaxRatio > 0 and MaxRatio <= 1) or MatchThreshold < 0:
         raise ValueError("invalid MaxRatio / MatchThreshold")  # inputParser validators :60-62
     # normalizeInputs :237-292

@@ -276,8 +276,9 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 operands, f32 accumulate + exact f32 re-rank", "data": "synthetic",
+            "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl, "F": F, "k": KNN, "ratio": RATIO, "pairs_per_step": pairs_total,
+                       "arithmetic": "bf16 tcgen05 operands, f32 accumulate, exact f32 re-rank of the candidates",
                        "l2": "512 MB buffer written between timed steps (L2 flush)",
                        "sharding": f"query rows in {world} contiguous blocks; records exchanged by NCCL broadcast",
                        "engine": stats["engine"], "fallback_rows_last_step": stats["fallback_rows"],
@@ -312,6 +313,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.warmup = max(3, args.warmup)   # timing rule: at least 3 untimed warm-up steps
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
