@@ -214,6 +214,12 @@ struct FloatSide {          // one prepared descriptor set
   const __nv_bfloat16* xb = nullptr;  // [N x Dp] or nullptr when the tensor path is not prepared
   const float* colscale = nullptr;
   const float* colbias = nullptr;
+  // train-side view of the tensor kernel (rows possibly sorted by scale, see aps_prep.cu)
+  const __nv_bfloat16* xb_t = nullptr;
+  const float* colscale_t = nullptr;
+  const float* colbias_t = nullptr;
+  const float4* tile_bounds = nullptr;
+  const int32_t* perm = nullptr;  // sorted position -> original row (nullptr: identity)
   int64_t N = 0;
 };
 
@@ -252,9 +258,10 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   APS_CUDA(cudaMemsetAsync(fb.p + nq, 0, sizeof(int32_t), c->stream));
   aps_tc_problem p;
   p.Qb = Q.xb;
-  p.Tb = T.xb;
-  p.colscale = T.colscale;
-  p.colbias = T.colbias;
+  p.Tb = T.xb_t;
+  p.colscale = T.colscale_t;
+  p.colbias = T.colbias_t;
+  p.tile_bounds = T.tile_bounds;
   p.bias = bias_mode;
   p.Fq_total = Q.N;
   p.Ft_total = T.N;
@@ -279,7 +286,8 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
     c->tc_events.push_back(ev1);
   }
   APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nslot, kcand, cidx.p,
-                       cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq));
+                       cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq, nullptr,
+                       nullptr, nullptr, T.perm));
   // Rows that could not be proven complete (device-side list, no host round trip) get a SECOND tensor pass with
   // 4 column segments = 32 candidates per row: with inexact (non bf16-representable) operands the error bound
   // is ~0.016 in squared distance and 8 candidates often do not reach beyond it; 32 usually do.
@@ -307,7 +315,7 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
     APS_TRY(aps_k_knn_tc(c->stream, c->sm_count, p2, nullptr, nullptr));
     APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nslot2, kcand, cidx2.p,
                          cscore2.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb2.p, fb2.p + nq, nullptr,
-                         fb.p, fb.p + nq));
+                         fb.p, fb.p + nq, T.perm));
     // still unproven: exact CUDA-core search
     APS_TRY(aps_k_knn_exact(c->stream, Q.xn, Q.sq, fb2.p, fb2.p + nq, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
                             out_row0, idx, dist));
@@ -328,6 +336,12 @@ struct FloatSet {
   DevBuf<__nv_bfloat16> xb;
   DevBuf<float> colscale, colbias;
   DevBuf<int32_t> flags;  // [8]: exact, maxdev bits, maxsq bits, maxabs bits
+  // train-side view (floatset_finish_train)
+  DevBuf<__nv_bfloat16> xb_t;
+  DevBuf<float> colscale_t, colbias_t;
+  DevBuf<int32_t> perm, sort_scratch;
+  DevBuf<float4> tile_bounds;
+  bool sorted = false;
   int64_t N = 0;
   int D = 0;
   FloatSide side() const {
@@ -339,6 +353,11 @@ struct FloatSet {
     s.xb = xb.p;
     s.colscale = colscale.p;
     s.colbias = colbias.p;
+    s.xb_t = sorted ? xb_t.p : xb.p;
+    s.colscale_t = sorted ? colscale_t.p : colscale.p;
+    s.colbias_t = sorted ? colbias_t.p : colbias.p;
+    s.tile_bounds = tile_bounds.p;
+    s.perm = sorted ? perm.p : nullptr;
     s.N = N;
     return s;
   }
@@ -360,8 +379,31 @@ static int floatset_reset_flags(aps_ctx* c, FloatSet& fs) {
   return APS_OK;
 }
 
+// Train-side view of the tensor kernel: rows bucket-sorted by scale when `sort` (whole-set searches; pairwise
+// units need each image's rows contiguous and keep the natural order) + per-tile pre-filter bounds.
+static int floatset_finish_train(aps_ctx* c, FloatSet& fs, bool sort) {
+  if (fs.N == 0 || !fs.xb.p) return APS_OK;
+  const int Dp = (fs.D + 63) / 64 * 64;
+  fs.sorted = false;
+  if (sort) {
+    APS_TRY(fs.xb_t.alloc((size_t)fs.N * Dp, c->stream));
+    APS_TRY(fs.colscale_t.alloc((size_t)fs.N + 256, c->stream));
+    APS_TRY(fs.colbias_t.alloc((size_t)fs.N + 256, c->stream));
+    APS_TRY(fs.perm.alloc((size_t)fs.N, c->stream));
+    APS_TRY(fs.sort_scratch.alloc((size_t)aps_sort_scratch_ints(), c->stream));
+    APS_TRY(aps_k_sort_train_by_scale(c->stream, fs.xb.p, fs.colscale.p, fs.colbias.p, fs.N, Dp, fs.sort_scratch.p,
+                                      fs.perm.p, fs.xb_t.p, fs.colscale_t.p, fs.colbias_t.p));
+    fs.sorted = true;
+  }
+  const int tr = aps_k_knn_tc_tile_rows();
+  APS_TRY(fs.tile_bounds.alloc((size_t)aps_ceil_div(fs.N, tr) + 2, c->stream));
+  APS_TRY(aps_k_tile_bounds(c->stream, fs.sorted ? fs.colscale_t.p : fs.colscale.p,
+                            fs.sorted ? fs.colbias_t.p : fs.colbias.p, fs.N, tr, fs.tile_bounds.p));
+  return APS_OK;
+}
+
 // normalise + (optionally) build tensor operands
-static int floatset_prepare(aps_ctx* c, FloatSet& fs, int norm_mode, bool tensor, int bias_mode) {
+static int floatset_prepare(aps_ctx* c, FloatSet& fs, int norm_mode, bool tensor, int bias_mode, bool sort = true) {
   if (fs.N == 0) return APS_OK;
   if (norm_mode != APS_NORM_NONE && !fs.xn.p) APS_TRY(fs.xn.alloc((size_t)fs.N * fs.D, c->stream));
   float* xn = (norm_mode != APS_NORM_NONE) ? fs.xn.p : fs.raw.p;
@@ -373,6 +415,7 @@ static int floatset_prepare(aps_ctx* c, FloatSet& fs, int norm_mode, bool tensor
     APS_TRY(fs.colbias.alloc((size_t)fs.N + 256, c->stream));  // +256: whole-tile bulk loads
     APS_TRY(aps_k_prepare_operands(c->stream, fs.raw.p, xn, fs.sq.p, fs.invn.p, fs.N, fs.D, Dp, fs.flags.p,
                                    bias_mode, fs.xb.p, fs.colscale.p, fs.colbias.p));
+    APS_TRY(floatset_finish_train(c, fs, sort));
   }
   return APS_OK;
 }
@@ -449,6 +492,7 @@ extern "C" int aps_flann_knn(aps_ctx* c, const void* train, int64_t Ft, const vo
                                        Q.xb.p, Q.colscale.p, Q.colbias.p));
         APS_TRY(aps_k_prepare_operands(c->stream, T.raw.p, T.raw.p, T.sq.p, T.invn.p, Ft, D, Dp, T.flags.p, 1,
                                        T.xb.p, T.colscale.p, T.colbias.p));
+        APS_TRY(floatset_finish_train(c, T, true));
       }
     }
     qs = Q.side();
@@ -555,6 +599,7 @@ extern "C" int aps_nearest2_ssd(aps_ctx* c, const float* A, int64_t N1, const fl
                                    QA.xb.p, QA.colscale.p, QA.colbias.p));
     APS_TRY(aps_k_prepare_operands(c->stream, TB.raw.p, TB.raw.p, TB.sq.p, TB.invn.p, N2, D, Dp, TB.flags.p, 1,
                                    TB.xb.p, TB.colscale.p, TB.colbias.p));
+    APS_TRY(floatset_finish_train(c, TB, true));
   }
   DevBuf<uint32_t> di;
   DevBuf<float> dd1, dd2;
@@ -945,13 +990,14 @@ static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* des
     APS_TRY(ps.rawset.colbias.alloc((size_t)F + 256, c->stream));
     APS_TRY(aps_k_prepare_operands(c->stream, ps.rawset.raw.p, ps.rawset.raw.p, ps.rawset.sq.p, ps.rawset.invn.p, F,
                                    D, Dp, ps.rawset.flags.p, 1, ps.rawset.xb.p, ps.rawset.colscale.p, ps.rawset.colbias.p));
+    APS_TRY(floatset_finish_train(c, ps.rawset, /*sort*/ false));  // image ranges must stay contiguous
   }
   if (any_big) {
     APS_TRY(floatset_alloc(c, ps.normset, F, D));
     APS_TRY(floatset_reset_flags(c, ps.normset));
     APS_CUDA(cudaMemcpyAsync(ps.normset.raw.p, ps.rawset.raw.p, (size_t)F * D * 4, cudaMemcpyDeviceToDevice, c->stream));
     // normalised rows: scale-only scoring (bias would have to be scaled per query row)
-    APS_TRY(floatset_prepare(c, ps.normset, APS_NORM_PAIRWISE, tensor, 0));
+    APS_TRY(floatset_prepare(c, ps.normset, APS_NORM_PAIRWISE, tensor, 0, /*sort*/ false));
   }
   return APS_OK;
 }
@@ -1193,7 +1239,8 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       APS_CUDA(cudaMemcpyAsync(d_units.p, units.data(), units.size() * sizeof(aps_tc_unit), cudaMemcpyHostToDevice, s));
       APS_CUDA(cudaStreamSynchronize(s));  // host tables are pageable
       aps_tc_problem tp;
-      tp.Qb = side.xb; tp.Tb = side.xb; tp.colscale = side.colscale; tp.colbias = side.colbias; tp.bias = bias_mode;
+      tp.Qb = side.xb; tp.Tb = side.xb_t; tp.colscale = side.colscale_t; tp.colbias = side.colbias_t;
+      tp.tile_bounds = side.tile_bounds; tp.bias = bias_mode;
       tp.Fq_total = side.N; tp.Ft_total = side.N; tp.Dp = (D + 63) / 64 * 64;
       tp.q0 = 0; tp.q1 = 0; tp.t0 = 0; tp.t1 = 0; tp.nslot = 1; tp.kcand = 8;
       tp.cand_idx = cidx.p; tp.cand_score = cscore.p; tp.dump = nullptr;
@@ -1410,7 +1457,9 @@ extern "C" int aps_debug_tc_scores(aps_ctx* c, const float* Q, int64_t nq, const
   APS_TRY(cidx.alloc((size_t)nq * nslot * 8, c->stream));
   APS_TRY(cscore.alloc((size_t)nq * nslot * 8, c->stream));
   aps_tc_problem p;
-  p.Qb = qs.xb.p; p.Tb = ts.xb.p; p.colscale = ts.colscale.p; p.colbias = ts.colbias.p; p.bias = 1;
+  APS_TRY(floatset_finish_train(c, ts, /*sort*/ false));  // natural column order: the dump is indexed by column
+  p.Qb = qs.xb.p; p.Tb = ts.xb.p; p.colscale = ts.colscale.p; p.colbias = ts.colbias.p; p.tile_bounds = ts.tile_bounds.p;
+  p.bias = 1;
   p.Fq_total = nq; p.Ft_total = nt; p.Dp = Dp;
   p.q0 = 0; p.q1 = nq; p.t0 = 0; p.t1 = nt;
   p.nslot = nslot; p.kcand = 8;

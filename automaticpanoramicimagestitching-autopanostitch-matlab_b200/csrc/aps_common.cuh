@@ -105,6 +105,14 @@ int aps_k_prepare_operands(cudaStream_t s, const float* raw, const float* xn, co
                            int64_t F, int D, int Dp, const int32_t* exact_flag, int bias_mode, __nv_bfloat16* xb,
                            float* colscale, float* colbias);
 
+// train-side view of the tensor kernel (aps_prep.cu)
+int aps_k_sort_train_by_scale(cudaStream_t s, const __nv_bfloat16* xb, const float* colscale, const float* colbias,
+                              int64_t N, int Dp, int32_t* scratch, int32_t* perm, __nv_bfloat16* xb_t,
+                              float* colscale_t, float* colbias_t);
+int aps_sort_scratch_ints();
+int aps_k_tile_bounds(cudaStream_t s, const float* colscale, const float* colbias, int64_t N, int tile_rows,
+                      float4* out);
+
 // K2f aps_knn_exact.cu : exact CUDA-core kNN.  rows==nullptr -> queries [q0,q0+nq) ; else rows[i].
 //   metric 0: FLANN-order squared L2 ; metric 1: SSD order (a2 + b2) - 2*G with sq arrays.
 //   train columns [t0,t1) ; output idx 1-based RELATIVE TO t0 (idx = j - t0 + 1), row-major [.. x k],
@@ -129,6 +137,7 @@ struct aps_tc_problem {
   const __nv_bfloat16* Tb;  // [Ft_total x Dp] train operands
   const float* colscale;    // [Ft_total + 256] per train row
   const float* colbias;     // [Ft_total + 256] per train row (used iff bias)
+  const float4* tile_bounds;  // per 128-row tile of Tb: (1/scale_max, 1/scale_min, bias_max, -)
   int bias;                 // 0: score = dot*scale ; 1: score = dot*scale + bias
   int64_t Fq_total, Ft_total;
   int Dp;
@@ -142,6 +151,7 @@ struct aps_tc_problem {
   const int32_t* nrows_dev = nullptr;  // second pass: Qb holds *nrows_dev gathered rows (q0 = 0, q1 = upper bound)
 };
 int aps_k_knn_tc_supported(int Dp);
+int aps_k_knn_tc_tile_rows();  // rows per train tile (for aps_k_tile_bounds)
 int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, const aps_tc_unit* d_units,
                        int64_t n_units);
 int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1, int all_segmented = 0);  // lists per row
@@ -171,7 +181,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
                  int32_t* fb_count, const aps_pair_tables* pairs = nullptr, const int32_t* row_map = nullptr,
-                 const int32_t* nrows_dev = nullptr);
+                 const int32_t* nrows_dev = nullptr, const int32_t* perm = nullptr);
 
 // K5 aps_filter.cu
 int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, int k, int64_t q0, int64_t q1,

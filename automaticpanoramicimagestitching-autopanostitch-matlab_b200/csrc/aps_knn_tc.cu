@@ -217,6 +217,7 @@ struct KParams {
   int tiles_per_seg;    // tiles per segment of a tail unit
   const float* colscale;  // [Ft_total + 256] per train row
   const float* colbias;   // [Ft_total + 256] per train row (read only by the BIAS variant)
+  const float4* tile_bounds;  // per train tile: (1/scale_max, 1/scale_min, bias_max, -), 1e-6 safety included
   uint32_t* cand_idx;
   float* cand_score;
   float* dump;
@@ -381,11 +382,12 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       float bv[KC];
 #pragma unroll
       for (int i = 0; i < KC; ++i) {
-        bv[i] = -CUDART_INF_F;
+        bv[i] = __uint_as_float(0xff7ffff8u | (uint32_t)i);  // ~ -FLT_MAX with the slot number in the low bits
         sts_u32(si + i * SLOT_STRIDE, 0xffffffffu);
       }
-      float theta = -CUDART_INF_F;  // min of bv == the row's K'-th best score so far
-      int minpos = 0;               // slot holding it
+      float theta = bv[KC - 1];     // min of bv == the row's K'-th best score so far (empty slots: -FLT_MAX)
+      int minpos = KC - 1;          // slot holding it
+      float4 tb_next = (x.tl < x.th) ? __ldg(P.tile_bounds + x.tl) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int64_t t = x.tl; t < x.th; ++t, ++tcount) {
         const uint32_t slot = (tcount & 1) * RB + grp, acph = (tcount >> 1) & 1;
         const uint32_t cs = tcount % NUM_CS_STAGES, cph = (tcount / NUM_CS_STAGES) & 1;
@@ -396,6 +398,17 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         const int64_t col0 = t * TN + ch * CG;
         const bool partial = (col0 < x.t0) || (col0 + CG > x.t1);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * TN + ch * CG;
+        // Conservative pre-filter on the RAW accumulators: a column can only beat theta if
+        //   acc > (theta - bias_max(tile)) / scale_max(tile)     (1/scale_min when the numerator is negative);
+        // train rows are sorted by scale (aps_prep.cu), so the bound is tight and the common path needs
+        // neither the per-column constants nor a multiply.
+        const float4 tb = tb_next;  // fetched one tile ahead: the global-load latency stays off the critical path
+        if (t + 1 < x.th) tb_next = __ldg(P.tile_bounds + t + 1);
+        auto pre_threshold = [&](float th) {
+          const float num = th - tb.z - 1.0e-6f * (fabsf(th) + fabsf(tb.z));
+          return num * (num >= 0.f ? tb.x : tb.y);
+        };
+        float thr_pre = pre_threshold(theta);
         float va[32], vb[32];
         if (CSPLIT == 1) {  // two warps per sub-partition: double-buffer the TMEM loads
           tmem_ld32(taddr, va);
@@ -414,64 +427,76 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
               tmem_ld32(taddr + c * 32, cur);
               tmem_wait_ld(cur);
             }
-            float gm[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 s0 = lds_f32x4(cscale + (c * 32 + 8 * g) * 4);
-              const float4 s1 = lds_f32x4(cscale + (c * 32 + 8 * g + 4) * 4);
-              if (BIAS) {
-                const float4 b0 = lds_f32x4(cscale + (TN + c * 32 + 8 * g) * 4);
-                const float4 b1 = lds_f32x4(cscale + (TN + c * 32 + 8 * g + 4) * 4);
-                cur[8 * g + 0] = fmaf(cur[8 * g + 0], s0.x, b0.x); cur[8 * g + 1] = fmaf(cur[8 * g + 1], s0.y, b0.y);
-                cur[8 * g + 2] = fmaf(cur[8 * g + 2], s0.z, b0.z); cur[8 * g + 3] = fmaf(cur[8 * g + 3], s0.w, b0.w);
-                cur[8 * g + 4] = fmaf(cur[8 * g + 4], s1.x, b1.x); cur[8 * g + 5] = fmaf(cur[8 * g + 5], s1.y, b1.y);
-                cur[8 * g + 6] = fmaf(cur[8 * g + 6], s1.z, b1.z); cur[8 * g + 7] = fmaf(cur[8 * g + 7], s1.w, b1.w);
-              } else {
-                cur[8 * g + 0] *= s0.x; cur[8 * g + 1] *= s0.y; cur[8 * g + 2] *= s0.z; cur[8 * g + 3] *= s0.w;
-                cur[8 * g + 4] *= s1.x; cur[8 * g + 5] *= s1.y; cur[8 * g + 6] *= s1.z; cur[8 * g + 7] *= s1.w;
-              }
-            }
-            if (partial || DUMP) {  // first / last tile of the searched range: mask foreign columns
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t col = col0 + c * 32 + j;
-                const bool ok = col >= x.t0 && col < x.t1;
-                if (DUMP && ok && qrow < P.q1) P.dump[(qrow - P.q0) * (P.t1 - P.t0) + (col - P.t0)] = cur[j];
-                if (!ok) cur[j] = -CUDART_INF_F;
-              }
-            }
+            float rm[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
               m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
               m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
-              gm[g] = fmaxf(m, cur[8 * g + 7]);
+              rm[g] = fmaxf(m, cur[8 * g + 7]);
             }
-            if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) > theta) {
+            if (partial || DUMP || fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) > thr_pre) {
+              float gm[4];
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                // branch-free replace-min of the group's maximum; loops only if the same 8 columns hold
-                // a second candidate
-                while (gm[g] > theta) {
-                  int js = 7;
-#pragma unroll
-                  for (int j = 6; j >= 0; --j) js = (cur[8 * g + j] == gm[g]) ? j : js;
-                  sts_u32(si + minpos * SLOT_STRIDE, (uint32_t)(col0 + c * 32 + 8 * g + js));
-#pragma unroll
-                  for (int i = 0; i < KC; ++i) bv[i] = (i == minpos) ? gm[g] : bv[i];
-                  float m01 = fminf(fminf(bv[0], bv[1]), bv[2]);
-                  float m23 = fminf(fminf(bv[3], bv[4]), bv[5]);
-                  theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
-                  minpos = 7;
-#pragma unroll
-                  for (int i = 6; i >= 0; --i) minpos = (bv[i] == theta) ? i : minpos;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) cur[8 * g + j] = (j == js) ? -CUDART_INF_F : cur[8 * g + j];
-                  float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
-                  m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
-                  m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
-                  gm[g] = fmaxf(m, cur[8 * g + 7]);
+                const float4 s0 = lds_f32x4(cscale + (c * 32 + 8 * g) * 4);
+                const float4 s1 = lds_f32x4(cscale + (c * 32 + 8 * g + 4) * 4);
+                if (BIAS) {
+                  const float4 b0 = lds_f32x4(cscale + (TN + c * 32 + 8 * g) * 4);
+                  const float4 b1 = lds_f32x4(cscale + (TN + c * 32 + 8 * g + 4) * 4);
+                  cur[8 * g + 0] = fmaf(cur[8 * g + 0], s0.x, b0.x); cur[8 * g + 1] = fmaf(cur[8 * g + 1], s0.y, b0.y);
+                  cur[8 * g + 2] = fmaf(cur[8 * g + 2], s0.z, b0.z); cur[8 * g + 3] = fmaf(cur[8 * g + 3], s0.w, b0.w);
+                  cur[8 * g + 4] = fmaf(cur[8 * g + 4], s1.x, b1.x); cur[8 * g + 5] = fmaf(cur[8 * g + 5], s1.y, b1.y);
+                  cur[8 * g + 6] = fmaf(cur[8 * g + 6], s1.z, b1.z); cur[8 * g + 7] = fmaf(cur[8 * g + 7], s1.w, b1.w);
+                } else {
+                  cur[8 * g + 0] *= s0.x; cur[8 * g + 1] *= s0.y; cur[8 * g + 2] *= s0.z; cur[8 * g + 3] *= s0.w;
+                  cur[8 * g + 4] *= s1.x; cur[8 * g + 5] *= s1.y; cur[8 * g + 6] *= s1.z; cur[8 * g + 7] *= s1.w;
                 }
+              }
+              if (partial || DUMP) {  // first / last tile of the searched range: mask foreign columns
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int64_t col = col0 + c * 32 + j;
+                  const bool ok = col >= x.t0 && col < x.t1;
+                  if (DUMP && ok && qrow < P.q1) P.dump[(qrow - P.q0) * (P.t1 - P.t0) + (col - P.t0)] = cur[j];
+                  if (!ok) cur[j] = -CUDART_INF_F;
+                }
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
+                m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
+                m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
+                gm[g] = fmaxf(m, cur[8 * g + 7]);
+              }
+              if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) > theta) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  // branch-free replace-min of the group's maximum; loops only if the same 8 columns hold
+                  // a second candidate
+                  while (gm[g] > theta) {
+                    int js = 7;
+#pragma unroll
+                    for (int j = 6; j >= 0; --j) js = (cur[8 * g + j] == gm[g]) ? j : js;
+                    sts_u32(si + minpos * SLOT_STRIDE, (uint32_t)(col0 + c * 32 + 8 * g + js));
+                    // the 3 low mantissa bits of a retained score hold its slot number: one FMNMX tree yields the
+                    // new minimum AND its slot (the 7-ulp truncation is covered by the re-rank's eps)
+                    const float key = __uint_as_float((__float_as_uint(gm[g]) & ~7u) | (uint32_t)minpos);
+#pragma unroll
+                    for (int i = 0; i < KC; ++i) bv[i] = (i == minpos) ? key : bv[i];
+                    float m01 = fminf(fminf(bv[0], bv[1]), bv[2]);
+                    float m23 = fminf(fminf(bv[3], bv[4]), bv[5]);
+                    theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
+                    minpos = (int)(__float_as_uint(theta) & 7u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cur[8 * g + j] = (j == js) ? -CUDART_INF_F : cur[8 * g + j];
+                    float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
+                    m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
+                    m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
+                    gm[g] = fmaxf(m, cur[8 * g + 7]);
+                  }
+                }
+                thr_pre = pre_threshold(theta);
               }
             }
             if (CSPLIT == 1 && c + 1 < CG / 32) tmem_wait_ld(nxt);
@@ -548,6 +573,7 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dp, in
 }  // namespace
 
 int aps_k_knn_tc_supported(int Dp) { return Dp == 64 || Dp == 128; }
+int aps_k_knn_tc_tile_rows() { return TN; }
 
 // Work decomposition shared by the launcher and by callers that size the candidate buffers.
 struct TcSchedule {
@@ -620,6 +646,7 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.tiles_per_seg = sc.tiles_per_seg;
   P.colscale = p.colscale;
   P.colbias = p.colbias;
+  P.tile_bounds = p.tile_bounds;
   P.cand_idx = p.cand_idx;
   P.cand_score = p.cand_score;
   P.dump = p.dump;
@@ -691,6 +718,7 @@ int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, co
   P.nslot = 1;
   P.colscale = p.colscale;
   P.colbias = p.colbias;
+  P.tile_bounds = p.tile_bounds;
   P.cand_idx = p.cand_idx;
   P.cand_score = p.cand_score;
   P.dump = nullptr;

@@ -185,3 +185,148 @@ int aps_k_prepare_operands(cudaStream_t s, const float* raw, const float* xn, co
   APS_LAUNCHED();
   return APS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Train-side view of the tensor kernel.  The epilogue pre-filters RAW accumulators against a per-row
+// threshold (theta - bias_max(tile)) / scale_max(tile); to make that bound tight the train rows are
+// bucket-sorted by their scale (1/norm), so the 128 rows of a tile have nearly the same scale.  perm[pos] is
+// the original row of sorted position pos (order inside a bucket is arbitrary: the exact re-rank works
+// on original indices, so results do not depend on it).
+constexpr int NBUCKET = 4096;
+
+__global__ void k_scale_minmax(const float* __restrict__ sc, int64_t N, int32_t* __restrict__ mm) {
+  float mn = 3.0e38f, mx = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = sc[i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {  // scales are positive: integer order == float order
+    atomicMin(&mm[0], __float_as_int(mn));
+    atomicMax(&mm[1], __float_as_int(mx));
+  }
+}
+__device__ __forceinline__ int scale_bucket(float v, const int32_t* mm) {
+  const float mn = __int_as_float(mm[0]), mx = __int_as_float(mm[1]);
+  const float range = mx - mn;
+  if (!(range > 0.f)) return 0;
+  int b = (int)((v - mn) / range * (float)(NBUCKET - 1));
+  return b < 0 ? 0 : (b >= NBUCKET ? NBUCKET - 1 : b);
+}
+__global__ void k_bucket_hist(const float* __restrict__ sc, int64_t N, const int32_t* __restrict__ mm,
+                              int32_t* __restrict__ hist) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&hist[scale_bucket(sc[i], mm)], 1);
+}
+__global__ void k_bucket_scan(const int32_t* __restrict__ hist, int32_t* __restrict__ cursor) {
+  __shared__ int32_t part[1024];
+  const int per = NBUCKET / 1024, t = threadIdx.x;
+  int sum = 0;
+  for (int i = 0; i < per; ++i) sum += hist[t * per + i];
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      const int v = part[i];
+      part[i] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  int run = part[t];
+  for (int i = 0; i < per; ++i) {
+    cursor[t * per + i] = run;
+    run += hist[t * per + i];
+  }
+}
+__global__ void k_bucket_scatter(const float* __restrict__ sc, int64_t N, const int32_t* __restrict__ mm,
+                                 int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    perm[atomicAdd(&cursor[scale_bucket(sc[i], mm)], 1)] = (int32_t)i;
+}
+__global__ void k_gather_train(const uint4* __restrict__ xb, const float* __restrict__ sc, const float* __restrict__ bi,
+                               const int32_t* __restrict__ perm, int64_t N, int chunks, uint4* __restrict__ xb_t,
+                               float* __restrict__ sc_t, float* __restrict__ bi_t) {
+  const int64_t total = N * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pos = i / chunks;
+    const int c = (int)(i - pos * chunks);
+    const int64_t r = perm[pos];
+    xb_t[i] = xb[r * chunks + c];
+    if (c == 0) {
+      sc_t[pos] = sc[r];
+      bi_t[pos] = bi[r];
+    }
+  }
+}
+
+int aps_k_sort_train_by_scale(cudaStream_t s, const __nv_bfloat16* xb, const float* colscale, const float* colbias,
+                              int64_t N, int Dp, int32_t* scratch /* 2 + 2*NBUCKET ints */, int32_t* perm,
+                              __nv_bfloat16* xb_t, float* colscale_t, float* colbias_t) {
+  if (N == 0) return APS_OK;
+  int32_t* mm = scratch;
+  int32_t* hist = scratch + 2;
+  int32_t* cursor = hist + NBUCKET;
+  static const int32_t init_mm[2] = {0x7f7fffff, 0};
+  APS_CUDA(cudaMemcpyAsync(mm, init_mm, sizeof init_mm, cudaMemcpyHostToDevice, s));
+  APS_CUDA(cudaMemsetAsync(hist, 0, NBUCKET * sizeof(int32_t), s));
+  const unsigned grid = (unsigned)aps_min64(aps_ceil_div(N, 256), 148 * 8);
+  k_scale_minmax<<<grid, 256, 0, s>>>(colscale, N, mm);
+  APS_LAUNCHED();
+  k_bucket_hist<<<grid, 256, 0, s>>>(colscale, N, mm, hist);
+  APS_LAUNCHED();
+  k_bucket_scan<<<1, 1024, 0, s>>>(hist, cursor);
+  APS_LAUNCHED();
+  k_bucket_scatter<<<grid, 256, 0, s>>>(colscale, N, mm, cursor, perm);
+  APS_LAUNCHED();
+  const int chunks = Dp * 2 / 16;
+  const unsigned g2 = (unsigned)aps_min64(aps_ceil_div(N * chunks, 256), 148 * 16);
+  k_gather_train<<<g2, 256, 0, s>>>((const uint4*)xb, colscale, colbias, perm, N, chunks, (uint4*)xb_t, colscale_t,
+                                    colbias_t);
+  APS_LAUNCHED();
+  return APS_OK;
+}
+int aps_sort_scratch_ints() { return 2 + 2 * NBUCKET; }
+
+// per 128-row tile of the train view: (1/scale_max, 1/scale_min) with a 1e-6 safety factor, bias_max
+__global__ void k_tile_bounds(const float* __restrict__ sc, const float* __restrict__ bi, int64_t N, int tile_rows,
+                              int64_t ntiles, float4* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= ntiles) return;
+  float smax = 0.f, smin = 3.0e38f, bmax = -3.0e38f;
+  for (int r = lane; r < tile_rows; r += 32) {
+    const int64_t j = t * tile_rows + r;
+    if (j < N) {
+      smax = fmaxf(smax, sc[j]);
+      smin = fminf(smin, sc[j]);
+      bmax = fmaxf(bmax, bi[j]);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+  }
+  if (lane == 0) {
+    float4 v;
+    v.x = smax > 0.f ? (1.0f / smax) * (1.0f - 1.0e-6f) : 0.f;      // multiplies (theta - bias_max) >= 0
+    v.y = (smin > 0.f && smin < 3.0e38f) ? (1.0f / smin) * (1.0f + 1.0e-6f) : 3.0e38f;  // ... when it is negative
+    v.z = bmax > -3.0e38f ? bmax : 0.f;
+    v.w = 0.f;
+    out[t] = v;
+  }
+}
+int aps_k_tile_bounds(cudaStream_t s, const float* colscale, const float* colbias, int64_t N, int tile_rows,
+                      float4* out) {
+  const int64_t ntiles = aps_ceil_div(N, tile_rows);
+  if (ntiles == 0) return APS_OK;
+  k_tile_bounds<<<(unsigned)aps_ceil_div(ntiles, 8), 256, 0, s>>>(colscale, colbias, N, tile_rows, ntiles, out);
+  APS_LAUNCHED();
+  return APS_OK;
+}

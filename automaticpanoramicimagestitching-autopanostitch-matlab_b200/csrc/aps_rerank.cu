@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
                                                 float* __restrict__ dist, int32_t* __restrict__ fb_rows,
                                                 int32_t* __restrict__ fb_count, aps_pair_tables pt,
                                                 const int32_t* __restrict__ row_map,
-                                                const int32_t* __restrict__ nrows_dev) {
+                                                const int32_t* __restrict__ nrows_dev,
+                                                const int32_t* __restrict__ perm) {
   constexpr int RPW = 32 / G;  // rows per warp
   if (nrows_dev && (int64_t)blockIdx.x * (blockDim.x >> 5) * RPW >= (int64_t)(*nrows_dev)) return;  // second pass: short list
   const int lane = threadIdx.x & 31, sub = lane / G, sl = lane % G;
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   if (row_ok && sl < ncand) {
     ci = cand_idx[r * ncand + sl];
     sc = cand_score[r * ncand + sl];
+    if (perm && ci != 0xffffffffu) ci = (uint32_t)perm[ci];  // position in the sorted train view -> original row
   }
   const bool valid = ci != 0xffffffffu;
   const float sapx = valid ? fmaf(beta, sc, alpha) : CUDART_INF_F;  // monotone in sc; its own rounding is inside eps
@@ -136,7 +138,8 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const float* sqT, int D, int metric, int64_t q0, int64_t nq, int64_t t0, int nseg, int kcand,
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
-                 int32_t* fb_count, const aps_pair_tables* pairs, const int32_t* row_map, const int32_t* nrows_dev) {
+                 int32_t* fb_count, const aps_pair_tables* pairs, const int32_t* row_map, const int32_t* nrows_dev,
+                 const int32_t* perm) {
   (void)exact_flag;
   if (nq == 0) return APS_OK;
   if (nseg * kcand > 32) {
@@ -155,7 +158,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
   k_rerank<G><<<(unsigned)aps_ceil_div(nq, 8 * (32 / G)), 256, 0, s>>>(Q, sqQ, invnQ, T, sqT, D, metric, q0, nq, t0, \
                                                                        nseg, kcand, cand_idx, cand_score, flags,     \
                                                                        bias_mode, k, out_row0, idx, dist, fb_rows,  \
-                                                                       fb_count, pt, row_map, nrows_dev)
+                                                                       fb_count, pt, row_map, nrows_dev, perm)
   if (ncand <= 8) APS_RERANK(8);
   else if (ncand <= 16) APS_RERANK(16);
   else APS_RERANK(32);
