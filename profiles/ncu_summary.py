@@ -27,7 +27,13 @@ for vals in rows[2:]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[start], [r for r in rows[start + 1:] if len(r) == len(rows[start])]
+data = []
+for r in rows[start + 1:]:  # first kernel of the report only
+    if r and r[0] == "Address":
+        break
+    if len(r) == len(rows[start]):
+        data.append(r)
+hdr = rows[start]
 ci = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ci["# Samples"]]) for r in data) or 1
 reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
