@@ -19,10 +19,14 @@
 //              independent issuers remove head-of-line blocking between the two epilogue groups
 //   warps 3-6: epilogue group 0 = row block 0, warps 7-10: group 1 = row block 1 (thread == query row,
 //              tcgen05.ld 32x32b from the warp's TMEM lane quadrant).  Per 32-column chunk:
-//              score = acc*scale (+bias) with the constants read as broadcast LDS.128, a FMNMX3 tree to
-//              four 8-column group maxima, one compare with the row's K'-th best (theta, a register).
-//              Only groups that contain a candidate run the branch-free replace-min (scores in
-//              registers, train-row indices in shared memory).
+//              (1) raw pre-filter: FMNMX3 tree over the 32 accumulators, one compare with a per-tile
+//                  threshold derived from the row's K'-th best (theta) and the tile's (min,max) column
+//                  scale / bias (aps_k_tile_bounds; the train view is sorted by scale so the bounds are
+//                  tight) -- a chunk that cannot hold a candidate costs ~31 instructions;
+//              (2) otherwise score = acc*scale (+bias) with the constants read as broadcast LDS.128,
+//                  exact group maxima, and a branch-free replace-min for the groups that hold a
+//                  candidate: scores in registers as packed keys (value bits & ~7 | slot), train-row
+//                  indices in shared memory.
 // TMEM: 4 accumulator slots of 128 columns = slot(tile parity, row block): the tensor pipe fills the
 // slots of tile t+1 while both groups drain tile t.  Pipelines (all mbarrier based): B ring (4 x 32 KB),
 // A pair (single buffered per unit), accumulator slots, (scale,bias) ring.
@@ -30,18 +34,21 @@
 // partial round are split into up to 4 column segments so that the tail is balanced.
 //
 // What bounds it (round 1 measurements, C2 = 163840^2 pairs, D = 128, same box, profiles/r1_ncu_history.txt):
-//   * with the selection skipped (accumulators never read) the TMA + MMA pipeline alone takes 3.99 ms
-//     = 1723 TFLOP/s;
-//   * with the selection: 6.6-6.7 ms = 1025-1040 TFLOP/s, unchanged by doubling the epilogue warps
-//     (CSPLIT = 2: 7.24 ms) or by cheaper polling -- every fp32 accumulator must cross TMEM -> registers,
-//     and tcgen05.ld moves ~64 B/clk/SM (B300_MICROARCH.md "TMEM-read 64 B/cyc"): 128 rows x 128 columns
-//     x 4 B x 2 row blocks = 128 KB per step = 2048 clk, measured 2380 clk per step.  16 outputs/clk/SM
-//     x 2*D FLOP = 1.19 PFLOP/s at D = 128 is the ceiling of any epilogue that inspects every distance
-//     in fp32; the kernel runs at 87 % of it.  (fp16 accumulators would halve the TMEM traffic but their
-//     rounding breaks the completeness proof on SIFT-like data: median d8-d4 gap 0.016.)
-//   * earlier designs: one row block per unit, epilogue split by columns (two lists per row, single MMA
-//     issuer): 8.23 ms; fully unrolled register-resident sorted top-K: 348 KB of SASS, 69 % instruction-
-//     fetch stalls, 109 ms.
+//   * selection skipped (accumulators never read): TMA + MMA alone 3.99 ms = 1723 TFLOP/s -- the floor of
+//     this tiling;
+//   * epilogue that reads every accumulator (tcgen05.ld) and runs 63 ALU instructions per chunk but never
+//     selects: 4.80 ms = 1432 TFLOP/s -- so the TMEM read path is NOT the limiter;
+//   * full kernel: 6.1 ms = 1120-1130 TFLOP/s (83-84 % of the measured sustained bf16 peak).  The epilogue
+//     is issue/latency bound: two epilogue warps per scheduler at IPC 0.43 ('wait' 31 % of the samples);
+//     2.25e9 epilogue warp instructions per launch = per tile 73 + 2 x 63 on the fast path, and 0.95e9
+//     in the candidate path, which 19 % of the chunks enter (K'(1 + ln(F/K')) ~ 87 insertions per row are
+//     inherent to a streaming top-K').  acc_full waits are 13 % of the samples: the first tiles of a unit
+//     are epilogue-bound (lists filling), the last ones MMA-bound.
+//   * not kept: two lists per row on column halves with 16 epilogue warps (6.89 ms: twice the
+//     insertions), a fully unrolled chunk loop (6.81 ms: instruction cache), fp16 accumulators (rounding
+//     breaks the completeness proof on SIFT-like data: median d8-d4 gap 0.016);
+//   * earlier designs: one row block per unit, epilogue split by columns, single MMA issuer: 8.23 ms;
+//     fully unrolled register-resident sorted top-K: 348 KB of SASS, 69 % instruction-fetch stalls, 109 ms.
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2*D per (query, train) pair.  HBM traffic is
 // negligible (operands stream from L2: every concurrently running CTA walks the same B tiles).
@@ -259,7 +266,7 @@ __device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
   return x;
 }
 
-template <bool BIAS, bool DUMP>
+template <bool BIAS, bool DUMP, bool PRE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const KParams Pin) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -387,7 +394,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       }
       float theta = bv[KC - 1];     // min of bv == the row's K'-th best score so far (empty slots: -FLT_MAX)
       int minpos = KC - 1;          // slot holding it
-      float4 tb_next = (x.tl < x.th) ? __ldg(P.tile_bounds + x.tl) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 tb_next = (PRE && x.tl < x.th) ? __ldg(P.tile_bounds + x.tl) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int64_t t = x.tl; t < x.th; ++t, ++tcount) {
         const uint32_t slot = (tcount & 1) * RB + grp, acph = (tcount >> 1) & 1;
         const uint32_t cs = tcount % NUM_CS_STAGES, cph = (tcount / NUM_CS_STAGES) & 1;
@@ -403,12 +410,12 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         // train rows are sorted by scale (aps_prep.cu), so the bound is tight and the common path needs
         // neither the per-column constants nor a multiply.
         const float4 tb = tb_next;  // fetched one tile ahead: the global-load latency stays off the critical path
-        if (t + 1 < x.th) tb_next = __ldg(P.tile_bounds + t + 1);
+        if (PRE && t + 1 < x.th) tb_next = __ldg(P.tile_bounds + t + 1);
         auto pre_threshold = [&](float th) {
           const float num = th - tb.z - 1.0e-6f * (fabsf(th) + fabsf(tb.z));
           return num * (num >= 0.f ? tb.x : tb.y);
         };
-        float thr_pre = pre_threshold(theta);
+        float thr_pre = PRE ? pre_threshold(theta) : 0.f;
         float va[32], vb[32];
         if (CSPLIT == 1) {  // two warps per sub-partition: double-buffer the TMEM loads
           tmem_ld32(taddr, va);
@@ -427,15 +434,19 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
               tmem_ld32(taddr + c * 32, cur);
               tmem_wait_ld(cur);
             }
-            float rm[4];
+            float rm[4] = {0.f, 0.f, 0.f, 0.f};
+            if (PRE) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
-              m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
-              m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
-              rm[g] = fmaxf(m, cur[8 * g + 7]);
+              for (int g = 0; g < 4; ++g) {
+                float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
+                m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
+                m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
+                rm[g] = fmaxf(m, cur[8 * g + 7]);
+              }
             }
-            if (partial || DUMP || fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) > thr_pre) {
+            // PRE = false (short units, e.g. one image pair: the lists never leave their filling phase, the
+            // pre-filter would reject almost nothing) goes straight to the scaled scores
+            if (!PRE || partial || DUMP || fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) > thr_pre) {
               float gm[4];
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -496,7 +507,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                     gm[g] = fmaxf(m, cur[8 * g + 7]);
                   }
                 }
-                thr_pre = pre_threshold(theta);
+                if (PRE) thr_pre = pre_threshold(theta);
               }
             }
             if (CSPLIT == 1 && c + 1 < CG / 32) tmem_wait_ld(nxt);
@@ -670,10 +681,15 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
     kern<<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
     return APS_OK;
   };
+  // the raw pre-filter pays once a unit sweeps >= ~100 tiles (insert probability per chunk ~ 64 / tiles seen)
+  const int64_t sweep = (sc.tile_hi - sc.tile_lo) / ((sc.units_full && !p.nrows_dev) ? 1 : (sc.tail_seg > 0 ? sc.tail_seg : 1));
+  const bool pre = sweep >= 96 && p.tile_bounds != nullptr;
   if (p.dump)
-    APS_TRY(p.bias ? launch(k_knn_tc<true, true>) : launch(k_knn_tc<false, true>));
+    APS_TRY(p.bias ? launch(k_knn_tc<true, true, false>) : launch(k_knn_tc<false, true, false>));
+  else if (pre)
+    APS_TRY(p.bias ? launch(k_knn_tc<true, false, true>) : launch(k_knn_tc<false, false, true>));
   else
-    APS_TRY(p.bias ? launch(k_knn_tc<true, false>) : launch(k_knn_tc<false, false>));
+    APS_TRY(p.bias ? launch(k_knn_tc<true, false, false>) : launch(k_knn_tc<false, false, false>));
   APS_LAUNCHED();
   if (ev1) APS_CUDA(cudaEventRecord(ev1, s));
   return APS_OK;
@@ -732,7 +748,7 @@ int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, co
     kern<<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
     return APS_OK;
   };
-  APS_TRY(p.bias ? launch(k_knn_tc<true, false>) : launch(k_knn_tc<false, false>));
+  APS_TRY(p.bias ? launch(k_knn_tc<true, false, false>) : launch(k_knn_tc<false, false, false>));
   APS_LAUNCHED();
   return APS_OK;
 }
