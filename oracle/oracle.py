@@ -72,6 +72,12 @@ def lib():
         L.orc_pack_bits.argtypes = [_u8p, C.c_int64, C.c_int, _u8p]
         L.orc_l2sq.argtypes = [_f32p, _f32p, C.c_int]
         L.orc_l2sq.restype = C.c_float
+        L.orc_ransac_homography.argtypes = [_f64p, _f64p, C.c_int64, C.c_double, C.c_double, C.c_int, _u32p, C.c_int64,
+                                            _f64p, _u8p, _i32p, _i32p]
+        L.orc_ransac_homography.restype = C.c_int
+        L.orc_inv3.argtypes = [_f64p, _f64p]
+        L.orc_image_matching_batch.argtypes = [C.c_int64, _i64p, _f64p, _f64p, C.c_double, C.c_double, C.c_int, _u32p,
+                                               C.c_int64, _f64p, _f64p, _u8p, _i32p, _u8p, _i32p]
         _lib = L
     return _lib
 
@@ -240,6 +246,43 @@ def pack_bits(bits01):
     out = np.zeros((N, (Db + 7) // 8), np.uint8)
     lib().orc_pack_bits(bits01, N, Db, out)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# consumer of the match lists: RANSAC homographies (aps_oracle_ransac.c)
+# --------------------------------------------------------------------------------------------
+def ransac_homography(pts1, pts2, max_distance, confidence, max_trials, samples):
+    """estimateTransformationRANSAC.m:94-183 ('projective').  pts1/pts2: [n x 2] float64 (matchedPoints1/2),
+    samples: [n_draws x 4] zero-based minimal samples.  -> (found, model[3x3] row-major, inliers bool[n], draws_used)"""
+    p1 = np.ascontiguousarray(pts1, np.float64).reshape(-1, 2)
+    p2 = np.ascontiguousarray(pts2, np.float64).reshape(-1, 2)
+    smp = np.ascontiguousarray(samples, np.uint32).reshape(-1, 4)
+    n = p1.shape[0]
+    model = np.zeros(9, np.float64)
+    inl = np.zeros(max(n, 1), np.uint8)
+    ni, du = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    found = lib().orc_ransac_homography(p1.reshape(-1), p2.reshape(-1), n, float(max_distance), float(confidence),
+                                        int(max_trials), smp.reshape(-1), smp.shape[0], model, inl, ni, du)
+    return bool(found), model.reshape(3, 3), inl[:n].astype(bool), int(du[0])
+
+
+def image_matching_batch(pt_ptr, pts1, pts2, max_distance, confidence, max_trials, samples):
+    """imageMatching.m:121-156 for a batch of candidate pairs (CSR correspondences).  samples: [n_pairs x n_draws x 4].
+    -> dict(models [P x 3 x 3], models_inv, inliers bool[total], n_inliers, accepted, draws_used)"""
+    pt_ptr = np.ascontiguousarray(pt_ptr, np.int64)
+    P = pt_ptr.size - 1
+    p1 = np.ascontiguousarray(pts1, np.float64).reshape(-1, 2)
+    p2 = np.ascontiguousarray(pts2, np.float64).reshape(-1, 2)
+    smp = np.ascontiguousarray(samples, np.uint32).reshape(P, -1, 4)
+    total = p1.shape[0]
+    models, minv = np.zeros((P, 9)), np.zeros((P, 9))
+    inl = np.zeros(max(total, 1), np.uint8)
+    ni, du, acc = np.zeros(max(P, 1), np.int32), np.zeros(max(P, 1), np.int32), np.zeros(max(P, 1), np.uint8)
+    lib().orc_image_matching_batch(P, pt_ptr, p1.reshape(-1), p2.reshape(-1), float(max_distance), float(confidence),
+                                   int(max_trials), smp.reshape(-1), smp.shape[1], models.reshape(-1), minv.reshape(-1),
+                                   inl, ni, acc, du)
+    return dict(models=models.reshape(P, 3, 3), models_inv=minv.reshape(P, 3, 3), inliers=inl[:total].astype(bool),
+                n_inliers=ni[:P], accepted=acc[:P].astype(bool), draws_used=du[:P])
 
 
 # --------------------------------------------------------------------------------------------
