@@ -12,7 +12,11 @@ from .host import (  # noqa: F401
     GlobalPlan,
     binaryFeatures,
     featureMatchingGlobal,
+    estimateTransformationRANSAC,
     featureMatchingPairwise,
+    imageMatching,
+    imageMatchingBatch,
+    ransacSampleTable,
     flann_knn_win,
     matchFeaturesScratch,
     merge_pairwise_shards,

@@ -379,6 +379,129 @@ def selectImagePartners(matchesAll, m, ctx=None):
     return cand.reshape(n, n).T.astype(bool), pairs[:npairs.value] + 1
 
 
+def ransacSampleTable(pt_ptr, n_draws, seed=0, ctx=None):
+    """The device generator's table of minimal samples: [n_pairs x n_draws x 4] zero-based indices
+    (stand-in for randperm(numPoints, 4), estimateTransformationRANSAC.m:97)."""
+    ctx = ctx or default_context()
+    pt_ptr = np.ascontiguousarray(pt_ptr, np.int64)
+    P = pt_ptr.size - 1
+    out = np.zeros((max(P, 0), int(n_draws), 4), np.uint32)
+    if P > 0:
+        check(lib().aps_ransac_sample_table(ctx.handle, _ptr(pt_ptr), P, int(n_draws), int(seed), _ptr(out)))
+    return out
+
+
+def _ransac_params(input):
+    return (float(_field(input, "maxDistance", 2.0)), float(_field(input, "inliersConfidence", 99.9)),
+            int(_field(input, "maxIter", 500)))
+
+
+def imageMatchingBatch(pt_ptr, pts1, pts2, input=None, samples=None, n_draws=None, seed=0, ctx=None):
+    """RANSAC homographies for a batch of candidate pairs given as CSR correspondences (aps_image_matching_batch).
+    pts1 / pts2: [total x 2] (matchedPoints1 = image jj, matchedPoints2 = image ii).  Returns a dict with
+    models / models_inv [P x 3 x 3], inliers bool[total], n_inliers, accepted, draws_used."""
+    ctx = ctx or default_context()
+    md, conf, mt = _ransac_params(input or {})
+    pt_ptr = np.ascontiguousarray(pt_ptr, np.int64)
+    P = pt_ptr.size - 1
+    p1 = np.ascontiguousarray(pts1, np.float64).reshape(-1, 2)
+    p2 = np.ascontiguousarray(pts2, np.float64).reshape(-1, 2)
+    total = p1.shape[0]
+    if samples is not None:
+        samples = np.ascontiguousarray(samples, np.uint32).reshape(P, -1, 4)
+        n_draws = samples.shape[1]
+    n_draws = int(n_draws or 2 * mt)
+    models, minv = np.full((P, 3, 3), np.nan), np.full((P, 3, 3), np.nan)
+    inl, ni = np.zeros(max(total, 1), np.uint8), np.zeros(max(P, 1), np.int32)
+    acc, du = np.zeros(max(P, 1), np.uint8), np.zeros(max(P, 1), np.int32)
+    check(lib().aps_image_matching_batch(ctx.handle, P, _ptr(pt_ptr), _ptr(p1), _ptr(p2), md, conf, mt,
+                                         _ptr(samples) if samples is not None else C.c_void_p(0), n_draws, int(seed),
+                                         _ptr(models), _ptr(minv), _ptr(inl), _ptr(ni), _ptr(acc), _ptr(du)))
+    return dict(models=models, models_inv=minv, inliers=inl[:total].astype(bool), n_inliers=ni[:P],
+                accepted=acc[:P].astype(bool), draws_used=du[:P])
+
+
+def estimateTransformationRANSAC(matchedPoints1, matchedPoints2, transformType="projective", input=None, samples=None,
+                                 seed=0, ctx=None):
+    """[model, inliers, isFound] = estimateTransformationRANSAC(...) (estimateTransformationRANSAC.m:1-183).
+    Only 'projective' (PP/inputs.m:73) is built; model is None where the reference returns []."""
+    if str(transformType).lower() != "projective":
+        raise ValueError("Unknown transform type" if str(transformType).lower() not in
+                         ("affine", "similarity", "rigid", "translation") else
+                         f"transform type '{transformType}' is outside the B200 path (projective only)")
+    p1 = np.asarray(matchedPoints1, np.float64).reshape(-1, 2)
+    p2 = np.asarray(matchedPoints2, np.float64).reshape(-1, 2)
+    if p1.shape[0] != p2.shape[0]:
+        raise ValueError("matchedPoints1 and matchedPoints2 must have the same number of rows.")  # :51-53
+    if samples is not None:
+        samples = np.asarray(samples, np.uint32).reshape(1, -1, 4)
+    r = imageMatchingBatch([0, p1.shape[0]], p1, p2, input, samples, None, seed, ctx)
+    found = bool(np.isfinite(r["models"][0]).all() and r["n_inliers"][0] >= 4)
+    return (r["models"][0] if found else None), r["inliers"], found
+
+
+def imageMatching(input, n, keypoints, matchesAll, imagesProcessed=None, samples=None, seed=0, ctx=None):
+    """[allMatches, numMatches, tforms] = imageMatching(input, n, keypoints, matchesAll, imagesProcessed)
+    (imageMatching.m:1-156, custom 'ransac' branch): top-m partner selection, RANSAC homography per candidate
+    pair on the GPU (matched keypoints gathered on the device from the CSR lists), acceptance ni > 8 + 0.3 nf.
+    keypoints: list of [Ni x 2]; matchesAll: n x n nested list of [M x 2] 1-based index pairs.
+    Returns nested lists / an [n x n] array like the reference's cells; tforms[i][j] maps image j to image i."""
+    ctx = ctx or default_context()
+    n = int(n)
+    if len(matchesAll) != n or any(len(r) != n for r in matchesAll):
+        raise ValueError("matchesAll must be an n-by-n cell array.")  # imageMatching:InvalidMatchesAllSize
+    if len(keypoints) != n:
+        raise ValueError("keypoints must contain n elements (one per image).")
+    if str(_field(input, "imageMatchingMethod", "ransac")).lower() != "ransac" or int(_field(input, "useMATLABImageMatching", 0)):
+        raise ValueError("only input.imageMatchingMethod = 'ransac' with useMATLABImageMatching = 0 is built")
+    allMatches = [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]
+    numMatches = np.zeros((n, n))
+    tforms = [[None] * n for _ in range(n)]
+    _, lin1 = selectImagePartners(matchesAll, int(_field(input, "mBrownLowe", 6)), ctx)
+    if lin1.size == 0:
+        return allMatches, numMatches, tforms
+    lin = np.ascontiguousarray(lin1 - 1, np.int64)
+    # CSR of the cell (column-major cell index c = i + j*n), pooled keypoints
+    pair_ptr = np.zeros(n * n + 1, np.int64)
+    segs = []
+    for j in range(n):
+        for i in range(n):
+            a = np.asarray(matchesAll[i][j])
+            cnt = a.shape[0] if (a.ndim == 2 and i < j) else 0
+            pair_ptr[i + j * n + 1] = cnt
+            if cnt:
+                segs.append(np.ascontiguousarray(a, np.float64).astype(np.uint32))
+    pair_ptr = np.cumsum(pair_ptr)
+    rows = np.ascontiguousarray(np.vstack(segs), np.uint32) if segs else np.zeros((0, 2), np.uint32)
+    kps = [np.asarray(k, np.float64).reshape(-1, 2) for k in keypoints]
+    img_off = np.concatenate([[0], np.cumsum([k.shape[0] for k in kps])]).astype(np.int64)
+    kp = np.ascontiguousarray(np.vstack(kps)) if img_off[-1] else np.zeros((0, 2))
+    md, conf, mt = _ransac_params(input)
+    P = lin.size
+    total = int(sum(pair_ptr[c + 1] - pair_ptr[c] for c in lin))
+    if samples is not None:
+        samples = np.ascontiguousarray(samples, np.uint32).reshape(P, -1, 4)
+    n_draws = samples.shape[1] if samples is not None else 2 * mt
+    ptr = np.zeros(P + 1, np.int64)
+    models, minv = np.full((P, 3, 3), np.nan), np.full((P, 3, 3), np.nan)
+    inl, ni = np.zeros(max(total, 1), np.uint8), np.zeros(P, np.int32)
+    acc, du = np.zeros(P, np.uint8), np.zeros(P, np.int32)
+    check(lib().aps_image_matching(ctx.handle, n, _ptr(pair_ptr), _ptr(rows), _ptr(kp), _ptr(img_off), _ptr(lin), P, md,
+                                   conf, mt, _ptr(samples) if samples is not None else C.c_void_p(0), n_draws, int(seed),
+                                   _ptr(ptr), _ptr(models), _ptr(minv), _ptr(inl), _ptr(ni), _ptr(acc), _ptr(du)))
+    for p, c in enumerate(lin):
+        if not acc[p]:
+            continue
+        i, j = int(c % n), int(c // n)
+        m = np.asarray(matchesAll[i][j], np.float64)
+        allMatches[i][j] = m[inl[ptr[p]:ptr[p + 1]].astype(bool)]  # imageMatching.m:148
+        numMatches[i, j] = ni[p]
+        tforms[i][j], tforms[j][i] = models[p], minv[p]  # :150-151, :165-166
+    imageMatching.last = dict(pairs_lin=lin, pt_ptr=ptr, n_inliers=ni, accepted=acc.astype(bool), draws_used=du,
+                              models=models, inliers=inl[:total].astype(bool))
+    return allMatches, numMatches, tforms
+
+
 class GlobalPlan:
     """Staged global pipeline (aps_gplan_*): the building block bench.py and the multi-GPU host use."""
 

@@ -114,3 +114,36 @@ def make_config(cid, n=None, kp=None):
         c["kp"] = kp
     desc = synth_descriptors(c["kind"], c["n"], c["kp"], c["D"], 20070000 + cid, ring=c["ring"], empty=c["empty"])
     return desc, c
+
+
+def synth_matched_keypoints(n, kp, seed, per_pair=(0.25, 0.10), inlier_frac=(0.7, 0.5), noise=0.6, size=2000.0,
+                            stray=12):
+    """Synthetic input of the consumer stage (imageMatching.m): keypoints [kp x 2] per image and the n x n
+    nested list of putative match rows ([M x 2] float64, 1-based) of images on a ring.  Pair (i, i+1) gets
+    per_pair[0]*kp matches of which inlier_frac[0] follow a random mild homography of image i+1 -> image i
+    (+ gaussian pixel noise), pair (i, i+2) per_pair[1]*kp with inlier_frac[1]; every other pair gets `stray`
+    random rows.  Returns (keypoints, matchesAll, truth) with truth[(i, j)] = H mapping image j points to image i."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    keypoints = [rng.uniform(0.0, size, (kp, 2)) for _ in range(n)]
+    matches = [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]
+    truth = {}
+    for i in range(n):
+        for j in range(i + 1, n):
+            gap = min(j - i, n - (j - i))
+            if gap in (1, 2) and n > gap:
+                m = int(per_pair[gap - 1] * kp)
+                H = np.eye(3) + rng.normal(0.0, 1.0, (3, 3)) * np.array([[0.06, 0.06, 80.0], [0.06, 0.06, 80.0],
+                                                                           [3e-5, 3e-5, 0.0]])
+                ri = rng.permutation(kp)[:m]
+                rj = rng.permutation(kp)[:m]
+                good = rng.random(m) < inlier_frac[gap - 1]
+                # move the matched keypoints of image i onto H * (keypoints of image j) for the inliers
+                pj = np.c_[keypoints[j][rj], np.ones(m)]
+                q = (H @ pj.T).T
+                q = q[:, :2] / q[:, 2:3] + rng.normal(0.0, noise, (m, 2))
+                keypoints[i][ri[good]] = q[good]
+                matches[i][j] = np.c_[ri + 1, rj + 1].astype(np.float64)
+                truth[(i, j)] = H
+            elif stray:
+                matches[i][j] = np.c_[rng.integers(1, kp + 1, stray), rng.integers(1, kp + 1, stray)].astype(np.float64)
+    return keypoints, matches, truth

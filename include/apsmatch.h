@@ -160,6 +160,44 @@ void aps_matchlist_free(aps_matchlist* m);
 int aps_select_partners(aps_ctx* ctx, const int64_t* counts, int n, int m, uint8_t* cand, int64_t* pairs_lin,
                         int64_t* npairs);
 
+/* ---- consumer of the match lists: batched RANSAC homographies ---------------
+ * Replaces the parfor of PP/imageMatching/imageMatching.m:121-156 with its callee
+ * PP/imageMatching/estimateTransformationRANSAC.m ('projective' = PP/inputs.m:73; :94-183 loop + refit on
+ * all inliers, :188-225 normalised DLT, :444-516 symmetric transfer error, :518-530 checkModel,
+ * :532-572 isDegenerate).  All trials of all pairs are evaluated in parallel (one thread per trial),
+ * then the reference's sequential bookkeeping (best model, adaptive trial bound) is replayed.
+ *
+ * Candidate pair p owns correspondences pt_ptr[p] .. pt_ptr[p+1] (pt_ptr[0] = 0) of pts1 / pts2
+ * ([total x 2] ROW-major doubles): pts1 = matchedPoints1 = keypoints of image jj, pts2 = keypoints of
+ * image ii (refineMatch passes (matchedPts_2, matchedPts_1), imageMatching.m:242); the model maps pts1 -> pts2.
+ * Random minimal samples: `samples` [n_pairs x n_draws x 4] zero-based row indices within the pair, or NULL
+ * to draw them on the device from `seed` (aps_ransac_sample_table returns exactly that table).  Loop
+ * iteration d of a pair consumes draw d (valid or skipped); the loop also ends when the table is exhausted
+ * (n_draws >= 2 * max_trials reproduces the reference unless more than max_trials samples are invalid).
+ * max_distance / confidence / max_trials = input.maxDistance / inliersConfidence / maxIter (PP/inputs.m:68-72).
+ * Outputs (caller-allocated): models, models_inv [n_pairs x 9] ROW-major 3x3 (tforms{ii,jj}, tforms{jj,ii} =
+ * inv(model); NaN when nothing was found / not accepted), inliers [total] 0/1, n_inliers, accepted
+ * (ni > 8 + 0.3 nf, imageMatching.m:147; pairs with nf < 4 are skipped as in :133), draws_used.
+ * Double precision; per-trial arithmetic is round-to-nearest in a fixed order. */
+int aps_ransac_sample_table(aps_ctx* ctx, const int64_t* pt_ptr, int64_t n_pairs, int64_t n_draws, uint64_t seed,
+                            uint32_t* samples);
+int aps_image_matching_batch(aps_ctx* ctx, int64_t n_pairs, const int64_t* pt_ptr, const double* pts1,
+                             const double* pts2, double max_distance, double confidence, int max_trials,
+                             const uint32_t* samples, int64_t n_draws, uint64_t seed, double* models,
+                             double* models_inv, uint8_t* inliers, int32_t* n_inliers, uint8_t* accepted,
+                             int32_t* draws_used);
+/* Same, fed directly by the match lists (hand-off): pair_ptr / rows = the CSR of the
+ * n x n cell (aps_matchlist_pair_ptr / _rows), keypoints = pooled [F x 2] ROW-major doubles of all images,
+ * img_off [n_images + 1], pairs_lin = find(candidatePairs) from aps_select_partners.  The matched points are
+ * gathered on the device (refineMatch, imageMatching.m:224-227; out-of-range indices -> error id
+ * refineMatch:MatchIndexOutOfBounds).  pt_ptr_out [n_pairs + 1] receives the offsets of each pair's
+ * correspondences inside `inliers` (allMatches{ii,jj} = matches(inliers,:)). */
+int aps_image_matching(aps_ctx* ctx, int n_images, const int64_t* pair_ptr, const uint32_t* rows,
+                       const double* keypoints, const int64_t* img_off, const int64_t* pairs_lin, int64_t n_pairs,
+                       double max_distance, double confidence, int max_trials, const uint32_t* samples,
+                       int64_t n_draws, uint64_t seed, int64_t* pt_ptr_out, double* models, double* models_inv,
+                       uint8_t* inliers, int32_t* n_inliers, uint8_t* accepted, int32_t* draws_used);
+
 /* ---- staged global pipeline (building block of the multi-GPU host; bench.py times these) -----
  * All work is enqueued on the context's stream.  Query rows [q0,q1) of the pooled matrix may be
  * sharded across ranks: every rank holds all descriptors, so a query's neighbours are complete
