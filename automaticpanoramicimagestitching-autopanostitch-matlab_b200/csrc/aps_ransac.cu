@@ -9,15 +9,18 @@
 // The reference loop is sequential only through its bookkeeping (best model so far, adaptive trial bound);
 // given the minimal samples, every trial is independent.  So:
 //   K-R1 k_ransac_samples : counter-based generator of n_draws x 4 distinct indices per pair (randperm stand-in)
-//   K-R2 k_ransac_draws   : ONE THREAD PER (pair, draw): normalised DLT of the 4 correspondences (A'A, cyclic
-//                           Jacobi), checkModel, then a sequential sweep over the pair's correspondences
-//                           (symmetric transfer error, inlier count, error sum, degeneracy of the consensus
-//                           set).  Every operation is an explicit round-to-nearest intrinsic in the oracle's
-//                           order, so (count, mean error) per draw carry the oracle's bits.
+//   K-R2a k_ransac_models : one THREAD per (pair, draw): normalised DLT of the 4 correspondences (A'A, cyclic
+//                           Jacobi) and checkModel -> table of candidate models.
+//   K-R2b k_ransac_eval   : one WARP per (pair, draw): lanes stride over the pair's correspondences (symmetric
+//                           transfer error, consensus count, error sum, degeneracy of the consensus set;
+//                           lane partial sums combined by a fixed butterfly).  Every operation is an explicit
+//                           round-to-nearest intrinsic in the oracle's order, so (count, mean error) per draw
+//                           carry the oracle's bits.  Draws are evaluated in waves [0,64) [64,256) [256,n):
+//                           a pair whose loop has ended (adaptive bound) takes no part in later waves.
 //   K-R3 k_ransac_scan    : one thread per pair replays the reference's bookkeeping over the per-draw results:
 //                           trial / skipTrials counters, best = (more inliers, then smaller mean error),
 //                           maxTrials = min(maxTrials, ceil(log(1-conf)/log(1-ratio^4))).
-//   K-R4 k_ransac_final   : one CTA per pair: best model again, its inlier mask, refit on all inliers
+//   K-R4 k_ransac_final   : one CTA per pair: inlier mask of the best model, refit on all inliers
 //                           (block-wide reductions for the centroids and A'A, Jacobi on one thread),
 //                           checkModel + findInliers of the refit, acceptance rule, inverse.
 // Work per draw ~ 250 double operations per correspondence; bound = FP64 pipe.  Data: 32 B per
@@ -287,51 +290,76 @@ __global__ void k_ransac_samples(const int64_t* __restrict__ pt_ptr, int64_t n_d
   out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 
-// K-R2: one thread per (pair, draw).  cnt_out = -1: sample skipped (invalid model); otherwise the size of the
-// consensus set (0 when it is degenerate) and, for cnt >= 4, its mean error.
-__global__ void __launch_bounds__(128) k_ransac_draws(const int64_t* __restrict__ pt_ptr, const double2* __restrict__ p1,
-                                                      const double2* __restrict__ p2, const uint32_t* __restrict__ samples,
-                                                      int64_t n_draws, double thr, int32_t* __restrict__ cnt_out,
-                                                      double* __restrict__ err_out) {
+// K-R2a: one thread per (pair, draw): normalised DLT of the four sampled correspondences + checkModel.
+// Hs[slot] = the 3x3 model (row-major); cnt_out[slot] = -1 marks a skipped sample.
+__global__ void __launch_bounds__(128) k_ransac_models(const int64_t* __restrict__ pt_ptr, const double2* __restrict__ p1,
+                                                       const double2* __restrict__ p2, const uint32_t* __restrict__ samples,
+                                                       int64_t n_draws, int64_t d0, int64_t d1,
+                                                       const uint8_t* __restrict__ done, double* __restrict__ Hs,
+                                                       int32_t* __restrict__ cnt_out, double* __restrict__ err_out) {
   const int64_t pair = blockIdx.y;
-  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= n_draws) return;
+  const int64_t d = d0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= d1 || done[pair]) return;  // the pair's loop already ended inside an earlier wave of draws
   const int64_t o = pt_ptr[pair], n = pt_ptr[pair + 1] - o;
   const int64_t slot = pair * n_draws + d;
-  if (n < 4) {
-    cnt_out[slot] = -1;
-    err_out[slot] = CUDART_INF;
-    return;
-  }
-  const double2* q1 = p1 + o;
-  const double2* q2 = p2 + o;
+  cnt_out[slot] = -1;
+  err_out[slot] = CUDART_INF;
+  if (n < 4) return;
   uint32_t s[4];
   for (int i = 0; i < 4; ++i) s[i] = samples[slot * 4 + i];
   double H[9];
-  homography4(q1, q2, s, H);
-  if (!check_model(H)) {
-    cnt_out[slot] = -1;
-    err_out[slot] = CUDART_INF;
-    return;
-  }
+  homography4(p1 + o, p2 + o, s, H);
+  if (!check_model(H)) return;
+  for (int i = 0; i < 9; ++i) Hs[slot * 9 + i] = H[i];
+  cnt_out[slot] = 0;
+}
+
+// butterfly total of the lanes' partial sums (offsets 16, 8, 4, 2, 1): every lane ends with the same bits
+__device__ __forceinline__ double warp_total(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = ADD(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// K-R2b: one WARP per (pair, draw): lanes stride over the pair's correspondences (point r -> lane r mod 32),
+// symmetric transfer error, consensus count, error sum and the degeneracy test of the consensus set.
+// cnt_out = size of the consensus set (0 when degenerate), err_out = its mean error (cnt >= 4).
+__global__ void __launch_bounds__(128) k_ransac_eval(const int64_t* __restrict__ pt_ptr, const double2* __restrict__ p1,
+                                                     const double2* __restrict__ p2, int64_t n_draws, int64_t d0,
+                                                     int64_t d1, const uint8_t* __restrict__ done,
+                                                     const double* __restrict__ Hs, double thr,
+                                                     int32_t* __restrict__ cnt_out, double* __restrict__ err_out) {
+  const int64_t pair = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t d = d0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (d >= d1 || done[pair]) return;
+  const int64_t slot = pair * n_draws + d;
+  if (cnt_out[slot] < 0) return;  // skipped sample (warp-uniform)
+  const int64_t o = pt_ptr[pair], n = pt_ptr[pair + 1] - o;
+  const double2* q1 = p1 + o;
+  const double2* q2 = p2 + o;
+  double H[9];
+  for (int i = 0; i < 9; ++i) H[i] = Hs[slot * 9 + i];
   LU3 f;
   lu3(H, f);
-  int32_t cnt = 0;
+  int32_t c = 0;
   double es = 0.0, sx = 0.0, sy = 0.0;
-  for (int64_t r = 0; r < n; ++r) {
+  for (int64_t r = lane; r < n; r += 32) {
     const double2 a = q1[r], b = q2[r];
     const double e = point_error(H, f, a.x, a.y, b.x, b.y);
     if (e < thr) {
-      ++cnt;
+      ++c;
       es = ADD(es, e);
       sx = ADD(sx, a.x);
       sy = ADD(sy, a.y);
     }
   }
+  int32_t cnt = __reduce_add_sync(0xffffffffu, c);
+  es = warp_total(es);
   if (cnt >= 4) {
-    const double mx = DIV(sx, (double)cnt), my = DIV(sy, (double)cnt);
+    const double mx = DIV(warp_total(sx), (double)cnt), my = DIV(warp_total(sy), (double)cnt);
     double sxx = 0.0, sxy = 0.0, syy = 0.0;
-    for (int64_t r = 0; r < n; ++r) {
+    for (int64_t r = lane; r < n; r += 32) {
       const double2 a = q1[r], b = q2[r];
       const double e = point_error(H, f, a.x, a.y, b.x, b.y);
       if (e < thr) {
@@ -341,18 +369,22 @@ __global__ void __launch_bounds__(128) k_ransac_draws(const int64_t* __restrict_
         syy = ADD(syy, MUL(dy, dy));
       }
     }
-    if (degenerate_ratio(sxx, sxy, syy)) cnt = 0;
+    if (degenerate_ratio(warp_total(sxx), warp_total(sxy), warp_total(syy))) cnt = 0;
   }
-  cnt_out[slot] = cnt;
-  err_out[slot] = (cnt >= 4) ? DIV(es, (double)cnt) : CUDART_INF;
+  if (lane == 0) {
+    cnt_out[slot] = cnt;
+    err_out[slot] = (cnt >= 4) ? DIV(es, (double)cnt) : CUDART_INF;
+  }
 }
 
 // K-R3: the reference's sequential bookkeeping over the per-draw results
 __global__ void k_ransac_scan(int64_t n_pairs, const int64_t* __restrict__ pt_ptr, const int32_t* __restrict__ cnt,
-                              const double* __restrict__ err, int64_t n_draws, double confidence, int max_trials_in,
-                              int32_t* __restrict__ best_draw, int32_t* __restrict__ draws_used) {
+                              const double* __restrict__ err, int64_t n_draws, int64_t d_limit, double confidence,
+                              int max_trials_in, int32_t* __restrict__ best_draw, int32_t* __restrict__ draws_used,
+                              uint8_t* __restrict__ done) {
   const int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= n_pairs) return;
+  if (done[pair]) return;  // finished in an earlier wave: results stand
   const int64_t n = pt_ptr[pair + 1] - pt_ptr[pair];
   int32_t best = -1, bestCnt = 0;
   double bestErr = CUDART_INF;
@@ -362,7 +394,7 @@ __global__ void k_ransac_scan(int64_t n_pairs, const int64_t* __restrict__ pt_pt
     const int64_t maxSkip = (int64_t)max_trials_in * 10;
     int64_t trial = 1, skip = 0;
     const double lc = log(SUB(1.0, DIV(confidence, 100.0)));
-    while ((double)trial <= maxTrials && skip < maxSkip && d < n_draws) {
+    while ((double)trial <= maxTrials && skip < maxSkip && d < d_limit) {
       const int32_t c = cnt[pair * n_draws + d];
       const double e = err[pair * n_draws + d];
       const int32_t dd = (int32_t)d;
@@ -384,6 +416,10 @@ __global__ void k_ransac_scan(int64_t n_pairs, const int64_t* __restrict__ pt_pt
       }
       ++trial;
     }
+    // the reference's loop ended by its own conditions (not because this wave of draws ran out)
+    done[pair] = !((double)trial <= maxTrials && skip < maxSkip) || d_limit >= n_draws;
+  } else {
+    done[pair] = 1;
   }
   best_draw[pair] = best;
   draws_used[pair] = (int32_t)d;
@@ -402,7 +438,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // K-R4: one CTA per pair: refit on the consensus set of the best draw and the reference's final decisions
 __global__ void __launch_bounds__(256) k_ransac_final(const int64_t* __restrict__ pt_ptr, const double2* __restrict__ p1,
-                                                      const double2* __restrict__ p2, const uint32_t* __restrict__ samples,
+                                                      const double2* __restrict__ p2, const double* __restrict__ Hs_tab,
                                                       int64_t n_draws, double thr, const int32_t* __restrict__ best_draw,
                                                       uint8_t* __restrict__ mask_best, double* __restrict__ models,
                                                       double* __restrict__ models_inv, uint8_t* __restrict__ inliers,
@@ -424,13 +460,7 @@ __global__ void __launch_bounds__(256) k_ransac_final(const int64_t* __restrict_
     if (tid == 0) { n_inliers[pair] = 0; accepted[pair] = 0; }
     return;
   }
-  if (tid == 0) {
-    uint32_t s[4];
-    for (int i = 0; i < 4; ++i) s[i] = samples[(pair * n_draws + bd) * 4 + i];
-    double H[9];
-    homography4(q1, q2, s, H);
-    for (int i = 0; i < 9; ++i) Hs[i] = H[i];
-  }
+  if (tid < 9) Hs[tid] = Hs_tab[(pair * n_draws + bd) * 9 + tid];
   __syncthreads();
   double H[9];
   for (int i = 0; i < 9; ++i) H[i] = Hs[i];
@@ -570,18 +600,33 @@ static int ransac_device(aps_ctx* c, int64_t n_pairs, int64_t total, const int64
     APS_LAUNCHED();
   }
   DevBuf<int32_t> cnt, best;
-  DevBuf<double> err;
-  DevBuf<uint8_t> mask;
+  DevBuf<double> err, Htab;
+  DevBuf<uint8_t> mask, done;
+  APS_TRY(Htab.alloc((size_t)(n_pairs * n_draws) * 9, s));
+  APS_TRY(done.alloc((size_t)n_pairs, s));
+  APS_CUDA(cudaMemsetAsync(done.p, 0, (size_t)n_pairs, s));
   APS_TRY(cnt.alloc((size_t)(n_pairs * n_draws), s));
   APS_TRY(err.alloc((size_t)(n_pairs * n_draws), s));
   APS_TRY(best.alloc((size_t)n_pairs, s));
   APS_TRY(mask.alloc((size_t)(total > 0 ? total : 1), s));
-  k_ransac_draws<<<gd, 128, 0, s>>>(d_ptr, d_p1, d_p2, d_samples, n_draws, max_distance, cnt.p, err.p);
-  APS_LAUNCHED();
-  k_ransac_scan<<<(unsigned)((n_pairs + 63) / 64), 64, 0, s>>>(n_pairs, d_ptr, cnt.p, err.p, n_draws, confidence,
-                                                               max_trials, best.p, d_used);
-  APS_LAUNCHED();
-  k_ransac_final<<<(unsigned)n_pairs, 256, 0, s>>>(d_ptr, d_p1, d_p2, d_samples, n_draws, max_distance, best.p, mask.p,
+  // Draws are evaluated in waves [0,64), [64,256), [256,n_draws): the adaptive trial bound ends most loops
+  // within the first wave, and a pair whose loop has ended takes no part in later waves.  Every wave
+  // replays the bookkeeping from draw 0, so the outcome is that of one sequential pass.
+  const int64_t edges[4] = {0, 64, 256, n_draws};
+  for (int w = 0; w < 3; ++w) {
+    const int64_t d0 = edges[w] < n_draws ? edges[w] : n_draws, d1 = edges[w + 1] < n_draws ? edges[w + 1] : n_draws;
+    if (d1 <= d0) continue;
+    const dim3 gm((unsigned)((d1 - d0 + 127) / 128), (unsigned)n_pairs);
+    k_ransac_models<<<gm, 128, 0, s>>>(d_ptr, d_p1, d_p2, d_samples, n_draws, d0, d1, done.p, Htab.p, cnt.p, err.p);
+    APS_LAUNCHED();
+    const dim3 ge((unsigned)((d1 - d0 + 3) / 4), (unsigned)n_pairs);
+    k_ransac_eval<<<ge, 128, 0, s>>>(d_ptr, d_p1, d_p2, n_draws, d0, d1, done.p, Htab.p, max_distance, cnt.p, err.p);
+    APS_LAUNCHED();
+    k_ransac_scan<<<(unsigned)((n_pairs + 63) / 64), 64, 0, s>>>(n_pairs, d_ptr, cnt.p, err.p, n_draws, d1, confidence,
+                                                                 max_trials, best.p, d_used, done.p);
+    APS_LAUNCHED();
+  }
+  k_ransac_final<<<(unsigned)n_pairs, 256, 0, s>>>(d_ptr, d_p1, d_p2, Htab.p, n_draws, max_distance, best.p, mask.p,
                                                    d_models, d_minv, d_inl, d_ninl, d_acc);
   APS_LAUNCHED();
   return APS_OK;

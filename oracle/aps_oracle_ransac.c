@@ -18,6 +18,9 @@
  *     10*maxTrials skipped samples; identical unless more than n_draws - maxTrials samples are invalid);
  *   - V(:,end) of svd(A) is computed as the eigenvector of the smallest eigenvalue of A'A (cyclic Jacobi);
  *   - singular values of the centred n x 2 inlier matrix (isDegenerate) come from its 2 x 2 Gram matrix;
+ *   - sums over a pair's correspondences (inlier errors, centroid, scatter matrix in findInliers / isDegenerate)
+ *     use 32 interleaved partial accumulators (point r -> accumulator r mod 32) combined by a fixed butterfly
+ *     (offsets 16, 8, 4, 2, 1); MATLAB's own sum order is unspecified (multithreaded for long vectors);
  *   - rcond(H) is the exact 1-norm reciprocal condition number (MATLAB: LAPACK's estimate of it);
  *   - H \ x uses a 3 x 3 LU factorisation with partial pivoting, T2 \ X back-substitution (T2 is triangular).
  */
@@ -214,6 +217,16 @@ static double point_error(const double H[9], const lu3_t* f, const double* p1, c
   return e;
 }
 
+/* total of 32 interleaved partial sums, butterfly order */
+static double lane_total(double a[32]) {
+  double t[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < 32; ++l) t[l] = a[l] + a[l ^ o];
+    memcpy(a, t, sizeof t);
+  }
+  return a[0];
+}
+
 /* findInliers (:444-516) incl. isDegenerate (:532-572) on the inliers' source points.
  * returns the inlier count (0 when degenerate) and their error sum */
 static int64_t find_inliers(const double H[9], const double* p1, const double* p2, int64_t n, double thr,
@@ -221,28 +234,31 @@ static int64_t find_inliers(const double H[9], const double* p1, const double* p
   lu3_t f;
   lu3(H, &f);
   int64_t cnt = 0;
-  double es = 0.0, sx = 0.0, sy = 0.0;
+  double esl[32] = {0}, sxl[32] = {0}, syl[32] = {0};
   for (int64_t r = 0; r < n; ++r) {
     const double e = point_error(H, &f, p1, p2, r);
     const int in = e < thr;
     mask[r] = (uint8_t)in;
     if (in) {
       ++cnt;
-      es += e;
-      sx += p1[2 * r];
-      sy += p1[2 * r + 1];
+      esl[r & 31] += e;
+      sxl[r & 31] += p1[2 * r];
+      syl[r & 31] += p1[2 * r + 1];
     }
   }
+  double es = lane_total(esl);
+  const double sx = lane_total(sxl), sy = lane_total(syl);
   if (cnt >= 4) {
     const double mx = sx / (double)cnt, my = sy / (double)cnt;
-    double sxx = 0.0, sxy = 0.0, syy = 0.0;
+    double sxxl[32] = {0}, sxyl[32] = {0}, syyl[32] = {0};
     for (int64_t r = 0; r < n; ++r)
       if (mask[r]) {
         const double dx = p1[2 * r] - mx, dy = p1[2 * r + 1] - my;
-        sxx += dx * dx;
-        sxy += dx * dy;
-        syy += dy * dy;
+        sxxl[r & 31] += dx * dx;
+        sxyl[r & 31] += dx * dy;
+        syyl[r & 31] += dy * dy;
       }
+    const double sxx = lane_total(sxxl), sxy = lane_total(sxyl), syy = lane_total(syyl);
     /* singular values^2 of the centred matrix = eigenvalues of [sxx sxy; sxy syy] */
     const double hd = 0.5 * (sxx - syy);
     const double l1 = 0.5 * (sxx + syy) + sqrt(hd * hd + sxy * sxy);
