@@ -1,6 +1,7 @@
 // shim_driver.cpp -- exercises one gateway (compiled together with it) under the mex shim.
 // Without a GPU only the argument validation is checked (it happens before any CUDA call and must
 // raise the reference's identifiers); with a GPU (argv[1] == "gpu") a small real call runs too.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -83,6 +84,47 @@ int main(int argc, char** argv) {
     mexFunction(1, out, 5, in);
     const mxArray* c01 = mxGetCell(out[0], 2);  // cell (1,2) -> linear index 0 + 1*2
     bad += !(c01 && mxIsDouble(c01) && mxGetN(c01) == 2 && mxGetM(c01) >= 3);
+  }
+#elif defined(GATE_IMATCH)
+  mxArray* kp = mxCreateCellMatrix(1, 2);
+  mxArray* mm = mxCreateCellMatrix(2, 2);
+  mxArray* m3 = mxCreateCellMatrix(2, 3);
+  mxArray *six = mxCreateDoubleScalar(6), *md = mxCreateDoubleScalar(5.5), *cf = mxCreateDoubleScalar(99.9), *it = mxCreateDoubleScalar(500);
+  { const mxArray* in[] = {kp, mm, six}; bad += expect_error("apsmatch:args", 3, 3, in); }
+  { const mxArray* in[] = {kp, m3, six, md, cf, it}; bad += expect_error("imageMatching:InvalidMatchesAllSize", 3, 6, in); }
+  { mxArray* kp3 = mxCreateCellMatrix(1, 3);
+    const mxArray* in[] = {kp3, mm, six, md, cf, it}; bad += expect_error("imageMatching:InvalidKeypointsLength", 3, 6, in); }
+  if (gpu) {
+    // image 2 = image 1 shifted by (10, -5): 40 correspondences, 30 exact + 10 wrong
+    const int N = 40;
+    mxArray *k1 = mxCreateDoubleMatrix(N, 2, mxREAL), *k2 = mxCreateDoubleMatrix(N, 2, mxREAL), *m12 = mxCreateDoubleMatrix(N, 2, mxREAL);
+    for (int r = 0; r < N; ++r) {
+      const double x = (double)((r * 37) % 101) * 7.0, y = (double)((r * 53) % 89) * 9.0;
+      mxGetPr(k1)[r] = x; mxGetPr(k1)[r + N] = y;
+      mxGetPr(k2)[r] = (r < 30) ? x - 10.0 : (double)((r * 11) % 97) * 5.0;
+      mxGetPr(k2)[r + N] = (r < 30) ? y + 5.0 : (double)((r * 29) % 83) * 3.0;
+      mxGetPr(m12)[r] = r + 1; mxGetPr(m12)[r + N] = r + 1;
+    }
+    mxSetCell(kp, 0, k1); mxSetCell(kp, 1, k2); mxSetCell(mm, 2, m12);
+    mxArray* out[3] = {nullptr, nullptr, nullptr};
+    const mxArray* in[] = {kp, mm, six, md, cf, it};
+    mexFunction(3, out, 6, in);
+    const mxArray* a12 = mxGetCell(out[0], 2);
+    const mxArray* t12 = mxGetCell(out[2], 2);
+    bad += !(a12 && mxGetM(a12) == 30 && mxGetN(a12) == 2 && mxGetPr(out[1])[2] == 30.0);
+    if (t12) {  // model maps image 2 keypoints to image 1: translation (+10, -5); column-major 3x3
+      const double* t = mxGetPr(t12);
+      bad += !(std::fabs(t[6] / t[8] - 10.0) < 1e-6 && std::fabs(t[7] / t[8] + 5.0) < 1e-6 && std::fabs(t[0] / t[8] - 1.0) < 1e-8);
+    } else {
+      ++bad;
+    }
+    bad += mxGetCell(out[2], 1) == nullptr;  // tforms{2,1} = inv(model)
+  } else {
+    mxArray *k1 = mxCreateDoubleMatrix(5, 2, mxREAL), *k2 = mxCreateDoubleMatrix(5, 2, mxREAL), *m12 = mxCreateDoubleMatrix(5, 2, mxREAL);
+    for (int r = 0; r < 10; ++r) mxGetPr(m12)[r] = (r % 5) + 1;
+    mxSetCell(kp, 0, k1); mxSetCell(kp, 1, k2); mxSetCell(mm, 2, m12);
+    const mxArray* in[] = {kp, mm, six, md, cf, it};
+    bad += expect_error("apsmatch:nogpu", 3, 6, in);  // no CPU fallback
   }
 #endif
   std::printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
