@@ -222,6 +222,9 @@ struct KParams {
   int64_t tile_lo;      // first TN-column tile (global tile grid)
   int64_t tile_hi;      // one past the last tile
   int tiles_per_seg;    // tiles per segment of a tail unit
+  int tail_balanced;    // 1: the tail's tile steps (tail_units x tiles, unit-major) are cut into `grid` equal
+                        //    contiguous shares, one per CTA (<= 2 pieces per CTA, <= nslot pieces per unit)
+  int grid;             // CTAs launched (balanced tail only)
   const float* colscale;  // [Ft_total + 256] per train row
   const float* colbias;   // [Ft_total + 256] per train row (read only by the BIAS variant)
   const float4* tile_bounds;  // per train tile: (1/scale_max, 1/scale_min, bias_max, -), 1e-6 safety included
@@ -241,26 +244,44 @@ struct Unit {
   int64_t out_row;   // candidate-buffer row of qrow0
   int64_t tl, th;    // tile range
   int seg;           // candidate list this unit fills
-  bool full;         // spans all tiles: also clears the row's unused lists
+  int clear_from;    // this unit also marks the row's lists [clear_from, nslot) empty (nslot: none)
+  bool skip;         // no work (balanced tail: a CTA's share may lie inside one unit)
 };
 __device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
   Unit x;
   if (P.unit_table) {
     const aps_tc_unit t = P.unit_table[u];
     x.qrow0 = t.qrow0; x.qend = t.qend; x.t0 = t.t0; x.t1 = t.t1; x.out_row = t.out_row;
-    x.tl = t.t0 / TN; x.th = (t.t1 + TN - 1) / TN; x.seg = 0; x.full = true;
+    x.tl = t.t0 / TN; x.th = (t.t1 + TN - 1) / TN; x.seg = 0; x.clear_from = 1; x.skip = false;
     return x;
   }
   int64_t rb2;
+  x.skip = false;
   if (u < P.units_full) {
-    rb2 = u; x.tl = P.tile_lo; x.th = P.tile_hi; x.seg = 0; x.full = true;
+    rb2 = u; x.tl = P.tile_lo; x.th = P.tile_hi; x.seg = 0; x.clear_from = CSPLIT;
+  } else if (P.tail_balanced) {
+    const int64_t v = u - P.units_full, G = P.grid;
+    const int64_t j = v % G, k = v / G;  // CTA j's k-th piece (k = 0, 1); units_full is a multiple of G
+    const int64_t T = P.tile_hi - P.tile_lo, W = (int64_t)P.tail_units * T;
+    const int64_t w0 = j * W / G, w1 = (j + 1) * W / G;
+    const int64_t r0 = w0 / T, r = r0 + k;
+    const int64_t a = (k == 0) ? w0 - r0 * T : 0;
+    const int64_t b = min(T, w1 - r * T);
+    x.skip = (w1 <= w0) || (b <= a);
+    const int64_t own0 = ((r * T + 1) * G - 1) / W;  // CTA whose share holds the unit's first tile step
+    const int64_t ownl = ((r * T + T) * G - 1) / W;  // ... and its last one
+    x.seg = (int)(j - own0);
+    x.clear_from = (x.seg == 0) ? (int)(ownl - own0 + 1) : P.nslot;
+    rb2 = P.units_full + r;
+    x.tl = P.tile_lo + a;
+    x.th = P.tile_lo + b;
   } else {
     const int64_t v = u - P.units_full;
     x.seg = (int)(v / P.tail_units);                 // segment-major: neighbours share B tiles in L2
     rb2 = P.units_full + (v % P.tail_units);
     x.tl = P.tile_lo + (int64_t)x.seg * P.tiles_per_seg;
     x.th = min(P.tile_hi, x.tl + P.tiles_per_seg);
-    x.full = false;
+    x.clear_from = P.nslot;
   }
   x.qrow0 = P.q0 + rb2 * RB * TM; x.qend = P.q1; x.t0 = P.t0; x.t1 = P.t1; x.out_row = rb2 * RB * TM;
   return x;
@@ -289,7 +310,9 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     P.units_full = 0;
     P.tail_units = (int)((n + RB * TM - 1) / (RB * TM));
   }
-  const int64_t num_units = P.unit_table ? P.n_table_units : (int64_t)P.units_full + (int64_t)P.tail_units * P.tail_seg;
+  const int64_t num_units = P.unit_table ? P.n_table_units
+                            : (P.tail_balanced ? (int64_t)P.units_full + 2 * (int64_t)P.grid
+                                               : (int64_t)P.units_full + (int64_t)P.tail_units * P.tail_seg);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], RB); }
@@ -384,6 +407,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     uint32_t tcount = 0;  // tiles consumed so far (same sequence as the MMA warp's)
     for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
       const Unit x = get_unit(P, u);
+      if (x.skip) continue;  // balanced tail: this CTA's share has no second piece
       const int64_t qrow = x.qrow0 + grp * TM + row_in_tile;
       // row-private top-KC (unsorted; aps_rerank.cu orders exactly): scores in registers, train rows in smem
       float bv[KC];
@@ -527,8 +551,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           P.cand_idx[o + i] = lds_u32(si + i * SLOT_STRIDE);
           P.cand_score[o + i] = bv[i];
         }
-        if (x.full && ch == 0)  // rows of full-width units use the first CSPLIT lists: mark the others empty
-          for (int sl = CSPLIT; sl < P.nslot; ++sl)
+        if (ch == 0)  // e.g. rows of full-width units use the first CSPLIT lists: mark the others empty
+          for (int sl = x.clear_from - x.seg * CSPLIT; sl < P.nslot - x.seg * CSPLIT; ++sl)
             for (int i = 0; i < KC; ++i) {
               P.cand_idx[o + sl * KC + i] = 0xffffffffu;
               P.cand_score[o + sl * KC + i] = -CUDART_INF_F;
@@ -588,11 +612,12 @@ int aps_k_knn_tc_tile_rows() { return TN; }
 
 // Work decomposition shared by the launcher and by callers that size the candidate buffers.
 struct TcSchedule {
-  int units_full, tail_units, tail_seg, nslot, tiles_per_seg;
+  int units_full, tail_units, tail_seg, nslot, tiles_per_seg, tail_balanced;
   int64_t tile_lo, tile_hi;
 };
 static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1, bool all_segmented = false) {
   TcSchedule sc;
+  sc.tail_balanced = 0;
   if (all_segmented) {
     sc.tile_lo = t0 / TN;
     sc.tile_hi = aps_ceil_div(t1, TN);
@@ -613,11 +638,28 @@ static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1
   sc.tail_units = (int)(pairs - sc.units_full);
   sc.tail_seg = 1;
   if (sc.tail_units > 0) {
-    int64_t seg = grid / sc.tail_units;  // fill the last round
-    if (seg > MAX_SEG) seg = MAX_SEG;
-    if (seg > tiles) seg = tiles;
-    if (seg < 1) seg = 1;
+    // segments per tail unit: minimise the length of the last round, ceil(tail_units * s / grid) / s
+    int64_t seg = 1, best_num = aps_ceil_div((int64_t)sc.tail_units, grid), best_den = 1;
+    for (int64_t sg = 2; sg <= MAX_SEG && sg <= tiles; ++sg) {
+      const int64_t num = aps_ceil_div((int64_t)sc.tail_units * sg, grid);
+      if (num * best_den < best_num * sg) { seg = sg; best_num = num; best_den = sg; }
+    }
     sc.tail_seg = (int)seg;
+    // Balanced tail: cut the tail's tile steps (unit-major) into `grid` equal shares.  Length of the last round
+    // = tail_units / grid exactly, at the price of up to ceil(grid / tail_units) + 1 lists per row.
+    if (CSPLIT == 1 && tiles >= 8 && sc.units_full > 0) {
+      const int64_t T = tiles, W = (int64_t)sc.tail_units * T, G = grid;
+      int64_t max_pieces = 0;
+      for (int64_t r = 0; r < sc.tail_units; ++r) {
+        const int64_t own0 = ((r * T + 1) * G - 1) / W, ownl = ((r * T + T) * G - 1) / W;
+        if (ownl - own0 + 1 > max_pieces) max_pieces = ownl - own0 + 1;
+      }
+      // worth it if it shortens the last round by more than 5 %
+      if (max_pieces <= MAX_SEG && (int64_t)sc.tail_units * best_den * 100 < best_num * G * 95) {
+        sc.tail_balanced = 1;
+        sc.tail_seg = (int)max_pieces;
+      }
+    }
   }
   sc.nslot = (sc.tail_units > 0 ? sc.tail_seg : 1) * CSPLIT;
   sc.tiles_per_seg = (int)aps_ceil_div(tiles, sc.tail_seg);
@@ -655,6 +697,8 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.tile_lo = sc.tile_lo;
   P.tile_hi = sc.tile_hi;
   P.tiles_per_seg = sc.tiles_per_seg;
+  P.tail_balanced = sc.tail_balanced;
+  P.grid = sm_count;
   P.colscale = p.colscale;
   P.colbias = p.colbias;
   P.tile_bounds = p.tile_bounds;
@@ -673,7 +717,8 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   // every (row, list) slot is written by exactly one work unit (full-width units clear the unused lists)
   const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
                       (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * CSPLIT * KC * TM * 4 + sizeof(Barriers);
-  const int64_t units = (int64_t)sc.units_full + (int64_t)sc.tail_units * sc.tail_seg;
+  const int64_t units = sc.tail_balanced ? (int64_t)sc.units_full + 2 * (int64_t)sm_count
+                                         : (int64_t)sc.units_full + (int64_t)sc.tail_units * sc.tail_seg;
   const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);  // upper bound in second-pass mode
   if (ev0) APS_CUDA(cudaEventRecord(ev0, s));
   auto launch = [&](auto kern) -> int {

@@ -76,7 +76,8 @@ def test_tc_integer_descriptors_are_exact(aps):
     assert np.array_equal(got.astype(np.float64), exp.astype(np.float32).astype(np.float64))
 
 
-@pytest.mark.parametrize("nq,nt", [(300, 5000), (256 * 150, 700), (256 * 149 + 10, 1300)])
+@pytest.mark.parametrize("nq,nt", [(300, 5000), (256 * 150, 700), (256 * 149 + 10, 1300), (256 * 228, 1536),
+                                   (256 * 208 - 77, 2000)])
 def test_tc_tail_units_split_columns(aps, nq, nt):
     """Work units of the last partial round are split into column segments (several lists per row);
     whatever the split, the union of a row's lists must contain its best columns."""
