@@ -222,8 +222,9 @@ struct KParams {
   int64_t tile_lo;      // first TN-column tile (global tile grid)
   int64_t tile_hi;      // one past the last tile
   int tiles_per_seg;    // tiles per segment of a tail unit
-  int tail_balanced;    // 1: the tail's tile steps (tail_units x tiles, unit-major) are cut into `grid` equal
-                        //    contiguous shares, one per CTA (<= 2 pieces per CTA, <= nslot pieces per unit)
+  int tail_balanced;    // > 0: the tail's tile steps (tail_units x tiles, unit-major) are cut into `grid` equal
+                        //    contiguous shares, one per CTA; value = pieces a share can consist of (2, or 3 when
+                        //    the last full round is merged into the tail); <= nslot pieces per unit
   int grid;             // CTAs launched (balanced tail only)
   const float* colscale;  // [Ft_total + 256] per train row
   const float* colbias;   // [Ft_total + 256] per train row (read only by the BIAS variant)
@@ -261,7 +262,7 @@ __device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
     rb2 = u; x.tl = P.tile_lo; x.th = P.tile_hi; x.seg = 0; x.clear_from = CSPLIT;
   } else if (P.tail_balanced) {
     const int64_t v = u - P.units_full, G = P.grid;
-    const int64_t j = v % G, k = v / G;  // CTA j's k-th piece (k = 0, 1); units_full is a multiple of G
+    const int64_t j = v % G, k = v / G;  // CTA j's k-th piece (k < tail_balanced); units_full is a multiple of G
     const int64_t T = P.tile_hi - P.tile_lo, W = (int64_t)P.tail_units * T;
     const int64_t w0 = j * W / G, w1 = (j + 1) * W / G;
     const int64_t r0 = w0 / T, r = r0 + k;
@@ -311,7 +312,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     P.tail_units = (int)((n + RB * TM - 1) / (RB * TM));
   }
   const int64_t num_units = P.unit_table ? P.n_table_units
-                            : (P.tail_balanced ? (int64_t)P.units_full + 2 * (int64_t)P.grid
+                            : (P.tail_balanced ? (int64_t)P.units_full + (int64_t)P.tail_balanced * P.grid
                                                : (int64_t)P.units_full + (int64_t)P.tail_units * P.tail_seg);
 
   if (threadIdx.x == 0) {
@@ -656,7 +657,23 @@ static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1
       }
       // worth it if it shortens the last round by more than 5 %
       if (max_pieces <= MAX_SEG && (int64_t)sc.tail_units * best_den * 100 < best_num * G * 95) {
-        sc.tail_balanced = 1;
+        sc.tail_balanced = 2;
+        sc.tail_seg = (int)max_pieces;
+      }
+      // Few tail units (cannot be cut finely enough with 4 lists): merge the last full round into the tail, so
+      // that every share is >= one unit long (<= 3 pieces per CTA, <= 2 lists per row).  CTAs of that round no
+      // longer sweep the tiles in lockstep, so only while the bf16 train view stays L2-resident.
+      const double t_cur = sc.tail_balanced ? (double)sc.tail_units / G : (double)best_num / best_den;
+      if ((double)sc.tail_units / G < 0.95 * t_cur && sc.units_full >= G && (t1 - t0) <= 393216) {
+        sc.units_full -= (int)G;
+        sc.tail_units += (int)G;
+        sc.tail_balanced = 3;
+        const int64_t W2 = (int64_t)sc.tail_units * T;
+        max_pieces = 0;
+        for (int64_t r = 0; r < sc.tail_units; ++r) {
+          const int64_t own0 = ((r * T + 1) * G - 1) / W2, ownl = ((r * T + T) * G - 1) / W2;
+          if (ownl - own0 + 1 > max_pieces) max_pieces = ownl - own0 + 1;
+        }
         sc.tail_seg = (int)max_pieces;
       }
     }
@@ -717,7 +734,7 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   // every (row, list) slot is written by exactly one work unit (full-width units clear the unused lists)
   const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
                       (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * CSPLIT * KC * TM * 4 + sizeof(Barriers);
-  const int64_t units = sc.tail_balanced ? (int64_t)sc.units_full + 2 * (int64_t)sm_count
+  const int64_t units = sc.tail_balanced ? (int64_t)sc.units_full + (int64_t)sc.tail_balanced * sm_count
                                          : (int64_t)sc.units_full + (int64_t)sc.tail_units * sc.tail_seg;
   const unsigned grid = (unsigned)(units < sm_count ? units : sm_count);  // upper bound in second-pass mode
   if (ev0) APS_CUDA(cudaEventRecord(ev0, s));

@@ -70,6 +70,24 @@ def test_c2_full_size_float(aps, orc):
     assert np.array_equal(pair_ptr, pp2) and np.array_equal(rows, rows2)
 
 
+def test_c2_query_ranges_with_merged_and_balanced_tails(aps):
+    """Query ranges whose unit count leaves a short tail (the scheduler merges the last full round into a balanced
+    tail: two lists per row) must return the bits of the one-range run."""
+    ctx = aps._lib.default_context()
+    desc, c = aps.synth.make_config(2)
+    plan = aps.GlobalPlan(ctx, [d.shape[0] for d in desc], 128, False, 4)
+    plan.upload(desc)
+    plan.prepare()
+    plan.knn()
+    idx0, dist0 = plan.download_knn()
+    for cuts in ([0, 40448, plan.F], [0, 256 * 228, 256 * 228 + 256 * 300, plan.F]):
+        for q0, q1 in zip(cuts[:-1], cuts[1:]):
+            plan.knn(q0, q1)
+        idx, dist = plan.download_knn()
+        assert np.array_equal(idx, idx0) and np.array_equal(dist.view(np.uint32), dist0.view(np.uint32)), cuts
+    plan.close()
+
+
 def test_c4_large_binary(aps, orc):
     """configs[3] family: ORB 256-bit, BF Hamming k=4 (50 images x 4096 here; 20000/img in BASELINE)."""
     ctx = aps._lib.default_context()

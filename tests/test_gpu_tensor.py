@@ -77,7 +77,7 @@ def test_tc_integer_descriptors_are_exact(aps):
 
 
 @pytest.mark.parametrize("nq,nt", [(300, 5000), (256 * 150, 700), (256 * 149 + 10, 1300), (256 * 228, 1536),
-                                   (256 * 208 - 77, 2000)])
+                                   (256 * 208 - 77, 2000), (256 * 158, 1536)])
 def test_tc_tail_units_split_columns(aps, nq, nt):
     """Work units of the last partial round are split into column segments (several lists per row);
     whatever the split, the union of a row's lists must contain its best columns."""
