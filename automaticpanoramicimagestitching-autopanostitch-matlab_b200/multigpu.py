@@ -36,6 +36,41 @@ def exchange_records(rec, F: int, bounds, dist, group=None):
     return rec
 
 
+def upload_row_block(pool, host_mats, q0: int, q1: int, torch):
+    """Copies rows [q0, q1) of the pooled descriptor matrix from the per-image host matrices (pinned numpy views
+    or tensors, image i = rows off[i]..off[i+1]) into `pool` ([F x D] tensor, device or CPU).  Asynchronous on the
+    current stream when the sources are pinned."""
+    off = 0
+    for m in host_mats:
+        n = int(m.shape[0])
+        a, b = max(q0, off), min(q1, off + n)
+        if b > a:
+            src = m if torch.is_tensor(m) else torch.from_numpy(m)
+            pool[a:b].copy_(src[a - off:b - off], non_blocking=True)
+        off += n
+    return pool
+
+
+def gather_descriptors(pool, host_mats, rank: int, world: int, dist, torch, group=None):
+    """Descriptor hand-over for one process per GPU: every rank uploads ITS block of rows (shard_bounds) from host
+    memory, then the blocks are all-gathered over NVLink, so the host->device traffic is spread over all the
+    ranks' PCIe links instead of one (ncclAllGather of descriptor blocks).  pool: [F x D]."""
+    F = int(pool.shape[0])
+    bounds = shard_bounds(F, world)
+    q0, q1 = bounds[rank]
+    upload_row_block(pool, host_mats, q0, q1, torch)
+    if world == 1:
+        return pool
+    sizes = {b - a for a, b in bounds}
+    if len(sizes) == 1 and q1 > q0:  # equal blocks: one in-place all-gather
+        dist.all_gather_into_tensor(pool.reshape(-1), pool[q0:q1].reshape(-1), group=group)
+    else:
+        for r, (a, b) in enumerate(bounds):
+            if b > a:
+                dist.broadcast(pool[a:b], src=r, group=group)
+    return pool
+
+
 class CudaView:
     """Exposes a raw device pointer to torch via __cuda_array_interface__ (zero-copy, for collectives)."""
 

@@ -193,7 +193,7 @@ def run_ours(args, rank, world, local_rank):
     rec = desc_dev = None
     if world > 1:
         rec = torch.as_tensor(mg.CudaView(plan.records_device(), (2 * F,), "<i4"), device="cuda")
-        desc_dev = torch.as_tensor(mg.CudaView(plan.desc_device(), (F * D,), "<f4"), device="cuda")
+        desc_dev = torch.as_tensor(mg.CudaView(plan.desc_device(), (F, D), "<f4"), device="cuda")
 
     def step_device():
         mg.global_matching_step(plan, RATIO, rank, world, dist, rec)
@@ -238,9 +238,9 @@ def run_ours(args, rank, world, local_rank):
     def step_e2e():
         if world == 1:
             return pkg.featureMatchingGlobal({"k": KNN, "Ratiothreshold": RATIO}, host_views, n_img, ctx=ctx)
-        if rank == 0:
-            plan.upload_pointers(host_ptrs)
-        dist.broadcast(desc_dev, src=0)               # descriptors broadcast over NVLink
+        # every rank uploads its own block of rows from pinned memory (all PCIe links in parallel), the blocks
+        # are all-gathered over NVLink into the plan's pooled matrix
+        mg.gather_descriptors(desc_dev, host_views, rank, world, dist, torch)
         step_device()
         return plan.download() if rank == 0 else None
 
@@ -280,7 +280,8 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": wl, "F": F, "k": KNN, "ratio": RATIO, "pairs_per_step": pairs_total,
                        "arithmetic": "bf16 tcgen05 operands, f32 accumulate, exact f32 re-rank of the candidates",
                        "l2": "512 MB buffer written between timed steps (L2 flush)",
-                       "sharding": f"query rows in {world} contiguous blocks; records exchanged by NCCL broadcast",
+                       "sharding": f"query rows in {world} contiguous blocks; records exchanged by NCCL broadcast"
+                                   + ("; e2e: every rank uploads its row block, NCCL all-gather of the blocks" if world > 1 else ""),
                        "engine": stats["engine"], "fallback_rows_last_step": stats["fallback_rows"],
                        "match_rows": m_rows},
             "roofline": {"bound": "tensor", "kernel": "k_knn_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -48,3 +48,33 @@ def test_exchange_records_gloo_world2(tmp_path, F):
     exp = np.concatenate([np.arange(F) % 5, np.arange(F) + 1]).astype(np.int32)
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"rec{r}.npy"), exp)
+
+
+def _gather_worker(rank, world, port, counts, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    mg = ge.load_package().multigpu
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    mats = [rng.standard_normal((c, 8)).astype(np.float32) for c in counts]  # same data on every rank
+    pool = torch.full((sum(counts), 8), float("nan"))
+    mg.gather_descriptors(pool, mats, rank, world, dist, torch)
+    np.save(os.path.join(out_dir, f"pool{rank}.npy"), pool.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [[256, 256, 256, 256], [100, 0, 333, 77, 1]])
+def test_gather_descriptors_gloo_world2(tmp_path, counts):
+    """Each rank uploads its row block, blocks are all-gathered (equal blocks) or broadcast per owner (ragged)."""
+    import torch.multiprocessing as mp
+
+    port = 31500 + (os.getpid() + sum(counts)) % 2000
+    mp.spawn(_gather_worker, args=(2, port, counts, str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.default_rng(5)
+    exp = np.vstack([rng.standard_normal((c, 8)).astype(np.float32) for c in counts])
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"pool{r}.npy"), exp)
