@@ -307,6 +307,8 @@ __global__ void __launch_bounds__(128) k_ransac_models(const int64_t* __restrict
   if (n < 4) return;
   uint32_t s[4];
   for (int i = 0; i < 4; ++i) s[i] = samples[slot * 4 + i];
+  for (int i = 0; i < 4; ++i)
+    if ((int64_t)s[i] >= n) return;  // caller-supplied table with an index outside the pair: a skipped sample
   double H[9];
   homography4(p1 + o, p2 + o, s, H);
   if (!check_model(H)) return;

@@ -297,6 +297,10 @@ int orc_ransac_homography(const double* p1, const double* p2, int64_t n, double 
     const uint32_t* s = samples + 4 * d;
     ++d;
     double H[9];
+    if (s[0] >= n || s[1] >= n || s[2] >= n || s[3] >= n) { /* table entry outside the pair: a skipped sample */
+      ++skip;
+      continue;
+    }
     estimate_homography(p1, p2, s, 4, H);
     if (!check_model(H)) {
       ++skip;

@@ -68,6 +68,16 @@ def test_degenerate_and_invalid_samples(aps, orc):
     assert not g["accepted"].any() and not g["inliers"].any()
 
 
+def test_sample_indices_outside_the_pair_are_skipped(aps, orc):
+    ptr, p1, p2, smp = _batch(31, [50, 120], [0.8, 0.6], n_draws=300)
+    smp[0, ::3, 2] = 50          # == n: outside
+    smp[1, 1::2, 0] = 4_000_000
+    o = orc.image_matching_batch(ptr, p1, p2, 5.5, 99.9, 150, smp)
+    g = aps.imageMatchingBatch(ptr, p1, p2, {"maxDistance": 5.5, "inliersConfidence": 99.9, "maxIter": 150}, samples=smp)
+    _compare(g, o, ptr)
+    assert g["accepted"].all()
+
+
 def test_device_sample_table(aps, orc):
     ptr = np.array([0, 4, 9, 9, 1000, 1003], np.int64)
     t = aps.ransacSampleTable(ptr, 300, seed=42)
