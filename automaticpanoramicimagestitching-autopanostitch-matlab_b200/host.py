@@ -73,16 +73,18 @@ def _cells_from_matchlist(h, n, want_metric=False):
             else np.zeros((0, 2), np.uint32))
     mp = L.aps_matchlist_metric(h)
     metric = np.ctypeslib.as_array(mp, shape=(total,)).copy() if (want_metric and total and mp) else None
-    matches = [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]  # cell(numImg): every entry []
+    nothing = np.zeros((0, 0))
+    matches = [[nothing] * n for _ in range(n)]  # cell(numImg): every entry []
     metrics = [[None] * n for _ in range(n)]
-    for j in range(n):
-        for i in range(j):
-            c = i + j * n
-            a, b = int(pp[c]), int(pp[c + 1])
-            if b > a:
-                matches[i][j] = rows[a:b].astype(np.float64)  # double, [M x 2] (featureMatchingGlobal.m:155-159)
-                if metric is not None:
-                    metrics[i][j] = metric[a:b]
+    # double, [M x 2] (featureMatchingGlobal.m:155-159): one conversion, then views per cell
+    rows_f = rows.astype(np.float64)
+    filled = np.flatnonzero(np.diff(pp) > 0)
+    for c in filled.tolist():
+        i, j = c % n, c // n
+        if i < j:
+            matches[i][j] = rows_f[pp[c]:pp[c + 1]]
+            if metric is not None:
+                metrics[i][j] = metric[pp[c]:pp[c + 1]]
     return matches, metrics, pp, rows
 
 
@@ -200,10 +202,12 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
     finally:
         lib().aps_matchlist_free(h)
     # featureMatchingPairwise fills EVERY upper-triangle cell (possibly 0 x 2), :62
+    empty = np.zeros((0, 2))
     for j in range(n):
-        for i in range(j):
-            if matches[i][j].size == 0:
-                matches[i][j] = np.zeros((0, 2))
+        col = [matches[i][j] for i in range(j)]
+        for i, m in enumerate(col):
+            if m.size == 0:
+                matches[i][j] = empty
     return (matches, metrics) if return_metric else matches
 
 
