@@ -1201,6 +1201,7 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   APS_CUDA(cudaMemcpyAsync(d_toff.p, toff.data(), np * 4, cudaMemcpyHostToDevice, s));
   APS_CUDA(cudaMemcpyAsync(d_tcnt.p, tcnt.data(), np * 4, cudaMemcpyHostToDevice, s));
   aps_pair_tables pt;
+  memset(&pt, 0, sizeof pt);
   pt.eoff = d_eoff.p; pt.qoff = d_qoff.p; pt.toff = d_toff.p; pt.tcnt = d_tcnt.p; pt.boff = d_boff.p; pt.npairs = np;
 
   if (dtype == APS_U8) {
@@ -1232,8 +1233,9 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       DevBuf<uint32_t> cidx;
       DevBuf<float> cscore;
       APS_TRY(d_units.alloc(units.size(), s));
-      APS_TRY(cidx.alloc((size_t)E * 8, s));
-      APS_TRY(cscore.alloc((size_t)E * 8, s));
+      constexpr int KCP = 4;  // candidates per (query, train image): k = 2 needs the two best and one witness
+      APS_TRY(cidx.alloc((size_t)E * KCP, s));
+      APS_TRY(cscore.alloc((size_t)E * KCP, s));
       APS_TRY(fb.alloc((size_t)E + 1, s));
       APS_CUDA(cudaMemsetAsync(fb.p + E, 0, sizeof(int32_t), s));
       APS_CUDA(cudaMemcpyAsync(d_units.p, units.data(), units.size() * sizeof(aps_tc_unit), cudaMemcpyHostToDevice, s));
@@ -1242,11 +1244,15 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       tp.Qb = side.xb; tp.Tb = side.xb_t; tp.colscale = side.colscale_t; tp.colbias = side.colbias_t;
       tp.tile_bounds = side.tile_bounds; tp.bias = bias_mode;
       tp.Fq_total = side.N; tp.Ft_total = side.N; tp.Dp = (D + 63) / 64 * 64;
-      tp.q0 = 0; tp.q1 = 0; tp.t0 = 0; tp.t1 = 0; tp.nslot = 1; tp.kcand = 8;
+      tp.q0 = 0; tp.q1 = 0; tp.t0 = 0; tp.t1 = 0; tp.nslot = 1; tp.kcand = KCP;
       tp.cand_idx = cidx.p; tp.cand_score = cscore.p; tp.dump = nullptr;
       APS_TRY(aps_k_knn_tc_units(s, c->sm_count, tp, d_units.p, (int64_t)units.size()));
-      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, /*metric*/ 1, 0, E, 0, 1, 8, cidx.p,
-                           cscore.p, S.flags.p, bias_mode, S.flags.p, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &pt));
+      aps_pair_tables ptr_ = pt;  // re-rank may skip rows the ratio / threshold test provably rejects
+      ptr_.prune = 1;
+      ptr_.prune_r2 = max_ratio * max_ratio;
+      ptr_.prune_mt = match_threshold;
+      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, /*metric*/ 1, 0, E, 0, 1, KCP, cidx.p,
+                           cscore.p, S.flags.p, bias_mode, S.flags.p, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &ptr_));
       APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, 1, pt, fb.p, fb.p + E, E, i2.p, dd.p));
       APS_CUDA(cudaMemcpyAsync(c->h_flags + 33, fb.p + E, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     } else {

@@ -170,6 +170,11 @@ struct aps_pair_tables {
   const int32_t* tcnt;   // [npairs] rows of the train image
   const int64_t* boff;   // [npairs + 1] offsets into per-train-row scratch (sum of tcnt)
   int npairs;
+  // K3 shortcut for the batched pairwise path: a query whose APPROXIMATE best / second-best distances already
+  // prove that matchFeaturesScratch.m:174-178 rejects it (d1 > r2*d2 or d1 > MatchThreshold, with the eps
+  // margin on both sides) is written as "no neighbour" without recomputing exact distances.
+  int prune;
+  double prune_r2, prune_mt;
 };
 
 // K3 aps_rerank.cu : exact FP32 re-rank of the candidates + completeness proof.

@@ -288,7 +288,8 @@ __device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
   return x;
 }
 
-template <bool BIAS, bool DUMP, bool PRE>
+// KCT = candidates kept per list: 8, or 4 for the per-pair searches (k = 2: fewer insertions on short sweeps)
+template <bool BIAS, bool DUMP, bool PRE, int KCT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const KParams Pin) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -411,14 +412,14 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       if (x.skip) continue;  // balanced tail: this CTA's share has no second piece
       const int64_t qrow = x.qrow0 + grp * TM + row_in_tile;
       // row-private top-KC (unsorted; aps_rerank.cu orders exactly): scores in registers, train rows in smem
-      float bv[KC];
+      float bv[KCT];
 #pragma unroll
-      for (int i = 0; i < KC; ++i) {
+      for (int i = 0; i < KCT; ++i) {
         bv[i] = __uint_as_float(0xff7ffff8u | (uint32_t)i);  // ~ -FLT_MAX with the slot number in the low bits
         sts_u32(si + i * SLOT_STRIDE, 0xffffffffu);
       }
-      float theta = bv[KC - 1];     // min of bv == the row's K'-th best score so far (empty slots: -FLT_MAX)
-      int minpos = KC - 1;          // slot holding it
+      float theta = bv[KCT - 1];    // min of bv == the row's K'-th best score so far (empty slots: -FLT_MAX)
+      int minpos = KCT - 1;         // slot holding it
       float4 tb_next = (PRE && x.tl < x.th) ? __ldg(P.tile_bounds + x.tl) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int64_t t = x.tl; t < x.th; ++t, ++tcount) {
         const uint32_t slot = (tcount & 1) * RB + grp, acph = (tcount >> 1) & 1;
@@ -519,10 +520,14 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                     // new minimum AND its slot (the 7-ulp truncation is covered by the re-rank's eps)
                     const float key = __uint_as_float((__float_as_uint(gm[g]) & ~7u) | (uint32_t)minpos);
 #pragma unroll
-                    for (int i = 0; i < KC; ++i) bv[i] = (i == minpos) ? key : bv[i];
-                    float m01 = fminf(fminf(bv[0], bv[1]), bv[2]);
-                    float m23 = fminf(fminf(bv[3], bv[4]), bv[5]);
-                    theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
+                    for (int i = 0; i < KCT; ++i) bv[i] = (i == minpos) ? key : bv[i];
+                    if constexpr (KCT == 8) {
+                      float m01 = fminf(fminf(bv[0], bv[1]), bv[2]);
+                      float m23 = fminf(fminf(bv[3], bv[4]), bv[5]);
+                      theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
+                    } else {
+                      theta = fminf(fminf(bv[0], bv[1]), fminf(bv[2], bv[3]));
+                    }
                     minpos = (int)(__float_as_uint(theta) & 7u);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) cur[8 * g + j] = (j == js) ? -CUDART_INF_F : cur[8 * g + j];
@@ -546,17 +551,17 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         }
       }
       if (qrow < x.qend) {
-        const int64_t o = ((x.out_row + grp * TM + row_in_tile) * P.nslot + x.seg * CSPLIT + ch) * KC;
+        const int64_t o = ((x.out_row + grp * TM + row_in_tile) * P.nslot + x.seg * CSPLIT + ch) * KCT;
 #pragma unroll
-        for (int i = 0; i < KC; ++i) {
+        for (int i = 0; i < KCT; ++i) {
           P.cand_idx[o + i] = lds_u32(si + i * SLOT_STRIDE);
           P.cand_score[o + i] = bv[i];
         }
         if (ch == 0)  // e.g. rows of full-width units use the first CSPLIT lists: mark the others empty
           for (int sl = x.clear_from - x.seg * CSPLIT; sl < P.nslot - x.seg * CSPLIT; ++sl)
-            for (int i = 0; i < KC; ++i) {
-              P.cand_idx[o + sl * KC + i] = 0xffffffffu;
-              P.cand_score[o + sl * KC + i] = -CUDART_INF_F;
+            for (int i = 0; i < KCT; ++i) {
+              P.cand_idx[o + sl * KCT + i] = 0xffffffffu;
+              P.cand_score[o + sl * KCT + i] = -CUDART_INF_F;
             }
       }
     }
@@ -747,11 +752,11 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   const int64_t sweep = (sc.tile_hi - sc.tile_lo) / ((sc.units_full && !p.nrows_dev) ? 1 : (sc.tail_seg > 0 ? sc.tail_seg : 1));
   const bool pre = sweep >= 96 && p.tile_bounds != nullptr;
   if (p.dump)
-    APS_TRY(p.bias ? launch(k_knn_tc<true, true, false>) : launch(k_knn_tc<false, true, false>));
+    APS_TRY(p.bias ? launch(k_knn_tc<true, true, false, KC>) : launch(k_knn_tc<false, true, false, KC>));
   else if (pre)
-    APS_TRY(p.bias ? launch(k_knn_tc<true, false, true>) : launch(k_knn_tc<false, false, true>));
+    APS_TRY(p.bias ? launch(k_knn_tc<true, false, true, KC>) : launch(k_knn_tc<false, false, true, KC>));
   else
-    APS_TRY(p.bias ? launch(k_knn_tc<true, false, false>) : launch(k_knn_tc<false, false, false>));
+    APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, KC>) : launch(k_knn_tc<false, false, false, KC>));
   APS_LAUNCHED();
   if (ev1) APS_CUDA(cudaEventRecord(ev1, s));
   return APS_OK;
@@ -810,7 +815,14 @@ int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, co
     kern<<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
     return APS_OK;
   };
-  APS_TRY(p.bias ? launch(k_knn_tc<true, false, false>) : launch(k_knn_tc<false, false, false>));
+  if (p.kcand == 4)
+    APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, 4>) : launch(k_knn_tc<false, false, false, 4>));
+  else if (p.kcand == KC)
+    APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, KC>) : launch(k_knn_tc<false, false, false, KC>));
+  else {
+    aps_set_error(APS_ERR_ARGS, "", "kcand must be 4 or %d", KC);
+    return APS_ERR_ARGS;
+  }
   APS_LAUNCHED();
   return APS_OK;
 }

@@ -87,7 +87,24 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
     float o = __shfl_sync(0xffffffffu, ub, l, G);
     below += (o < lb);
   }
-  const bool need = valid && below < k;
+  // batched pairwise shortcut: rejection of the row by the ratio / threshold test proven from the approximate
+  // distances alone: exact d1 >= m1 - eps (rows outside the list have s~ >= W >= m1) and exact d2 <= m2 + eps
+  bool rej = false;
+  if (pt.prune) {
+    float m1 = sapx;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) m1 = fminf(m1, __shfl_xor_sync(0xffffffffu, m1, o, G));
+    const unsigned eq = __ballot_sync(0xffffffffu, sapx == m1) & segmask;
+    float m2 = (eq != 0u && lane == __ffs(eq) - 1) ? CUDART_INF_F : sapx;  // drop ONE instance of the minimum
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xffffffffu, m2, o, G));
+    if (m2 < CUDART_INF_F) {  // at least two candidates
+      const double lb1 = (double)m1 - (double)eps, ub2 = (double)m2 + (double)eps;
+      const double slack = 1e-6 * (fabs(lb1) + 1.0);
+      rej = (lb1 > pt.prune_r2 * ub2 + slack) || (lb1 > pt.prune_mt + slack);
+    }
+  }
+  const bool need = valid && below < k && !rej;
   float d = CUDART_INF_F;
   if (need) {
     const float* a = Q + q * D;
@@ -125,6 +142,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
     proven = (W - eps > dk);
   else
     proven = (W == CUDART_INF_F);  // every train row was a candidate
+  if (rej) proven = true;  // nothing to prove: the row is reported as having no neighbour
   if (nan_seen) proven = false;
   if (row_ok && !proven && sl == 0) {
     int pos = atomicAdd(fb_count, 1);
