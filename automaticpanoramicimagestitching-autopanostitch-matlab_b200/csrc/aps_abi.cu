@@ -275,6 +275,7 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   p.cand_idx = cidx.p;
   p.cand_score = cscore.p;
   p.dump = nullptr;
+  p.exact_flag = flags_dev;  // exact bf16 operands (integer SIFT): 6 candidates per list are enough to prove a top-5
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (c->timing) {
     APS_CUDA(cudaEventCreate(&ev0));

@@ -149,6 +149,9 @@ struct aps_tc_problem {
   float* cand_score;    // same shape: score (dot*scale+bias), -inf for empty slots
   float* dump;          // optional [ (q1-q0) x (t1-t0) ] raw scores (tests only), else nullptr
   const int32_t* nrows_dev = nullptr;  // second pass: Qb holds *nrows_dev gathered rows (q0 = 0, q1 = upper bound)
+  const int32_t* exact_flag = nullptr; // device flag "operands are exact in bf16" (K1): when given, the first pass keeps 6
+                                       // candidates per list instead of 8 for exact operands (lists stay 8 wide, two
+                                       // entries empty): eps is ~1e-4 then, and 6 still prove a top-5
 };
 int aps_k_knn_tc_supported(int Dp);
 int aps_k_knn_tc_tile_rows();  // rows per train tile (for aps_k_tile_bounds)

@@ -234,6 +234,9 @@ struct KParams {
   float* dump;
   const aps_tc_unit* unit_table;  // batched (pairwise) mode: explicit units, one list per row; else nullptr
   int64_t n_table_units;
+  int cand_stride;                // entries per list in cand_idx / cand_score (>= KCT; the rest is written empty)
+  const int32_t* variant_flag;    // when set: this launch runs only if (*variant_flag != 0) == variant_want
+  int variant_want;
   const int32_t* nrows_dev;       // second-pass mode: the query matrix holds *nrows_dev gathered rows (device-side
                                   // count); every unit is split into tail_seg column segments
 };
@@ -292,6 +295,8 @@ __device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
 template <bool BIAS, bool DUMP, bool PRE, int KCT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const KParams Pin) {
+  // two launches cover one search when the list size depends on a device-side flag: the other one exits here
+  if (Pin.variant_flag && ((*Pin.variant_flag != 0) != (Pin.variant_want != 0))) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16-byte aligned: align by hand
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -525,6 +530,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                       float m01 = fminf(fminf(bv[0], bv[1]), bv[2]);
                       float m23 = fminf(fminf(bv[3], bv[4]), bv[5]);
                       theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
+                    } else if constexpr (KCT == 6) {
+                      theta = fminf(fminf(fminf(bv[0], bv[1]), bv[2]), fminf(fminf(bv[3], bv[4]), bv[5]));
                     } else {
                       theta = fminf(fminf(bv[0], bv[1]), fminf(bv[2], bv[3]));
                     }
@@ -551,17 +558,22 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         }
       }
       if (qrow < x.qend) {
-        const int64_t o = ((x.out_row + grp * TM + row_in_tile) * P.nslot + x.seg * CSPLIT + ch) * KCT;
+        const int cstr = P.cand_stride;
+        const int64_t o = ((x.out_row + grp * TM + row_in_tile) * P.nslot + x.seg * CSPLIT + ch) * cstr;
 #pragma unroll
         for (int i = 0; i < KCT; ++i) {
           P.cand_idx[o + i] = lds_u32(si + i * SLOT_STRIDE);
           P.cand_score[o + i] = bv[i];
         }
+        for (int i = KCT; i < cstr; ++i) {
+          P.cand_idx[o + i] = 0xffffffffu;
+          P.cand_score[o + i] = -CUDART_INF_F;
+        }
         if (ch == 0)  // e.g. rows of full-width units use the first CSPLIT lists: mark the others empty
           for (int sl = x.clear_from - x.seg * CSPLIT; sl < P.nslot - x.seg * CSPLIT; ++sl)
-            for (int i = 0; i < KCT; ++i) {
-              P.cand_idx[o + sl * KCT + i] = 0xffffffffu;
-              P.cand_score[o + sl * KCT + i] = -CUDART_INF_F;
+            for (int i = 0; i < cstr; ++i) {
+              P.cand_idx[o + sl * cstr + i] = 0xffffffffu;
+              P.cand_score[o + sl * cstr + i] = -CUDART_INF_F;
             }
       }
     }
@@ -729,6 +741,9 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.dump = p.dump;
   P.unit_table = nullptr;
   P.n_table_units = 0;
+  P.cand_stride = KC;
+  P.variant_flag = nullptr;
+  P.variant_want = 0;
   P.nrows_dev = p.nrows_dev;
   if (p.nrows_dev) {  // second pass: every unit in MAX_SEG column segments (more candidate lists per row)
     P.units_full = 0;
@@ -753,7 +768,21 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   const bool pre = sweep >= 96 && p.tile_bounds != nullptr;
   if (p.dump)
     APS_TRY(p.bias ? launch(k_knn_tc<true, true, false, KC>) : launch(k_knn_tc<false, true, false, KC>));
-  else if (pre)
+  else if (p.exact_flag && !p.nrows_dev) {
+    // list size chosen by a device-side flag, no host round trip: both variants are launched, one exits at once
+    P.variant_flag = p.exact_flag;
+    P.variant_want = 1;
+    if (pre)
+      APS_TRY(p.bias ? launch(k_knn_tc<true, false, true, 6>) : launch(k_knn_tc<false, false, true, 6>));
+    else
+      APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, 6>) : launch(k_knn_tc<false, false, false, 6>));
+    APS_LAUNCHED();
+    P.variant_want = 0;
+    if (pre)
+      APS_TRY(p.bias ? launch(k_knn_tc<true, false, true, KC>) : launch(k_knn_tc<false, false, true, KC>));
+    else
+      APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, KC>) : launch(k_knn_tc<false, false, false, KC>));
+  } else if (pre)
     APS_TRY(p.bias ? launch(k_knn_tc<true, false, true, KC>) : launch(k_knn_tc<false, false, true, KC>));
   else
     APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, KC>) : launch(k_knn_tc<false, false, false, KC>));
@@ -807,6 +836,7 @@ int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, co
   P.dump = nullptr;
   P.unit_table = d_units;
   P.n_table_units = n_units;
+  P.cand_stride = p.kcand;
   const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
                       (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * CSPLIT * KC * TM * 4 + sizeof(Barriers);
   const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
