@@ -6,8 +6,9 @@
 // evaluated as a dense bf16 contraction: tcgen05.mma (cta_group::1, M=128, N=128, K=16 per
 // instruction) with the accumulator in TMEM, operands staged in shared memory by TMA
 // (SWIZZLE_128B, K-major), and a fused top-K' selection in the epilogue: the distance matrix is
-// never written.  The K' = 8 best train rows per (query row, column segment) go to aps_rerank.cu,
-// which recomputes them exactly in FP32 and proves the top-k complete.
+// never written.  The K' best train rows per (query row, column segment) go to aps_rerank.cu, which
+// recomputes them exactly in FP32 and proves the top-k complete.  K' = 8; 6 when the operands are exact in
+// bf16 (device flag, both variants launched, one exits at once); 4 in the per-pair searches (k = 2).
 //
 // CTA = 352 threads, persistent over work units.  A unit = TWO 128-row query blocks (256 rows, both A
 // tiles resident in shared memory) x a range of 128-column train tiles; every B tile feeds two MMA
@@ -30,15 +31,17 @@
 // TMEM: 4 accumulator slots of 128 columns = slot(tile parity, row block): the tensor pipe fills the
 // slots of tile t+1 while both groups drain tile t.  Pipelines (all mbarrier based): B ring (4 x 32 KB),
 // A pair (single buffered per unit), accumulator slots, (scale,bias) ring.
-// Scheduling: units that fill whole rounds of the grid span all train tiles; the units of the last,
-// partial round are split into up to 4 column segments so that the tail is balanced.
+// Scheduling: units that fill whole rounds of the grid span all train tiles; the last, partial round is
+// balanced either by cutting its units into <= 4 equal column segments or by cutting its tile steps into
+// one equal share per CTA (make_schedule), each piece filling its own candidate list of the row.
 //
 // What bounds it (round 1 measurements, C2 = 163840^2 pairs, D = 128, same box, profiles/r1_ncu_history.txt):
 //   * selection skipped (accumulators never read): TMA + MMA alone 3.99 ms = 1723 TFLOP/s -- the floor of
 //     this tiling;
 //   * epilogue that reads every accumulator (tcgen05.ld) and runs 63 ALU instructions per chunk but never
 //     selects: 4.80 ms = 1432 TFLOP/s -- so the TMEM read path is NOT the limiter;
-//   * full kernel: 6.1 ms = 1120-1130 TFLOP/s (83-84 % of the measured sustained bf16 peak).  The epilogue
+//   * full kernel: 6.1 ms = 1120-1130 TFLOP/s (83-84 % of the measured sustained bf16 peak) with 8 candidates per
+//     list, 5.75 ms = 1194 TFLOP/s (89 %) with 6 (operands exact in bf16, e.g. integer SIFT).  The epilogue
 //     is issue/latency bound: two epilogue warps per scheduler at IPC 0.43 ('wait' 31 % of the samples);
 //     2.25e9 epilogue warp instructions per launch = per tile 73 + 2 x 63 on the fast path, and 0.95e9
 //     in the candidate path, which 19 % of the chunks enter (K'(1 + ln(F/K')) ~ 87 insertions per row are
