@@ -286,9 +286,17 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
     c->tc_events.push_back(ev0);
     c->tc_events.push_back(ev1);
   }
-  APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nslot, kcand, cidx.p,
-                       cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq, nullptr,
-                       nullptr, nullptr, T.perm));
+  // rows of full-width units keep all their candidates in list 0: 8 lanes per row instead of 32
+  const int64_t rows_full = nslot > 1 ? aps_k_knn_tc_full_rows(c->sm_count, nq, t0, t1) : 0;
+  if (rows_full > 0)
+    APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, rows_full, t0, 1, kcand, cidx.p,
+                         cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq, nullptr,
+                         nullptr, nullptr, T.perm, nslot * kcand));
+  if (nq > rows_full)
+    APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0 + rows_full, nq - rows_full, t0, nslot,
+                         kcand, cidx.p + (size_t)rows_full * nslot * kcand, cscore.p + (size_t)rows_full * nslot * kcand,
+                         flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq, nullptr, nullptr,
+                         nullptr, T.perm));
   // Rows that could not be proven complete (device-side list, no host round trip) get a SECOND tensor pass with
   // 4 column segments = 32 candidates per row: with inexact (non bf16-representable) operands the error bound
   // is ~0.016 in squared distance and 8 candidates often do not reach beyond it; 32 usually do.

@@ -158,6 +158,7 @@ int aps_k_knn_tc_tile_rows();  // rows per train tile (for aps_k_tile_bounds)
 int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, const aps_tc_unit* d_units,
                        int64_t n_units);
 int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1, int all_segmented = 0);  // lists per row
+int64_t aps_k_knn_tc_full_rows(int sm_count, int64_t nq, int64_t t0, int64_t t1);  // leading query rows that only fill list 0
 int aps_k_gather_rows(cudaStream_t s, const __nv_bfloat16* src, int Dp, const int32_t* rows, const int32_t* nrows_dev,
                       int64_t max_rows, __nv_bfloat16* dst);
 // ev0/ev1 (optional): recorded immediately before / after the candidate kernel itself
@@ -189,7 +190,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
                  int32_t* fb_count, const aps_pair_tables* pairs = nullptr, const int32_t* row_map = nullptr,
-                 const int32_t* nrows_dev = nullptr, const int32_t* perm = nullptr);
+                 const int32_t* nrows_dev = nullptr, const int32_t* perm = nullptr, int cand_stride = 0);
 
 // K5 aps_filter.cu
 int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, int k, int64_t q0, int64_t q1,

@@ -702,6 +702,12 @@ static TcSchedule make_schedule(int sm_count, int64_t nq, int64_t t0, int64_t t1
   sc.tiles_per_seg = (int)aps_ceil_div(tiles, sc.tail_seg);
   return sc;
 }
+// rows [0, full_rows) of the query range belong to full-width units: their candidates are all in list 0
+int64_t aps_k_knn_tc_full_rows(int sm_count, int64_t nq, int64_t t0, int64_t t1) {
+  const TcSchedule sc = make_schedule(sm_count, nq, t0, t1, false);
+  const int64_t rows = (int64_t)sc.units_full * RB * TM;
+  return rows < nq ? rows : nq;
+}
 int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1, int all_segmented) {
   return make_schedule(sm_count, nq, t0, t1, all_segmented != 0).nslot;
 }

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
                                                 int32_t* __restrict__ fb_count, aps_pair_tables pt,
                                                 const int32_t* __restrict__ row_map,
                                                 const int32_t* __restrict__ nrows_dev,
-                                                const int32_t* __restrict__ perm) {
+                                                const int32_t* __restrict__ perm, int cand_stride) {
   constexpr int RPW = 32 / G;  // rows per warp
   if (nrows_dev && (int64_t)blockIdx.x * (blockDim.x >> 5) * RPW >= (int64_t)(*nrows_dev)) return;  // second pass: short list
   const int lane = threadIdx.x & 31, sub = lane / G, sl = lane % G;
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   uint32_t ci = 0xffffffffu;
   float sc = -CUDART_INF_F;
   if (row_ok && sl < ncand) {
-    ci = cand_idx[r * ncand + sl];
-    sc = cand_score[r * ncand + sl];
+    ci = cand_idx[r * cand_stride + sl];  // cand_stride > ncand: only the row's first nseg lists are read
+    sc = cand_score[r * cand_stride + sl];
     if (perm && ci != 0xffffffffu) ci = (uint32_t)perm[ci];  // position in the sorted train view -> original row
   }
   const bool valid = ci != 0xffffffffu;
@@ -157,7 +157,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
                  int32_t* fb_count, const aps_pair_tables* pairs, const int32_t* row_map, const int32_t* nrows_dev,
-                 const int32_t* perm) {
+                 const int32_t* perm, int cand_stride) {
   (void)exact_flag;
   if (nq == 0) return APS_OK;
   if (nseg * kcand > 32) {
@@ -168,6 +168,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
   memset(&pt, 0, sizeof pt);
   if (pairs) pt = *pairs;
   const int ncand = nseg * kcand;
+  if (cand_stride <= 0) cand_stride = ncand;
   if (k > 8 || k > ncand) {
     aps_set_error(APS_ERR_ARGS, "", "rerank: k must be <= min(8, candidates)");
     return APS_ERR_ARGS;
@@ -176,7 +177,8 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
   k_rerank<G><<<(unsigned)aps_ceil_div(nq, 8 * (32 / G)), 256, 0, s>>>(Q, sqQ, invnQ, T, sqT, D, metric, q0, nq, t0, \
                                                                        nseg, kcand, cand_idx, cand_score, flags,     \
                                                                        bias_mode, k, out_row0, idx, dist, fb_rows,  \
-                                                                       fb_count, pt, row_map, nrows_dev, perm)
+                                                                       fb_count, pt, row_map, nrows_dev, perm,       \
+                                                                       cand_stride)
   if (ncand <= 8) APS_RERANK(8);
   else if (ncand <= 16) APS_RERANK(16);
   else APS_RERANK(32);
