@@ -1,5 +1,6 @@
-"""Times the RANSAC consumer (aps_image_matching_batch) on one GPU next to the oracle on the host cores.
-usage: time_ransac.py [n_images] [kp] [--no-cpu]   (C2-like default: 20 images x 8192 keypoints on a ring)"""
+"""Times the RANSAC consumer (aps_image_matching) on one GPU.  The CPU oracle is timed beside it, on the same input,
+by tests/test_gpu_ransac.py::test_c2_like_scale_and_timing (only tests may load oracle/).
+usage: time_ransac.py [n_images] [kp]   (C2-like default: 20 images x 8192 keypoints on a ring)"""
 import os
 import sys
 import time
@@ -27,16 +28,3 @@ for it in range(3):
     print(f"it{it}: {P} candidate pairs, {total} correspondences, 1000 draws/pair evaluated: {dt*1e3:.2f} ms end to end "
           f"({evals/dt:.3e} trial-correspondence evaluations/s), accepted {int(last['accepted'].sum())}, "
           f"draws consumed median {int(np.median(last['draws_used']))}")
-if "--no-cpu" not in sys.argv:
-    from oracle import oracle as orc
-    lin, ptr = last["pairs_lin"], last["pt_ptr"]
-    P1 = np.vstack([keypoints[c // n][np.asarray(matches[c % n][c // n], np.int64)[:, 1] - 1] for c in lin])
-    P2 = np.vstack([keypoints[c % n][np.asarray(matches[c % n][c // n], np.int64)[:, 0] - 1] for c in lin])
-    tab = pkg.ransacSampleTable(ptr, 1000, seed=1)
-    t0 = time.perf_counter()
-    o = orc.image_matching_batch(ptr, P1, P2, 5.5, 99.9, 500, tab)
-    dt = time.perf_counter() - t0
-    same = np.array_equal(o["inliers"], last["inliers"]) and np.array_equal(o["accepted"], last["accepted"])
-    used = float(np.sum(np.diff(ptr) * o["draws_used"]))
-    print(f"oracle (sequential loop, stops at the adaptive bound; {orc.num_threads()} threads over pairs): {dt*1e3:.1f} ms "
-          f"({used/dt:.3e} evaluations/s on the draws it consumed); identical result: {same}")

@@ -135,6 +135,34 @@ def test_image_matching_end_to_end(aps, orc):
     assert np.count_nonzero(numM) == n_acc
 
 
+def test_c2_like_scale_and_timing(aps, orc, capsys):
+    """C2-like size (20 images x 8192 keypoints, m = 6: 76 candidate pairs, ~58 k correspondences): identical inlier
+    sets at full size, and both sides timed on the same input (GPU end to end incl. copies vs oracle on all host cores)."""
+    import time
+
+    n, kp = 20, 8192
+    keypoints, matches, _ = aps.synth.synth_matched_keypoints(n, kp, seed=77)
+    inp = dict(PARAMS, mBrownLowe=6)
+    aps.imageMatching(inp, n, keypoints, matches, seed=1)  # warm-up (allocations, module load)
+    t0 = time.perf_counter()
+    aps.imageMatching(inp, n, keypoints, matches, seed=1)
+    t_gpu = time.perf_counter() - t0
+    last = aps.imageMatching.last
+    lin, ptr = last["pairs_lin"], last["pt_ptr"]
+    P1 = np.vstack([keypoints[c // n][np.asarray(matches[c % n][c // n], np.int64)[:, 1] - 1] for c in lin])
+    P2 = np.vstack([keypoints[c % n][np.asarray(matches[c % n][c // n], np.int64)[:, 0] - 1] for c in lin])
+    tab = aps.ransacSampleTable(ptr, 1000, seed=1)
+    t0 = time.perf_counter()
+    o = orc.image_matching_batch(ptr, P1, P2, 5.5, 99.9, 500, tab)
+    t_cpu = time.perf_counter() - t0
+    assert np.array_equal(o["inliers"], last["inliers"]) and np.array_equal(o["accepted"], last["accepted"])
+    assert np.array_equal(o["draws_used"], last["draws_used"]) and o["accepted"].sum() >= 2 * n
+    assert np.allclose(last["models"][o["accepted"]], o["models"][o["accepted"]], rtol=1e-9, atol=1e-12)
+    with capsys.disabled():
+        print(f"\n[ransac C2-like] {len(lin)} pairs, {int(ptr[-1])} correspondences: GPU {t_gpu * 1e3:.1f} ms end to end, "
+              f"oracle {t_cpu * 1e3:.1f} ms on {orc.num_threads()} host threads")
+
+
 def test_reference_error_behaviour(aps):
     kps = [np.zeros((5, 2)), np.zeros((5, 2))]
     bad = [[np.zeros((0, 0)), np.array([[1.0, 9.0], [2, 2], [3, 3], [4, 4]])], [np.zeros((0, 0)), np.zeros((0, 0))]]
