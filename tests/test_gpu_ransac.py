@@ -163,6 +163,22 @@ def test_c2_like_scale_and_timing(aps, orc, capsys):
               f"oracle {t_cpu * 1e3:.1f} ms on {orc.num_threads()} host threads")
 
 
+def test_gpu_against_committed_lapack_vectors(aps):
+    """The GPU path against tests/golden/ransac_v1.npz (numpy/LAPACK restatement; no oracle involved)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ransac_v1.npz"))
+    for c in [str(x) for x in g["cases"]]:
+        md, conf, mt = g[f"{c}_params"]
+        inp = {"maxDistance": md, "inliersConfidence": conf, "maxIter": int(mt)}
+        m, inl, found = aps.estimateTransformationRANSAC(g[f"{c}_p1"], g[f"{c}_p2"], "projective", inp,
+                                                         samples=g[f"{c}_samples"])
+        assert found, c
+        assert np.array_equal(inl, g[f"{c}_inliers"]), c
+        gm = g[f"{c}_model"]
+        assert np.allclose(m / m[2, 2], gm / gm[2, 2], rtol=1e-7, atol=1e-9), c
+
+
 def test_reference_error_behaviour(aps):
     kps = [np.zeros((5, 2)), np.zeros((5, 2))]
     bad = [[np.zeros((0, 0)), np.array([[1.0, 9.0], [2, 2], [3, 3], [4, 4]])], [np.zeros((0, 0)), np.zeros((0, 0))]]

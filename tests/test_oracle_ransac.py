@@ -65,3 +65,22 @@ def test_batch_acceptance_rule_and_inverse():
         if r["accepted"][p]:
             assert np.allclose(r["models"][p] @ r["models_inv"][p], np.eye(3), atol=1e-9)
     assert list(r["accepted"]) == [True, False, True, False, False]
+
+
+def _golden_cases():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ransac_v1.npz"))
+    return g, [str(c) for c in g["cases"]]
+
+
+def test_oracle_against_committed_lapack_vectors():
+    """tests/golden/ransac_v1.npz (made by make_golden_ransac.py from the numpy/LAPACK restatement alone)."""
+    g, cases = _golden_cases()
+    for c in cases:
+        md, conf, mt = g[f"{c}_params"]
+        f, m, inl, used = orc.ransac_homography(g[f"{c}_p1"], g[f"{c}_p2"], md, conf, int(mt), g[f"{c}_samples"])
+        assert f and used == int(g[f"{c}_draws"]), c
+        assert np.array_equal(inl, g[f"{c}_inliers"]), c
+        gm = g[f"{c}_model"]
+        assert np.allclose(m / m[2, 2], gm / gm[2, 2], rtol=1e-7, atol=1e-9), c
