@@ -82,12 +82,16 @@ __global__ void k_prepare_norm(const float* __restrict__ raw, int64_t F, int D, 
   __syncthreads();
   int exact = 1;
   float maxabs = 0.f;
-  for (int i = threadIdx.x; i < nr * D; i += blockDim.x) {
-    int r = i / D, c = i - r * D;
+  // (row, column) of element i advance by a fixed step per iteration: no division in the loops
+  const int step_r = (int)blockDim.x / D, step_c = (int)blockDim.x - step_r * D;
+  const int first_r = (int)threadIdx.x / D, first_c = (int)threadIdx.x - first_r * D;
+#define APS_NEXT_RC() { r += step_r; c += step_c; if (c >= D) { c -= D; ++r; } }
+  for (int i = threadIdx.x, r = first_r, c = first_c; i < nr * D; i += blockDim.x) {
     float v = raw[(r0 + r) * D + c];
     tile[r * ld + c] = v;
     exact &= (__bfloat162float(__float2bfloat16_rn(v)) == v);
     maxabs = fmaxf(maxabs, fabsf(v));
+    APS_NEXT_RC()
   }
   if (!exact) atomicAnd(&s_exact, 0);
   atomicMax(&s_maxabs, __float_as_int(maxabs));
@@ -103,9 +107,9 @@ __global__ void k_prepare_norm(const float* __restrict__ raw, int64_t F, int D, 
   }
   __syncthreads();
   if (norm_mode != APS_NORM_NONE) {
-    for (int i = threadIdx.x; i < nr * D; i += blockDim.x) {
-      int r = i / D, c = i - r * D;
+    for (int i = threadIdx.x, r = first_r, c = first_c; i < nr * D; i += blockDim.x) {
       tile[r * ld + c] = __fdiv_rn(tile[r * ld + c], s_norm[r]);
+      APS_NEXT_RC()
     }
     __syncthreads();
   }
@@ -119,10 +123,11 @@ __global__ void k_prepare_norm(const float* __restrict__ raw, int64_t F, int D, 
     atomicMax(&s_maxsq, __float_as_int(sum));
   }
   if (xn != raw || norm_mode != APS_NORM_NONE)
-    for (int i = threadIdx.x; i < nr * D; i += blockDim.x) {
-      int r = i / D, c = i - r * D;
+    for (int i = threadIdx.x, r = first_r, c = first_c; i < nr * D; i += blockDim.x) {
       xn[(r0 + r) * D + c] = tile[r * ld + c];
+      APS_NEXT_RC()
     }
+#undef APS_NEXT_RC
   __syncthreads();
   if (threadIdx.x == 0) {
     if (!s_exact) atomicAnd(&flags[0], 0);
