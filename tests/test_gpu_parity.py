@@ -300,24 +300,30 @@ def test_pairwise_mixed_magnitudes_and_empty_images(aps, orc):
                 assert np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
 
 
-def test_pairwise_tensor_engine_large(aps, orc):
+@pytest.mark.parametrize("cid,n,kp", [(5, 5, 3000), (1, 4, 2500)])
+def test_pairwise_tensor_engine_large(aps, orc, cid, n, kp):
+    """sweeps of >= 16 train tiles per unit: the unit-table launch runs with the raw pre-filter (bias and
+    scale-only scores), image boundaries not aligned to the 128-row tiles."""
     ctx = aps._lib.default_context()
-    desc, c = aps.synth.make_config(5, n=5, kp=3000)
+    desc, c = aps.synth.make_config(cid, n=n, kp=kp)
     ctx.set_float_engine(2)
     try:
-        got = aps.featureMatchingPairwise({"Matchingthreshold": 1.5, "Ratiothreshold": 0.7}, desc, 5)
+        got = aps.featureMatchingPairwise({"Matchingthreshold": 1.5, "Ratiothreshold": 0.7}, desc, n)
         stats = ctx.last_stats()
     finally:
         ctx.set_float_engine(0)
     assert stats["engine"] == "tcgen05"
     ref = orc.feature_matching_pairwise(desc, 1.5, 0.7)
     rows = 0
-    for j in range(5):
+    for j in range(n):
         for i in range(j):
             exp = ref["cells"].get((i, j))
-            assert exp is not None and np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
+            if exp is None:
+                assert got[i][j].shape[0] == 0, (i, j)
+                continue
+            assert np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
             rows += len(exp)
-    assert rows > 3000
+    assert rows > (3000 if cid == 5 else 500)
 
 
 def test_match_features_unpacked_bits_packed_on_device(aps, orc):
