@@ -111,6 +111,30 @@ def cpu_reference_rate(desc, target_seconds, threads_note=True):
     return {"value": nq * F / dt, "seconds": dt, "queries": nq, "F": F, "cores": oracle.num_threads()}
 
 
+def flann_kdtree_rate(X, exact_idx1, q0, nq):
+    """The reference's DEFAULT global float engine (PP/mex/flann_knn.cpp:229-234: cv::flann::Index, KDTree(4),
+    knnSearch(checks=32)) through the OpenCV python module of this image -- approximate and randomised, so it is
+    reported beside the exact arm, never as the parity oracle.  Returns None when cv2 is not importable."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    F = X.shape[0]
+    t0 = time.perf_counter()
+    index = cv2.flann_Index(X, dict(algorithm=1, trees=4))
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    idx, _ = index.knnSearch(X[q0:q0 + nq], KNN, params=dict(checks=32))
+    t_search = time.perf_counter() - t0
+    hits = sum(len(set(idx[r].tolist()) & set((exact_idx1[r] - 1).tolist())) for r in range(nq))
+    total_s = t_build + t_search * F / nq
+    return {"engine": f"cv2 {cv2.__version__} flann_Index KDTree(trees=4), knnSearch(checks=32); reference pins OpenCV 4.12",
+            "value": F * float(F) / total_s, "unit": UNIT + " (F^2 / time: pair-equivalents of an approximate search)",
+            "cores": 1, "build_s": t_build, "search_s_scaled": t_search * F / nq,
+            "recall_at_k_vs_exact": hits / float(nq * KNN),
+            "sample": f"index over all {F} rows, {nq} queries searched, search time scaled linearly"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference path's own CPU arithmetic on this box's host cores.
     MATLAB cannot run here and flann_knn.cpp needs OpenCV C++ (absent), so this is the oracle port
@@ -149,6 +173,9 @@ def run_reference(args, rank, world):
             "config": {"workload": wl, "F": F, "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    approx = flann_kdtree_rate(X, idx, q0, nq)   # idx: the exact neighbours of the last timed sample
+    if approx is not None:
+        line["reference_default_engine"] = approx
     print(json.dumps(line), flush=True)
 
 

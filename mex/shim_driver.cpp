@@ -126,6 +126,59 @@ int main(int argc, char** argv) {
     const mxArray* in[] = {kp, mm, six, md, cf, it};
     bad += expect_error("apsmatch:nogpu", 3, 6, in);  // no CPU fallback
   }
+#elif defined(GATE_MATCHF)
+  mxArray* A = mxCreateNumericMatrix(6, 8, mxSINGLE_CLASS, mxREAL);
+  mxArray* B = mxCreateNumericMatrix(7, 8, mxSINGLE_CLASS, mxREAL);
+  mxArray* B5 = mxCreateNumericMatrix(7, 5, mxSINGLE_CLASS, mxREAL);
+  mxArray* E = mxCreateNumericMatrix(0, 8, mxSINGLE_CLASS, mxREAL);
+  mxArray* U = mxCreateNumericMatrix(4, 32, mxUINT8_CLASS, mxREAL);
+  mxArray* U0 = mxCreateNumericMatrix(0, 32, mxUINT8_CLASS, mxREAL);
+  mxArray *kf = mxCreateDoubleScalar(0), *kb = mxCreateDoubleScalar(1), *k9 = mxCreateDoubleScalar(9);
+  mxArray *thr = mxCreateDoubleScalar(3.5), *ratio = mxCreateDoubleScalar(0.6), *r2 = mxCreateDoubleScalar(1.5);
+  mxArray* uq = mxCreateLogicalMatrix(1, 1);
+  ((unsigned char*)mxGetData(uq))[0] = 1;
+  { const mxArray* in[] = {A, B, kf}; bad += expect_error("apsmatch:args", 2, 3, in); }
+  { const mxArray* in[] = {A, B, k9, thr, ratio, uq}; bad += expect_error("apsmatch:args", 2, 6, in); }
+  { const mxArray* in[] = {A, B, kf, thr, r2, uq}; bad += expect_error("apsmatch:args", 2, 6, in); }     // MaxRatio > 1
+  { const mxArray* in[] = {A, B5, kf, thr, ratio, uq}; bad += expect_error("apsmatch:dim", 2, 6, in); }
+  { const mxArray* in[] = {A, U, kf, thr, ratio, uq}; bad += expect_error("apsmatch:type", 2, 6, in); }
+  { const mxArray* in[] = {A, B, kb, thr, ratio, uq}; bad += expect_error("apsmatch:type", 2, 6, in); }   // float data as bytes
+  { const mxArray* in[] = {E, B, kf, thr, ratio, uq}; bad += expect_error("MATLAB:expectedNonempty", 2, 6, in); }
+  {  // binary early exit (matchFeaturesScratch.m:84-88): zeros(0,2,'uint32'), zeros(0,1,'single'), no GPU touched
+    mxArray* out[2] = {nullptr, nullptr};
+    const mxArray* in[] = {U0, U, kb, thr, ratio, uq};
+    mexFunction(2, out, 6, in);
+    bad += !(mxIsUint32(out[0]) && mxGetM(out[0]) == 0 && mxGetN(out[0]) == 2 && mxIsSingle(out[1]) && mxGetM(out[1]) == 0);
+  }
+  if (gpu) {
+    float *pa = (float*)mxGetData(A), *pb = (float*)mxGetData(B);
+    // rows 0..3 of B are near copies of rows 0..3 of A (unit-scale values: no normalisation), the rest far away
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 8; ++c) pa[r + 6 * c] = (float)(((r * 5 + c * 3) % 11) - 5) * 0.15f;
+    for (int r = 0; r < 7; ++r)
+      for (int c = 0; c < 8; ++c)
+        pb[r + 7 * c] = r < 4 ? pa[r + 6 * c] + 0.001f * (float)(c + 1) : (float)(((r * 7 + c * 5) % 13) - 6) * 0.3f;
+    mxArray* out[2] = {nullptr, nullptr};
+    const mxArray* in[] = {A, B, kf, thr, ratio, uq};
+    mexFunction(2, out, 6, in);
+    bad += !(mxIsUint32(out[0]) && mxGetN(out[0]) == 2 && mxGetM(out[0]) >= 4 && mxIsDouble(out[1]) && mxGetM(out[1]) == mxGetM(out[0]));
+    const uint32_t* m = (const uint32_t*)mxGetData(out[0]);
+    const size_t K = mxGetM(out[0]);
+    for (size_t r = 0; r < K; ++r)
+      if (m[r] <= 4) bad += m[r + K] != m[r];                       // planted copies match their source row
+    for (size_t r = 1; r < K; ++r) bad += mxGetPr(out[1])[r] < mxGetPr(out[1])[r - 1];  // Unique: ascending metric
+    // packed bytes: identical sets match row to row at 0 percent, metric is single
+    unsigned char* u = (unsigned char*)mxGetData(U);
+    for (int i = 0; i < 4 * 32; ++i) u[i] = (unsigned char)((i * 37 + (i % 4) * 101) & 0xff);
+    mxArray* o2[2] = {nullptr, nullptr};
+    mxArray* t10 = mxCreateDoubleScalar(10.0);
+    const mxArray* in2[] = {U, U, kb, t10, ratio, uq};
+    mexFunction(2, o2, 6, in2);
+    bad += !(mxGetM(o2[0]) == 4 && mxIsSingle(o2[1]) && ((const float*)mxGetData(o2[1]))[0] == 0.0f);
+  } else {
+    const mxArray* in[] = {A, B, kf, thr, ratio, uq};
+    bad += expect_error("apsmatch:nogpu", 2, 6, in);  // no CPU fallback
+  }
 #endif
   std::printf(bad ? "FAILED (%d)\n" : "OK\n", bad);
   return bad ? 1 : 0;

@@ -181,6 +181,8 @@ static inline double mxGetScalar(const mxArray* a) {
     default: return 0.0;
   }
 }
+static inline bool mxIsLogicalScalar(const mxArray* a) { return a->cls == mxLOGICAL_CLASS && mxGetNumberOfElements(a) == 1; }
+static inline bool mxIsLogicalScalarTrue(const mxArray* a) { return mxIsLogicalScalar(a) && a->data[0] != 0; }
 static inline mxArray* mxGetCell(const mxArray* a, mwIndex i) { return i < a->cells.size() ? a->cells[i] : nullptr; }
 static inline void mxSetCell(mxArray* a, mwIndex i, mxArray* v) {
   if (i < a->cells.size()) a->cells[i] = v;

@@ -1,5 +1,5 @@
 """The MEX gateways in mex/ (drop-in names flann_knn_win, nearest2HammingExhaustive{,OMP}MEX and the batched
-aps_featureMatching_mex / aps_imageMatching_mex) compiled against the mex shim and driven by mex/shim_driver.cpp.
+aps_featureMatching_mex / aps_imageMatching_mex / aps_matchFeatures_mex) compiled against the mex shim and driven by mex/shim_driver.cpp.
 CPU: argument validation raises the reference's error identifiers and a missing GPU raises
 apsmatch:nogpu (no CPU fallback).  GPU: the same binaries run a small real call."""
 import os
@@ -8,7 +8,7 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GATES = ["gate_flann", "gate_hamming", "gate_hamming_omp", "gate_batched", "gate_imatch"]
+GATES = ["gate_flann", "gate_hamming", "gate_hamming_omp", "gate_batched", "gate_imatch", "gate_matchf"]
 
 
 def _build():
