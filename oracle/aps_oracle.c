@@ -12,14 +12,17 @@
  *                             and against committed golden vectors made from them.
  *   - orc_knn_hamming       : pinned against cv2.BFMatcher(NORM_HAMMING).knnMatch (OpenCV 4.13;
  *                             the reference pins 4.12) golden vectors -- PP/mex/flann_knn.cpp:199-223.
- *   - orc_knn_l2            : exact search with the flann_knn output contract; golden vectors
- *                             from cv2.BFMatcher(NORM_L2SQR) pin the INDICES (distances differ
- *                             in the last ulps: OpenCV's SIMD order is not FLANN's scalar order).
- *                             The reference's float engine itself (FLANN KD-tree, randomised,
- *                             approximate) cannot pin an exact matcher: "parity unpinned" for
- *                             the float distance bits, pinned for indices/contract.
- *   - MATLAB-only steps (filter loop, ratio tests, unique, top-m): no MATLAB here and the
- *     reference ships no tests => restated line by line; "parity unpinned" beyond hand-made KATs.
+ *   - orc_knn_l2            : exact search with the flann_knn output contract; pinned against
+ *                             cv2.flann_Index(LINEAR).knnSearch golden vectors = FLANN's own L2<float>
+ *                             functor and result order: indices AND float32 distance bits identical.
+ *                             The reference's default float engine (FLANN KD-tree, randomised,
+ *                             approximate) cannot pin an exact matcher.
+ *   - MATLAB-only steps (normalisations, filter loop, ratio tests, unique, SSD 2-NN, top-m, packBits): no
+ *     MATLAB / Octave here and the reference ships no tests => "parity unpinned" against MATLAB itself.
+ *     Cross-checked bit for bit against an independent numpy restatement of the same .m lines
+ *     (tests/matlab_restatement.py, tests/test_oracle_matlab_restatement.py: tie-heavy random inputs) and
+ *     against golden vectors minted from that restatement alone (tests/golden/matlab_semantics_v1.npz),
+ *     plus hand-made known-answer tests (tests/test_oracle_semantics.py).
  *
  * Floating-point discipline: compile with -ffp-contract=off (no FMA), every float operation is a
  * single IEEE-754 binary32 operation in the order written, so that the CUDA re-rank kernel

@@ -342,3 +342,38 @@ def test_match_features_unpacked_bits_packed_on_device(aps, orc):
         omet = np.zeros(400)
         K = O.lib().orc_filter_unique(idx2, d1, d2, 400, 500, 1, Dbits, 20.0, 0.8, 1, om.reshape(-1), omet)
         assert K > 100 and np.array_equal(m, om[:K]) and np.array_equal(met, omet[:K]), Dbits
+
+
+def test_golden_semantics_vectors_gpu(aps):
+    """the library against vectors minted from the numpy restatement of the MATLAB-only lines alone
+    (tests/matlab_restatement.py, tests/golden/make_golden_semantics.py): neither the oracle nor the library took
+    part in making them."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matlab_semantics_v1.npz"))
+    m, met = aps.matchFeaturesScratch(g["mf_A"], g["mf_B"], MatchThreshold=float(g["mf_thr"]), MaxRatio=float(g["mf_ratio"]))
+    assert np.array_equal(m, g["mf_matches"]) and np.array_equal(met, g["mf_metric"])
+    m, met = aps.matchFeaturesScratch(aps.binaryFeatures(g["mb_A"]), aps.binaryFeatures(g["mb_B"]),
+                                      MatchThreshold=float(g["mb_thr"]), MaxRatio=float(g["mb_ratio"]))
+    assert np.array_equal(m, g["mb_matches"]) and np.array_equal(met, g["mb_metric"])
+    for tag, binary in (("gl", True), ("gf", False)):
+        counts = g[tag + "_counts"]
+        n = len(counts)
+        desc = np.split(g[tag + "_desc"], np.cumsum(counts)[:-1])
+        cells = [aps.binaryFeatures(d) for d in desc] if binary else desc
+        got = aps.featureMatchingGlobal({"k": int(g[tag + "_k"]), "Ratiothreshold": float(g[tag + "_ratio"]), "BFMatch": 1},
+                                        cells, n)
+        pp, rows = g[tag + "_pair_ptr"], g[tag + "_rows"]
+        total = 0
+        for j in range(n):
+            for i in range(j):
+                c = i + j * n
+                exp = rows[pp[c]:pp[c + 1]]
+                if len(exp) == 0:
+                    assert got[i][j].shape[0] == 0, (tag, i, j)
+                else:
+                    assert np.array_equal(got[i][j], exp.astype(np.float64)), (tag, i, j)
+                    total += len(exp)
+        assert total == len(rows) and total > 30
+    cand, pairs = aps.selectImagePartners(g["sp_counts"], int(g["sp_m"]))
+    assert np.array_equal(cand, g["sp_cand"]) and np.array_equal(pairs, g["sp_lin"])
