@@ -69,6 +69,7 @@ def lib():
         "aps_error_id": (cp, []),
         "aps_abi_version": (i32, []),
         "aps_ctx_set_float_engine": (i32, [vp, i32]),
+        "aps_ctx_set_pairwise_epilogue": (i32, [vp, i32]),
         "aps_ctx_last_stats": (i32, [vp, C.POINTER(i64)]),
         "aps_ctx_enable_timing": (i32, [vp, i32]),
         "aps_ctx_tc_time": (i32, [vp, C.POINTER(dbl), C.POINTER(i64)]),
@@ -144,6 +145,10 @@ class Context:
 
     def set_float_engine(self, engine: int):
         check(lib().aps_ctx_set_float_engine(self._h, int(engine)))
+
+    def set_pairwise_epilogue(self, mode: int):
+        """0 = streaming top-4 (default), 1 = branch-free segment selection (see include/apsmatch.h)."""
+        check(lib().aps_ctx_set_pairwise_epilogue(self._h, int(mode)))
 
     def enable_timing(self, on=True):
         check(lib().aps_ctx_enable_timing(self._h, int(bool(on))))

@@ -127,6 +127,12 @@ extern "C" int aps_ctx_set_float_engine(aps_ctx* c, int engine) {
   c->float_engine = engine;
   return APS_OK;
 }
+extern "C" int aps_ctx_set_pairwise_epilogue(aps_ctx* c, int mode) {
+  if (!c || (mode != 0 && mode != 1))
+    APS_FAIL(APS_ERR_ARGS, "", "pairwise epilogue must be 0 (streaming) or 1 (segment selection)");
+  c->pairwise_epilogue = mode;
+  return APS_OK;
+}
 
 extern "C" int aps_ctx_last_stats(aps_ctx* c, int64_t stats[4]) {
   if (!c || !stats) APS_FAIL(APS_ERR_ARGS, "", "bad args");
@@ -1242,9 +1248,13 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       DevBuf<uint32_t> cidx;
       DevBuf<float> cscore;
       APS_TRY(d_units.alloc(units.size(), s));
-      constexpr int KCP = 4;  // candidates per (query, train image): k = 2 needs the two best and one witness
-      APS_TRY(cidx.alloc((size_t)E * KCP, s));
-      APS_TRY(cscore.alloc((size_t)E * KCP, s));
+      // candidates per (query, train image): k = 2 needs the two best and one witness.  4 = one streaming top-4 list;
+      // 3 = branch-free segment epilogue, two sorted lists of three (aps_knn_tc.cu, k_knn_tc<.., 3, 2>)
+      const int KCP = c->pairwise_epilogue == 1 ? 3 : 4;
+      const int nlist = KCP == 3 ? aps_k_knn_tc_tile_mode_stride() / 3 : 1;
+      const int cstride = nlist * KCP;
+      APS_TRY(cidx.alloc((size_t)E * cstride, s));
+      APS_TRY(cscore.alloc((size_t)E * cstride, s));
       APS_TRY(fb.alloc((size_t)E + 1, s));
       APS_CUDA(cudaMemsetAsync(fb.p + E, 0, sizeof(int32_t), s));
       APS_CUDA(cudaMemcpyAsync(d_units.p, units.data(), units.size() * sizeof(aps_tc_unit), cudaMemcpyHostToDevice, s));
@@ -1260,7 +1270,8 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       ptr_.prune = 1;
       ptr_.prune_r2 = max_ratio * max_ratio;
       ptr_.prune_mt = match_threshold;
-      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, /*metric*/ 1, 0, E, 0, 1, KCP, cidx.p,
+      ptr_.tile_mode = KCP == 3 ? aps_k_knn_tc_tile_mode_segment() : 0;
+      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, /*metric*/ 1, 0, E, 0, nlist, KCP, cidx.p,
                            cscore.p, S.flags.p, bias_mode, S.flags.p, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &ptr_));
       APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, 1, pt, fb.p, fb.p + E, E, i2.p, dd.p));
       APS_CUDA(cudaMemcpyAsync(c->h_flags + 33, fb.p + E, sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -45,6 +45,7 @@ struct aps_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int float_engine = 0;  // 0 auto, 1 exact only, 2 tensor required
+  int pairwise_epilogue = 0;  // 0 streaming top-4, 1 branch-free segment selection (aps_ctx_set_pairwise_epilogue)
   int64_t stats[4] = {0, 0, 0, 0};
   bool timing = false;
   std::vector<cudaEvent_t> tc_events;  // pairs (start, stop) of tcgen05 kernel launches
@@ -155,6 +156,8 @@ struct aps_tc_problem {
 };
 int aps_k_knn_tc_supported(int Dp);
 int aps_k_knn_tc_tile_rows();  // rows per train tile (for aps_k_tile_bounds)
+int aps_k_knn_tc_tile_mode_stride();   // unit-table launch with kcand == 3: candidate entries per row (2 lists x 3)
+int aps_k_knn_tc_tile_mode_segment();  // ... and the columns per segment (two best kept per segment)
 int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, const aps_tc_unit* d_units,
                        int64_t n_units);
 int aps_k_knn_tc_slots(int sm_count, int64_t nq, int64_t t0, int64_t t1, int all_segmented = 0);  // lists per row
@@ -179,6 +182,11 @@ struct aps_pair_tables {
   // margin on both sides) is written as "no neighbour" without recomputing exact distances.
   int prune;
   double prune_r2, prune_mt;
+  // > 0: the candidate lists come from the branch-free segment epilogue (k_knn_tc<.., 3, 2>): each list holds the
+  // three best of "two best per segment of tile_mode columns", sorted by approximate score.  A column outside a list
+  // is then bounded by the list's third entry -- or by its second when the two best share a segment -- and eps
+  // grows by the 7 key bits.
+  int tile_mode;
 };
 
 // K3 aps_rerank.cu : exact FP32 re-rank of the candidates + completeness proof.

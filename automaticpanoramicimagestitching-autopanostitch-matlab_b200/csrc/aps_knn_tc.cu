@@ -60,6 +60,9 @@
 
 #include "aps_common.cuh"
 
+// the KCT == 3 instantiation leaves the unit loop before the streaming top-K' code ("loop is not reachable")
+#pragma nv_diag_suppress 128
+
 namespace {
 
 constexpr int TM = 128;        // query rows per MMA (UMMA M); a unit holds RB of these row blocks
@@ -294,9 +297,54 @@ __device__ __forceinline__ Unit get_unit(const KParams& P, int64_t u) {
   return x;
 }
 
+// ---- branch-free selection for SHORT sweeps (per-pair searches, KCT == 3) -------------------------------------------
+// A streaming top-K' with thread == query row makes a whole warp take the insert path whenever ANY of its 32 rows has a
+// candidate in the chunk -- with only a few thousand columns per list that is nearly every chunk, and the ALU pipe
+// (FMNMX / LOP3 / FSETP: one warp instruction per 2 cycles per SMSP) ends up 50 % busy at IPC 0.46 with two epilogue
+// warps per SMSP (profiles/r1_ncu_k_knn_tc_pairwise.txt).  Here nothing depends on the data, so the columns of a tile
+// can be split over CS = 2 epilogue groups per row block (4 warps per SMSP hide each other's latencies) without the
+// doubled insertions that made the split lose in the streaming design: every score gets its column-in-tile packed
+// into the 7 low mantissa bits (key; the 127-ulp truncation is inside the re-rank's eps), a min/max tree yields the two
+// largest keys of each SEGMENT (the group's 64 columns of a tile), and those two are inserted into the group's sorted
+// top-3 of the row (value + train row as payload).  Completeness (aps_rerank.cu, tile mode): a column outside a list is
+// either one of its segment's two best (then it lost against the list's third entry) or is bounded by its segment's
+// second best, which is itself below the third entry unless the list's two best share a segment (then W = the second).
+__device__ __forceinline__ void top2_merge(float& h, float& l, const float h2, const float l2) {
+  const float lo = fminf(h, h2);
+  h = fmaxf(h, h2);
+  l = fmaxf(fmaxf(lo, l), l2);
+}
+// top-2 keys of v[0..32): in place, result in (v[0], v[1])
+__device__ __forceinline__ void top2_of_32(float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float a = v[i], b = v[i + 1];
+    v[i] = fmaxf(a, b);
+    v[i + 1] = fminf(a, b);
+  }
+#pragma unroll
+  for (int st = 2; st < 32; st *= 2)
+#pragma unroll
+    for (int i = 0; i < 32; i += 2 * st) top2_merge(v[i], v[i + 1], v[i + st], v[i + st + 1]);
+}
+// insert (x, payload px) into the descending list (l1, l2, l3); strict '>' keeps the earlier entry first on ties
+__device__ __forceinline__ void insert3(float x, uint32_t px, float& l1, float& l2, float& l3, uint32_t& p1, uint32_t& p2,
+                                        uint32_t& p3) {
+  const bool c1 = x > l1, c2 = x > l2, c3 = x > l3;
+  l3 = c2 ? l2 : (c3 ? x : l3);
+  p3 = c2 ? p2 : (c3 ? px : p3);
+  l2 = c1 ? l1 : (c2 ? x : l2);
+  p2 = c1 ? p1 : (c2 ? px : p2);
+  l1 = c1 ? x : l1;
+  p1 = c1 ? px : p1;
+}
+constexpr uint32_t kKeyFloorBits = 0xff7fff80u;  // finite, below every real score: masked columns / empty entries
+constexpr int threads_for(int cs) { return 32 * (1 + RB + 4 * RB * cs); }
+
 // KCT = candidates kept per list: 8, or 4 for the per-pair searches (k = 2: fewer insertions on short sweeps)
-template <bool BIAS, bool DUMP, bool PRE, int KCT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// CS = epilogue groups per row block (each scans TN/CS columns of every tile and keeps its own list)
+template <bool BIAS, bool DUMP, bool PRE, int KCT, int CS = CSPLIT>
+__global__ void __launch_bounds__(threads_for(CS), 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const KParams Pin) {
   // two launches cover one search when the list size depends on a device-side flag: the other one exits here
   if (Pin.variant_flag && ((*Pin.variant_flag != 0) != (Pin.variant_want != 0))) return;
@@ -307,8 +355,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   uint8_t* smem_a = smem;                                      // RB x a_bytes (both row blocks of the unit)
   uint8_t* smem_b = smem_a + RB * a_bytes;                     // NUM_B_STAGES x b_bytes
   float* smem_cs = (float*)(smem_b + NUM_B_STAGES * b_bytes);  // NUM_CS_STAGES x {TN scales, TN biases}
-  uint32_t* smem_topi = (uint32_t*)(smem_cs + NUM_CS_STAGES * 2 * TN);  // [RB*CSPLIT][KC][TM] train rows of the top-K'
-  Barriers* bars = (Barriers*)(smem_topi + RB * CSPLIT * KC * TM);
+  uint32_t* smem_topi = (uint32_t*)(smem_cs + NUM_CS_STAGES * 2 * TN);  // [RB*CS][KC][TM] train rows of the top-K'
+  Barriers* bars = (Barriers*)(smem_topi + RB * CS * KC * TM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksl = Pin.dp / KSLAB;   // 128-byte K slabs per operand row
@@ -328,8 +376,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     for (int i = 0; i < NUM_B_STAGES; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], RB); }
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, RB);
-    for (int i = 0; i < NUM_ACC_SLOTS; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4 * CSPLIT); }
-    for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < NUM_ACC_SLOTS; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4 * CS); }
+    for (int i = 0; i < NUM_CS_STAGES; ++i) { mbar_init(&bars->cs_full[i], 1); mbar_init(&bars->cs_empty[i], (4 * RB * CS)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (NUM_ACC_SLOTS x TN); one CTA per SM
@@ -409,9 +457,9 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     // Group g (4 warps, one per TMEM lane quadrant) owns row block g of the unit: thread == query row.
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
     const int egrp = (warp - FIRST_EPI_WARP) >> 2;
-    const int grp = egrp / CSPLIT;  // row block of the unit
-    const int ch = egrp % CSPLIT;   // column part of every tile this warp scans
-    constexpr int CG = TN / CSPLIT;
+    const int grp = egrp / CS;  // row block of the unit
+    const int ch = egrp % CS;   // column part of every tile this warp scans
+    constexpr int CG = TN / CS;
     const int row_in_tile = quad * 32 + lane;
     const uint32_t si = smem_u32(smem_topi + (egrp * KC) * TM + row_in_tile);  // this row's index slots
     uint32_t tcount = 0;  // tiles consumed so far (same sequence as the MMA warp's)
@@ -419,6 +467,74 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       const Unit x = get_unit(P, u);
       if (x.skip) continue;  // balanced tail: this CTA's share has no second piece
       const int64_t qrow = x.qrow0 + grp * TM + row_in_tile;
+      if constexpr (KCT == 3) {
+        // ---- short sweeps: branch-free two-best per segment, merged into the group's sorted top-3 of the row ----
+        float l1 = __uint_as_float(kKeyFloorBits), l2 = l1, l3 = l1;
+        uint32_t p1 = 0xffffffffu, p2 = 0xffffffffu, p3 = 0xffffffffu;
+        for (int64_t t = x.tl; t < x.th; ++t, ++tcount) {
+          const uint32_t slot = (tcount & 1) * RB + grp, acph = (tcount >> 1) & 1;
+          const uint32_t cs = tcount % NUM_CS_STAGES, cph = (tcount / NUM_CS_STAGES) & 1;
+          mbar_wait(&bars->acc_full[slot], acph);
+          mbar_wait(&bars->cs_full[cs], cph);
+          tc_fence_after();
+          const uint32_t cscale = smem_u32(smem_cs + cs * 2 * TN + ch * CG);
+          const int64_t col0 = t * TN + ch * CG;
+          const bool partial = (col0 < x.t0) || (col0 + CG > x.t1);
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * TN + ch * CG;
+          float m1 = __uint_as_float(kKeyFloorBits), m2 = m1;
+#pragma unroll 1
+          for (int c = 0; c < CG / 32; ++c) {
+            float cur[32];
+            tmem_ld32(taddr + c * 32, cur);  // the other warps of the sub-partition hide this latency
+            tmem_wait_ld(cur);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 s0 = lds_f32x4(cscale + (c * 32 + 8 * g) * 4);
+              const float4 s1 = lds_f32x4(cscale + (c * 32 + 8 * g + 4) * 4);
+              if (BIAS) {
+                const float4 b0 = lds_f32x4(cscale + (TN + c * 32 + 8 * g) * 4);
+                const float4 b1 = lds_f32x4(cscale + (TN + c * 32 + 8 * g + 4) * 4);
+                cur[8 * g + 0] = fmaf(cur[8 * g + 0], s0.x, b0.x); cur[8 * g + 1] = fmaf(cur[8 * g + 1], s0.y, b0.y);
+                cur[8 * g + 2] = fmaf(cur[8 * g + 2], s0.z, b0.z); cur[8 * g + 3] = fmaf(cur[8 * g + 3], s0.w, b0.w);
+                cur[8 * g + 4] = fmaf(cur[8 * g + 4], s1.x, b1.x); cur[8 * g + 5] = fmaf(cur[8 * g + 5], s1.y, b1.y);
+                cur[8 * g + 6] = fmaf(cur[8 * g + 6], s1.z, b1.z); cur[8 * g + 7] = fmaf(cur[8 * g + 7], s1.w, b1.w);
+              } else {
+                cur[8 * g + 0] *= s0.x; cur[8 * g + 1] *= s0.y; cur[8 * g + 2] *= s0.z; cur[8 * g + 3] *= s0.w;
+                cur[8 * g + 4] *= s1.x; cur[8 * g + 5] *= s1.y; cur[8 * g + 6] *= s1.z; cur[8 * g + 7] *= s1.w;
+              }
+            }
+            const uint32_t cbase = (uint32_t)(ch * CG + c * 32);  // column-in-tile of cur[0]
+#pragma unroll
+            for (int j = 0; j < 32; ++j)  // key = score with the column-in-tile in the 7 low mantissa bits
+              cur[j] = __uint_as_float((__float_as_uint(cur[j]) & ~127u) | (cbase + (uint32_t)j));
+            if (partial) {  // first / last tile of the train image: foreign columns can never be selected
+              const int lo = (int)max(x.t0 - col0, (int64_t)0) - c * 32, hi = (int)min(x.t1 - col0, (int64_t)CG) - c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < lo || j >= hi) cur[j] = __uint_as_float(kKeyFloorBits | (cbase + (uint32_t)j));
+            }
+            top2_of_32(cur);
+            top2_merge(m1, m2, cur[0], cur[1]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bars->acc_empty[slot]);
+            mbar_arrive(&bars->cs_empty[cs]);
+          }
+          const uint32_t base = (uint32_t)(t * TN);
+          insert3(m1, base + (__float_as_uint(m1) & 127u), l1, l2, l3, p1, p2, p3);
+          insert3(m2, base + (__float_as_uint(m2) & 127u), l1, l2, l3, p1, p2, p3);
+        }
+        if (qrow < x.qend) {  // CS lists of 3 per row, packed: [row][ch][3]
+          const int64_t o = (x.out_row + grp * TM + row_in_tile) * P.cand_stride + ch * 3;
+          const float floor_v = -1.0e38f;  // entries that never left the floor: fewer than 3 selectable columns
+          P.cand_idx[o + 0] = l1 > floor_v ? p1 : 0xffffffffu; P.cand_score[o + 0] = l1 > floor_v ? l1 : -CUDART_INF_F;
+          P.cand_idx[o + 1] = l2 > floor_v ? p2 : 0xffffffffu; P.cand_score[o + 1] = l2 > floor_v ? l2 : -CUDART_INF_F;
+          P.cand_idx[o + 2] = l3 > floor_v ? p3 : 0xffffffffu; P.cand_score[o + 2] = l3 > floor_v ? l3 : -CUDART_INF_F;
+        }
+        continue;
+      }
       // row-private top-KC (unsorted; aps_rerank.cu orders exactly): scores in registers, train rows in smem
       float bv[KCT];
 #pragma unroll
@@ -451,7 +567,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         };
         float thr_pre = PRE ? pre_threshold(theta) : 0.f;
         float va[32], vb[32];
-        if (CSPLIT == 1) {  // two warps per sub-partition: double-buffer the TMEM loads
+        if (CS == 1) {  // two warps per sub-partition: double-buffer the TMEM loads
           tmem_ld32(taddr, va);
           tmem_wait_ld(va);
         }
@@ -460,9 +576,9 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 #pragma unroll
           for (int h = 0; h < (CG >= 64 ? 2 : 1); ++h) {
             const int c = 2 * c2 + h;
-            float(&cur)[32] = (CSPLIT == 1 && h) ? vb : va;
-            float(&nxt)[32] = (CSPLIT == 1 && h) ? va : vb;
-            if (CSPLIT == 1) {
+            float(&cur)[32] = (CS == 1 && h) ? vb : va;
+            float(&nxt)[32] = (CS == 1 && h) ? va : vb;
+            if (CS == 1) {
               if (c + 1 < CG / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
             } else {  // four warps per sub-partition hide the load latency of each other: single buffer
               tmem_ld32(taddr + c * 32, cur);
@@ -535,8 +651,10 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                       theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
                     } else if constexpr (KCT == 6) {
                       theta = fminf(fminf(fminf(bv[0], bv[1]), bv[2]), fminf(fminf(bv[3], bv[4]), bv[5]));
-                    } else {
+                    } else if constexpr (KCT == 4) {
                       theta = fminf(fminf(bv[0], bv[1]), fminf(bv[2], bv[3]));
+                    } else {
+                      theta = fminf(fminf(bv[0], bv[1]), bv[2]);  // (KCT == 3 never reaches the streaming path)
                     }
                     minpos = (int)(__float_as_uint(theta) & 7u);
 #pragma unroll
@@ -550,7 +668,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                 if (PRE) thr_pre = pre_threshold(theta);
               }
             }
-            if (CSPLIT == 1 && c + 1 < CG / 32) tmem_wait_ld(nxt);
+            if (CS == 1 && c + 1 < CG / 32) tmem_wait_ld(nxt);
           }
         }
         tc_fence_before();
@@ -562,7 +680,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       }
       if (qrow < x.qend) {
         const int cstr = P.cand_stride;
-        const int64_t o = ((x.out_row + grp * TM + row_in_tile) * P.nslot + x.seg * CSPLIT + ch) * cstr;
+        const int64_t o = ((x.out_row + grp * TM + row_in_tile) * P.nslot + x.seg * CS + ch) * cstr;
 #pragma unroll
         for (int i = 0; i < KCT; ++i) {
           P.cand_idx[o + i] = lds_u32(si + i * SLOT_STRIDE);
@@ -572,8 +690,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           P.cand_idx[o + i] = 0xffffffffu;
           P.cand_score[o + i] = -CUDART_INF_F;
         }
-        if (ch == 0)  // e.g. rows of full-width units use the first CSPLIT lists: mark the others empty
-          for (int sl = x.clear_from - x.seg * CSPLIT; sl < P.nslot - x.seg * CSPLIT; ++sl)
+        if (ch == 0)  // e.g. rows of full-width units use the first CS lists: mark the others empty
+          for (int sl = x.clear_from - x.seg * CS; sl < P.nslot - x.seg * CS; ++sl)
             for (int i = 0; i < cstr; ++i) {
               P.cand_idx[o + sl * cstr + i] = 0xffffffffu;
               P.cand_score[o + sl * cstr + i] = -CUDART_INF_F;
@@ -630,6 +748,8 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dp, in
 
 int aps_k_knn_tc_supported(int Dp) { return Dp == 64 || Dp == 128; }
 int aps_k_knn_tc_tile_rows() { return TN; }
+int aps_k_knn_tc_tile_mode_stride() { return 2 * 3; }   // kcand == 3: two lists of three per row
+int aps_k_knn_tc_tile_mode_segment() { return TN / 2; }  // ... each over 64-column segments of the train tiles
 
 // Work decomposition shared by the launcher and by callers that size the candidate buffers.
 struct TcSchedule {
@@ -846,20 +966,26 @@ int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, co
   P.unit_table = d_units;
   P.n_table_units = n_units;
   P.cand_stride = p.kcand;
+  const int cs_groups = p.kcand == 3 ? 2 : CSPLIT;  // epilogue groups per row block of the variant launched below
   const size_t smem = 1024 + (size_t)RB * TM * p.Dp * 2 + (size_t)NUM_B_STAGES * TN * p.Dp * 2 +
-                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * CSPLIT * KC * TM * 4 + sizeof(Barriers);
+                      (size_t)NUM_CS_STAGES * 2 * TN * sizeof(float) + (size_t)RB * cs_groups * KC * TM * 4 + sizeof(Barriers);
   const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
+  int threads = NUM_THREADS;
   auto launch = [&](auto kern) -> int {
     APS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NUM_THREADS, smem, s>>>(map_q, map_t, P);
+    kern<<<grid, threads, smem, s>>>(map_q, map_t, P);
     return APS_OK;
   };
-  if (p.kcand == 4)
+  if (p.kcand == 3) {  // short sweeps: branch-free two-best per segment, two epilogue groups (lists) per row block
+    threads = threads_for(2);
+    P.cand_stride = aps_k_knn_tc_tile_mode_stride();
+    APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, 3, 2>) : launch(k_knn_tc<false, false, false, 3, 2>));
+  } else if (p.kcand == 4)
     APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, 4>) : launch(k_knn_tc<false, false, false, 4>));
   else if (p.kcand == KC)
     APS_TRY(p.bias ? launch(k_knn_tc<true, false, false, KC>) : launch(k_knn_tc<false, false, false, KC>));
   else {
-    aps_set_error(APS_ERR_ARGS, "", "kcand must be 4 or %d", KC);
+    aps_set_error(APS_ERR_ARGS, "", "kcand must be 3, 4 or %d", KC);
     return APS_ERR_ARGS;
   }
   APS_LAUNCHED();

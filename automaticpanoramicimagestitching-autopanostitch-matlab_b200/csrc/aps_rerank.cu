@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
     orow = e;
   }
   const int ncand = nseg * kcand;
-  const float eps = eps_bound(flags, bias_mode);
+  // tile mode: keys carry the column in their 7 low mantissa bits: |key - score| <= 2^-16 |score| <= 1.5e-5 * (|a.b| + |bias|)
+  // <= 2.3e-5 * max|x|^2, times |beta| = 2
+  const float eps = eps_bound(flags, bias_mode) +
+                    (pt.tile_mode ? 5.0e-5f * fmaxf(__int_as_float(flags[2]), 1.0f) : 0.0f);
   const bool exact = flags[0] != 0;
   const float a2 = sqQ[q];
   // s~ = alpha + beta*score
@@ -74,11 +77,29 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
 
   // W = min over lists of the worst (largest) retained approx distance
   float W = CUDART_INF_F;
-  for (int s = 0; s < nseg; ++s) {
-    float m = (sl >= s * kcand && sl < (s + 1) * kcand) ? sapx : -CUDART_INF_F;
+  if (pt.tile_mode) {
+    // lists of three sorted by approximate score (best first), each the top-3 of "two best per segment": a column
+    // outside list s is bounded by the list's third entry, or by its second when the two best share a segment;
+    // a list that is not full bounds its outsiders by its last entry (conservative: tiny train images only)
+    for (int s = 0; s < nseg; ++s) {
+      const uint32_t c0 = __shfl_sync(0xffffffffu, ci, s * 3, G), c1 = __shfl_sync(0xffffffffu, ci, s * 3 + 1, G);
+      const uint32_t c2 = __shfl_sync(0xffffffffu, ci, s * 3 + 2, G);
+      const float a0 = __shfl_sync(0xffffffffu, sapx, s * 3, G), a1 = __shfl_sync(0xffffffffu, sapx, s * 3 + 1, G);
+      const float a2 = __shfl_sync(0xffffffffu, sapx, s * 3 + 2, G);
+      float w;
+      if (c0 == 0xffffffffu) w = CUDART_INF_F;        // no selectable column in this list's part of the train range
+      else if (c1 == 0xffffffffu) w = a0;
+      else if (c2 == 0xffffffffu || c0 / (uint32_t)pt.tile_mode == c1 / (uint32_t)pt.tile_mode) w = a1;
+      else w = a2;
+      W = fminf(W, w);
+    }
+  } else {
+    for (int s = 0; s < nseg; ++s) {
+      float m = (sl >= s * kcand && sl < (s + 1) * kcand) ? sapx : -CUDART_INF_F;
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o, G));
-    W = fminf(W, m);
+      for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o, G));
+      W = fminf(W, m);
+    }
   }
   // prune: lanes whose lower bound exceeds the k-th smallest upper bound cannot be in the top-k
   const float ub = sapx + eps, lb = sapx - eps;

@@ -16,7 +16,9 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pc
         "sm__throughput.avg.pct", "smsp__issue_active.avg.pct", "sm__inst_executed.sum ", "sm__cycles_active.avg",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ", "smsp__inst_executed.sum ",
         "gpu__dram_throughput.avg.pct", "lts__throughput.avg.pct", "l1tex__throughput.avg.pct",
-        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg [", "smsp__cycles_active.avg "]
+        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg [", "smsp__cycles_active.avg ",
+        "sm__inst_executed_pipe_alu", "sm__inst_executed_pipe_fma", "sm__inst_executed_pipe_lsu",
+        "sm__pipe_alu_cycles_active", "sm__pipe_fma_cycles_active", "sm__pipe_fmaheavy_cycles_active"]
 for vals in rows[2:]:
     name = dict(zip(hdr, vals)).get("Kernel Name", "?")
     print("== kernel:", name[:100])

@@ -12,6 +12,8 @@ desc, c = pkg.synth.make_config(cid, n=n, kp=kp)
 cells = [pkg.binaryFeatures(d) for d in desc] if c["kind"] == "orb" else desc
 inp = {"Matchingmethod": "Exhaustive", "Matchingthreshold": 10.0 if c["kind"] == "orb" else 1.5, "Ratiothreshold": 0.7}
 ctx = pkg._lib.default_context()
+if os.environ.get("APS_PAIR_EPILOGUE"):   # 1 = branch-free segment selection (aps_ctx_set_pairwise_epilogue)
+    ctx.set_pairwise_epilogue(int(os.environ["APS_PAIR_EPILOGUE"]))
 pairs = sum(desc[i].shape[0] * desc[j].shape[0] for j in range(n) for i in range(j))
 import ctypes as C
 

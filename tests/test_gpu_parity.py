@@ -377,3 +377,38 @@ def test_golden_semantics_vectors_gpu(aps):
         assert total == len(rows) and total > 30
     cand, pairs = aps.selectImagePartners(g["sp_counts"], int(g["sp_m"]))
     assert np.array_equal(cand, g["sp_cand"]) and np.array_equal(pairs, g["sp_lin"])
+
+
+@pytest.mark.parametrize("cid,n,kp", [(5, 5, 3000), (1, 4, 2500), (5, 6, 500), (1, 3, 129), (5, 3, 40)])
+def test_pairwise_segment_epilogue_variant(aps, orc, cid, n, kp):
+    """aps_ctx_set_pairwise_epilogue(1): branch-free 'two best per 64-column segment -> sorted top-3' epilogue of the unit-table launch
+    (two lists per row, four epilogue warps per SM sub-partition); the re-rank's tile-mode proof (third entry of a list,
+    or its second when the two best share a segment, else exact fallback) must give the oracle's lists."""
+    ctx = aps._lib.default_context()
+    desc, c = aps.synth.make_config(cid, n=n, kp=kp)
+    desc = [d.copy() for d in desc]
+    if desc[1].shape[0] > 40 and desc[0].shape[0] > 40:
+        desc[1][5:9] = desc[0][20]      # four identical train rows inside one segment: best and second best share it
+        desc[1][30] = desc[0][21]
+        desc[1][31] = desc[0][21] * (1.0 if cid == 1 else 1.0005)
+    ctx.set_float_engine(2)
+    ctx.set_pairwise_epilogue(1)
+    try:
+        got = aps.featureMatchingPairwise({"Matchingthreshold": 1.5, "Ratiothreshold": 0.7}, desc, n)
+        stats = ctx.last_stats()
+    finally:
+        ctx.set_float_engine(0)
+        ctx.set_pairwise_epilogue(0)
+    assert stats["engine"] == "tcgen05"
+    ref = orc.feature_matching_pairwise(desc, 1.5, 0.7)
+    rows = 0
+    for j in range(n):
+        for i in range(j):
+            exp = ref["cells"].get((i, j))
+            if exp is None:
+                assert got[i][j].shape[0] == 0, (i, j)
+                continue
+            assert np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
+            rows += len(exp)
+    assert rows > (50 if kp > 100 else 5)
+    print("segment epilogue", cid, n, kp, stats)
