@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   int64_t q = q0 + (row_ok ? r : 0);
   if (row_map) q = row_ok ? (int64_t)row_map[r] : q0;  // second pass: candidate row r belongs to query row_map[r]
   int64_t orow = q - out_row0;  // output row
+  int64_t tn = 0;               // batched pairwise: rows of the train image
   if (pt.eoff) {  // batched pairwise: candidate row r is entry r of pair p: query off_i + (r - eoff[p]), train image j
     const int64_t e = row_ok ? r : 0;
     int lo = 0, hi = pt.npairs;  // last p with eoff[p] <= e
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
     }
     q = (int64_t)pt.qoff[lo] + (e - pt.eoff[lo]);
     t0 = pt.toff[lo];
+    tn = pt.tcnt[lo];
     orow = e;
   }
   const int ncand = nseg * kcand;
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
 
   // W = min over lists of the worst (largest) retained approx distance
   float W = CUDART_INF_F;
+  uint32_t segscan[2] = {0xffffffffu, 0xffffffffu}, segskip[4] = {0u, 0u, 0u, 0u};  // tile mode: segments to scan exactly
   if (pt.tile_mode) {
     // lists of three sorted by approximate score (best first), each the top-3 of "two best per segment": a column
     // outside list s is bounded by the list's third entry, or by its second when the two best share a segment;
@@ -89,8 +92,17 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
       float w;
       if (c0 == 0xffffffffu) w = CUDART_INF_F;        // no selectable column in this list's part of the train range
       else if (c1 == 0xffffffffu) w = a0;
-      else if (c2 == 0xffffffffu || c0 / (uint32_t)pt.tile_mode == c1 / (uint32_t)pt.tile_mode) w = a1;
-      else w = a2;
+      else if (c2 == 0xffffffffu) w = a1;
+      else {
+        w = a2;
+        // two best from one segment: the segment's other columns are only bounded by a1.  Instead of giving up, the
+        // row's lanes scan that one segment exactly further down (segscan) -- 64 columns, not the whole image.
+        if (c0 / (uint32_t)pt.tile_mode == c1 / (uint32_t)pt.tile_mode) {
+          if (segscan[0] == 0xffffffffu) { segscan[0] = c0 / (uint32_t)pt.tile_mode; segskip[0] = c0; segskip[1] = c1; }
+          else if (segscan[1] == 0xffffffffu) { segscan[1] = c0 / (uint32_t)pt.tile_mode; segskip[2] = c0; segskip[3] = c1; }
+          else w = a1;
+        }
+      }
       W = fminf(W, w);
     }
   } else {
@@ -163,6 +175,35 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
     proven = (W - eps > dk);
   else
     proven = (W == CUDART_INF_F);  // every train row was a candidate
+  if (pt.tile_mode) {
+    // segments whose two best both sit in a list: every other column of the segment must be farther than the k-th
+    // neighbour, checked with exact distances (strictly: a tie would have to be ranked by index)
+    const bool want = row_ok && proven && !rej && segscan[0] != 0xffffffffu;
+    if (__any_sync(0xffffffffu, want)) {
+      float dmin = CUDART_INF_F;
+      bool bad = false;
+      if (want) {
+        if (nvalid < k || !pt.eoff) bad = true;
+        for (int z = 0; z < 2 && !bad; ++z) {
+          if (segscan[z] == 0xffffffffu) break;
+          const int64_t cbeg = (int64_t)segscan[z] * pt.tile_mode;
+          const int64_t c_lo = cbeg > t0 ? cbeg : t0, c_hi = (cbeg + pt.tile_mode < t0 + tn) ? cbeg + pt.tile_mode : t0 + tn;
+          const float* a = Q + q * D;
+          for (int64_t col = c_lo + sl; col < c_hi; col += G) {
+            if ((uint32_t)col == segskip[2 * z] || (uint32_t)col == segskip[2 * z + 1]) continue;
+            const float* b = T + col * D;
+            const float dd = (metric == 0) ? l2sq_flann(a, b, D) : ssd_seq(a, b, D, a2, sqT[col]);
+            if (!(dd == dd)) bad = true;
+            dmin = fminf(dmin, dd);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o, G));
+      const bool anybad = (__ballot_sync(0xffffffffu, bad) & segmask) != 0u;
+      if (want && (anybad || !(dmin > dk))) proven = false;
+    }
+  }
   if (rej) proven = true;  // nothing to prove: the row is reported as having no neighbour
   if (nan_seen) proven = false;
   if (row_ok && !proven && sl == 0) {
