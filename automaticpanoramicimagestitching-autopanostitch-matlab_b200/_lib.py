@@ -147,7 +147,7 @@ class Context:
         check(lib().aps_ctx_set_float_engine(self._h, int(engine)))
 
     def set_pairwise_epilogue(self, mode: int):
-        """0 = streaming top-4 (default), 1 = branch-free segment selection (see include/apsmatch.h)."""
+        """-1 = auto (default), 0 = streaming top-4, 1 = branch-free segment selection (see include/apsmatch.h)."""
         check(lib().aps_ctx_set_pairwise_epilogue(self._h, int(mode)))
 
     def enable_timing(self, on=True):

@@ -128,8 +128,8 @@ extern "C" int aps_ctx_set_float_engine(aps_ctx* c, int engine) {
   return APS_OK;
 }
 extern "C" int aps_ctx_set_pairwise_epilogue(aps_ctx* c, int mode) {
-  if (!c || (mode != 0 && mode != 1))
-    APS_FAIL(APS_ERR_ARGS, "", "pairwise epilogue must be 0 (streaming) or 1 (segment selection)");
+  if (!c || mode < -1 || mode > 1)
+    APS_FAIL(APS_ERR_ARGS, "", "pairwise epilogue must be -1 (auto), 0 (streaming) or 1 (segment selection)");
   c->pairwise_epilogue = mode;
   return APS_OK;
 }
@@ -1250,7 +1250,13 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       APS_TRY(d_units.alloc(units.size(), s));
       // candidates per (query, train image): k = 2 needs the two best and one witness.  4 = one streaming top-4 list;
       // 3 = branch-free segment epilogue, two sorted lists of three (aps_knn_tc.cu, k_knn_tc<.., 3, 2>)
-      const int KCP = c->pairwise_epilogue == 1 ? 3 : 4;
+      // auto: the segment epilogue costs the same for every tile, the streaming one gets cheaper as a sweep goes on
+      // (inserts become rare): measured 52 vs 66 ms per batch at 32 tiles per sweep (profiles/r1_ncu_history.txt)
+      int64_t tile_steps = 0;
+      for (const aps_tc_unit& u : units) tile_steps += ((int64_t)u.t1 - u.t0 + 127) / 128;
+      const bool segment_epilogue = c->pairwise_epilogue == 1 ||
+                                    (c->pairwise_epilogue < 0 && tile_steps <= 48 * (int64_t)units.size());
+      const int KCP = segment_epilogue ? 3 : 4;
       const int nlist = KCP == 3 ? aps_k_knn_tc_tile_mode_stride() / 3 : 1;
       const int cstride = nlist * KCP;
       APS_TRY(cidx.alloc((size_t)E * cstride, s));

@@ -45,7 +45,7 @@ struct aps_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int float_engine = 0;  // 0 auto, 1 exact only, 2 tensor required
-  int pairwise_epilogue = 0;  // 0 streaming top-4, 1 branch-free segment selection (aps_ctx_set_pairwise_epilogue)
+  int pairwise_epilogue = -1;  // -1 auto, 0 streaming top-4, 1 branch-free segment selection (aps_ctx_set_pairwise_epilogue)
   int64_t stats[4] = {0, 0, 0, 0};
   bool timing = false;
   std::vector<cudaEvent_t> tc_events;  // pairs (start, stop) of tcgen05 kernel launches

@@ -68,9 +68,10 @@ int aps_abi_version(void);
  * 2 = tcgen05 path required (error if the shape is unsupported). */
 int aps_ctx_set_float_engine(aps_ctx* ctx, int engine);
 /* Epilogue of the batched pairwise tensor pass (aps_feature_matching_pairwise*, float descriptors): 0 = streaming
- * top-4 list per (query, train image) [default]; 1 = branch-free "two best per 64-column segment" selection with two
- * sorted lists of three per query and four epilogue warps per SM sub-partition.  Results are identical (both feed the
- * exact re-rank and its completeness proof); only speed and the share of rows sent to the exact fallback differ. */
+ * top-4 list per (query, train image); 1 = branch-free "two best per 64-column segment" selection with two sorted
+ * lists of three per query and four epilogue warps per SM sub-partition; -1 = auto [default]: 1 when the train
+ * images average at most 48 tiles of 128 descriptors, else 0.  Results are identical (both feed the exact re-rank
+ * and its completeness proof); only speed and the share of rows sent to the exact fallback differ. */
 int aps_ctx_set_pairwise_epilogue(aps_ctx* ctx, int mode);
 /* Counters of the last float search on this context: [0] rows searched, [1] rows whose
  * candidate set could not be PROVEN complete and were re-searched exactly, [2] engine used

@@ -35,4 +35,8 @@ def aps():
     """The product package (directory name is not an identifier, so it is loaded by path)."""
     import __graft_entry__ as ge
 
-    return ge.load_package()
+    pkg = ge.load_package()
+    mode = os.environ.get("APS_TEST_PAIR_EPILOGUE")  # GPU runs only: every pairwise test through the other epilogue
+    if mode is not None:
+        pkg._lib.default_context().set_pairwise_epilogue(int(mode))
+    return pkg

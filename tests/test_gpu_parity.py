@@ -2,6 +2,8 @@
 seeded inputs and against the committed golden vectors.  Integer/index work is compared bit-exact;
 float distances are compared bit-exact too (the re-rank uses the oracle's operation order) with the
 north star's 1e-4 relative tolerance stated as the fallback bar."""
+import os
+
 import numpy as np
 import pytest
 
@@ -300,18 +302,21 @@ def test_pairwise_mixed_magnitudes_and_empty_images(aps, orc):
                 assert np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
 
 
+@pytest.mark.parametrize("epilogue", [0, 1])
 @pytest.mark.parametrize("cid,n,kp", [(5, 5, 3000), (1, 4, 2500)])
-def test_pairwise_tensor_engine_large(aps, orc, cid, n, kp):
+def test_pairwise_tensor_engine_large(aps, orc, cid, n, kp, epilogue):
     """sweeps of >= 16 train tiles per unit: the unit-table launch runs with the raw pre-filter (bias and
     scale-only scores), image boundaries not aligned to the 128-row tiles."""
     ctx = aps._lib.default_context()
     desc, c = aps.synth.make_config(cid, n=n, kp=kp)
     ctx.set_float_engine(2)
+    ctx.set_pairwise_epilogue(epilogue)   # both epilogues of the unit-table launch (default: chosen by sweep length)
     try:
         got = aps.featureMatchingPairwise({"Matchingthreshold": 1.5, "Ratiothreshold": 0.7}, desc, n)
         stats = ctx.last_stats()
     finally:
         ctx.set_float_engine(0)
+        ctx.set_pairwise_epilogue(int(os.environ.get("APS_TEST_PAIR_EPILOGUE", "-1")))
     assert stats["engine"] == "tcgen05"
     ref = orc.feature_matching_pairwise(desc, 1.5, 0.7)
     rows = 0
@@ -398,7 +403,7 @@ def test_pairwise_segment_epilogue_variant(aps, orc, cid, n, kp):
         stats = ctx.last_stats()
     finally:
         ctx.set_float_engine(0)
-        ctx.set_pairwise_epilogue(0)
+        ctx.set_pairwise_epilogue(int(os.environ.get("APS_TEST_PAIR_EPILOGUE", "-1")))
     assert stats["engine"] == "tcgen05"
     ref = orc.feature_matching_pairwise(desc, 1.5, 0.7)
     rows = 0
