@@ -1294,7 +1294,10 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   std::vector<int32_t> hc(np);
   APS_CUDA(cudaMemcpyAsync(hc.data(), d_count.p, np * 4, cudaMemcpyDeviceToHost, s));
   APS_CUDA(cudaStreamSynchronize(s));
-  if (tensor && dtype == APS_F32) c->stats[1] += c->h_flags[33];
+  if (tensor && dtype == APS_F32) {
+    c->stats[1] += c->h_flags[33];
+    c->h_flags[32] = (int32_t)c->stats[1];  // aps_ctx_last_stats reports the fallback rows of a tensor search from here
+  }
   std::vector<int64_t> outoff(np + 1, 0);
   for (int p = 0; p < np; ++p) outoff[p + 1] = outoff[p] + hc[p];
   const int64_t M = outoff[np];

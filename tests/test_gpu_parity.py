@@ -416,4 +416,7 @@ def test_pairwise_segment_epilogue_variant(aps, orc, cid, n, kp):
             assert np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
             rows += len(exp)
     assert rows > (50 if kp > 100 else 5)
-    print("segment epilogue", cid, n, kp, stats)
+    if kp > 40:  # the planted identical train rows tie for best and second best: unprovable, must take the exact fallback
+        assert stats["fallback_rows"] >= 1, stats
+    if kp >= 500:  # (train images of one or two tiles have short lists, whose conservative bound sends ~10 % to the fallback)
+        assert stats["fallback_rows"] < 0.05 * stats["rows"] + 16, stats
