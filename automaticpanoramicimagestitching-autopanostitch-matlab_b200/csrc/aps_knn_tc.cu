@@ -8,7 +8,9 @@
 // (SWIZZLE_128B, K-major), and a fused top-K' selection in the epilogue: the distance matrix is
 // never written.  The K' best train rows per (query row, column segment) go to aps_rerank.cu, which
 // recomputes them exactly in FP32 and proves the top-k complete.  K' = 8; 6 when the operands are exact in
-// bf16 (device flag, both variants launched, one exits at once); 4 in the per-pair searches (k = 2).
+// bf16 (device flag, both variants launched, one exits at once); 4 in the per-pair searches (k = 2) -- or, for
+// per-pair sweeps of <= 48 tiles, the branch-free SEGMENT epilogue (KCT == 3, CS == 2; see top2_of_32 below):
+// 16 epilogue warps, two sorted lists of three per row, no data-dependent branch.
 //
 // CTA = 352 threads, persistent over work units.  A unit = TWO 128-row query blocks (256 rows, both A
 // tiles resident in shared memory) x a range of 128-column train tiles; every B tile feeds two MMA

@@ -11,6 +11,8 @@
 //   => if  W - eps > (k-th smallest exact candidate distance)  no outsider can enter or tie the top-k.
 //
 // Rows failing the test are appended to a list and re-searched by the exact CUDA-core kernel.
+// Tile mode (lists made by the segment epilogue of the per-pair searches): W per list = its third entry, and the one
+// segment whose two best both sit in a list is scanned exactly by the row's lanes (see the W computation below).
 // One warp per query row, one lane per candidate (nseg*kcand <= 32).
 #include <math_constants.h>
 
