@@ -54,7 +54,13 @@ typedef struct aps_ctx aps_ctx;             /* one per (process, GPU): device bu
 typedef struct aps_matchlist aps_matchlist; /* CSR form of the reference's n x n `matches` cell        */
 typedef struct aps_gplan aps_gplan;         /* staged global-matching pipeline (multi-GPU building block) */
 
-/* ---- context ------------------------------------------------------------------------------- */
+/* ---- context -------------------------------------------------------------------------------
+ * No function of the reference corresponds to these: the context stands in for the state a MATLAB process or
+ * parfor worker holds between MEX calls (PP/main.m:41-45 opens the pool, PP/featureMatching/
+ * featureMatchingPairwise.m:54-59 runs the matcher on its workers).  The gateways create one lazily per process and
+ * GPU and release it with mexAtExit (mex/aps_mex_common.h).  aps_last_error / aps_error_id carry what the
+ * reference passes to mexErrMsgIdAndTxt(id, msg) (PP/mex/flann_knn.cpp:94-95,126-177,202;
+ * PP/mex/nearest2HammingExhaustiveMEX.cpp:17-28). */
 int aps_ctx_create(int device, aps_ctx** out);
 void aps_ctx_destroy(aps_ctx* ctx);
 /* Use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own. */
@@ -84,7 +90,8 @@ int aps_ctx_last_stats(aps_ctx* ctx, int64_t stats[4]);
 int aps_ctx_enable_timing(aps_ctx* ctx, int enable);
 int aps_ctx_tc_time(aps_ctx* ctx, double* ms_total, int64_t* launches);
 int64_t aps_launch_count(void);
-/* Pinned host memory for callers that want asynchronous-speed copies (bench, MEX staging). */
+/* Pinned host memory for callers that want asynchronous-speed copies (bench, MEX staging) -- the descriptor cells the
+ * producer hands over (PP/featureMatching/getFeaturePoints.m:32-74 -> allDescriptors, PP/main.m:95-99) can be staged here. */
 void* aps_host_alloc(size_t bytes);
 void aps_host_free(void* p);
 
@@ -205,7 +212,9 @@ int aps_image_matching(aps_ctx* ctx, int n_images, const int64_t* pair_ptr, cons
                        uint8_t* inliers, int32_t* n_inliers, uint8_t* accepted, int32_t* draws_used);
 
 /* ---- staged global pipeline (building block of the multi-GPU host; bench.py times these) -----
- * All work is enqueued on the context's stream.  Query rows [q0,q1) of the pooled matrix may be
+ * The stages of PP/featureMatching/featureMatchingGlobal.m as separate calls: pooling + normalisation :70-97
+ * (create / upload), global kNN :106-120 (knn), per-feature filter loop :123-161 (filter, then compact after the
+ * ranks exchanged their record slices).  All work is enqueued on the context's stream.  Query rows [q0,q1) of the pooled matrix may be
  * sharded across ranks: every rank holds all descriptors, so a query's neighbours are complete
  * locally and no cross-GPU merge exists. */
 int aps_gplan_create(aps_ctx* ctx, const int64_t* counts, int n, int D, int dtype, int k, aps_gplan** out);
