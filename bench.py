@@ -135,6 +135,28 @@ def flann_kdtree_rate(X, exact_idx1, q0, nq):
             "sample": f"index over all {F} rows, {nq} queries searched, search time scaled linearly"}
 
 
+def blas_exhaustive_rate(X, nq):
+    """The reference's own EXHAUSTIVE float arithmetic (PP/featureMatching/matchFeaturesScratch.m:343-358,
+    nearest2SSDExhaustive: blocks of floor(1e7/N2) query rows, a2 + b2' - 2*A*B' by sgemm, min / mask / min) restated
+    with numpy on this box's BLAS threads -- MATLAB would run the same three steps on MKL.  Extended here to the k = 4
+    smallest per row (argpartition) so that it does the work of one global step.  Not bit-compatible with the oracle
+    (sgemm summation order), so it is a timing arm only."""
+    F = X.shape[0]
+    block = max(1, int(1e7 // max(F, 1)))
+    b2 = np.sum(X * X, axis=1, dtype=np.float32)
+    t0 = time.perf_counter()
+    for s0 in range(0, nq, block):
+        A = X[s0:min(nq, s0 + block)]
+        a2 = np.sum(A * A, axis=1, dtype=np.float32)
+        D2 = (a2[:, None] + b2[None, :]) - np.float32(2) * (A @ X.T)
+        part = np.argpartition(D2, KNN, axis=1)[:, :KNN]
+        np.take_along_axis(D2, part, axis=1).sort(axis=1)
+    dt = time.perf_counter() - t0
+    return {"engine": "numpy sgemm + argpartition (nearest2SSDExhaustive's blocked GEMM form, k = %d)" % KNN,
+            "value": nq * float(F) / dt, "unit": UNIT, "cores": os.cpu_count(),
+            "sample": f"{nq} query rows x all {F} train rows in blocks of {block} rows ({dt:.1f} s), scaled linearly"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference path's own CPU arithmetic on this box's host cores.
     MATLAB cannot run here and flann_knn.cpp needs OpenCV C++ (absent), so this is the oracle port
@@ -176,6 +198,7 @@ def run_reference(args, rank, world):
     approx = flann_kdtree_rate(X, idx, q0, nq)   # idx: the exact neighbours of the last timed sample
     if approx is not None:
         line["reference_default_engine"] = approx
+    line["reference_exhaustive_blas"] = blas_exhaustive_rate(X, min(F, 4 * nq))
     print(json.dumps(line), flush=True)
 
 
