@@ -26,7 +26,7 @@ from ._lib import APS_COL_MAJOR, APS_F32, APS_ROW_MAJOR, APS_U8, ApsError, check
 
 
 class binaryFeatures:
-    """Stand-in for MATLAB's binaryFeatures object: packed uint8 rows in `.Features`."""
+    """Stand-in for MATLAB's binaryFeatures object (featureMatchingGlobal.m:56-75, matchFeaturesScratch.m:259-262): packed uint8 rows in `.Features`."""
 
     def __init__(self, features):
         f = np.asarray(features)
@@ -507,7 +507,11 @@ def imageMatching(input, n, keypoints, matchesAll, imagesProcessed=None, samples
 
 
 class GlobalPlan:
-    """Staged global pipeline (aps_gplan_*): the building block bench.py and the multi-GPU host use."""
+    """Staged global pipeline (aps_gplan_*): the building block bench.py and the multi-GPU host use.
+
+    The stages of PP/featureMatching/featureMatchingGlobal.m as separate calls: pooling + normalisation :70-97
+    (upload / prepare), global kNN :106-120 (knn), per-feature filter loop :123-161 (filter, then compact once the
+    ranks have exchanged their record slices)."""
 
     def __init__(self, ctx, counts, D, is_binary, k):
         self.ctx, self.n, self.D, self.k = ctx, len(counts), int(D), int(k)
@@ -521,36 +525,46 @@ class GlobalPlan:
         self.F = int(lib().aps_gplan_total(h))
 
     def upload(self, mats):
+        """H2D of the per-image descriptor matrices into the pooled [F x D] matrix (vertcat, featureMatchingGlobal.m:70-77)."""
         ptrs, _, layout, keep = _desc_args(list(mats), [0 if m is None else m.shape[0] for m in mats])
         check(lib().aps_gplan_upload(self._h, ptrs, layout))
         self._keep = keep
 
     def upload_pointers(self, ptr_list, layout=APS_ROW_MAJOR):
+        """Same from raw host pointers (pinned staging buffers of aps_host_alloc), one per image."""
         ptrs = (C.c_void_p * max(self.n, 1))(*ptr_list)
         check(lib().aps_gplan_upload(self._h, ptrs, layout))
 
     def desc_device(self):
+        """Device pointer of the pooled descriptors (for the NCCL all-gather of row blocks, multigpu.gather_descriptors)."""
         return lib().aps_gplan_desc_device(self._h)
 
     def records_device(self):
+        """Device pointer of the per-query records: target[F] int32 then partner[F] uint32 (the accept / match of :140-152)."""
         return lib().aps_gplan_records_device(self._h)
 
     def knn_device(self):
+        """Device pointers (idx, dist) of the [F x k] kNN tables (nnIdxAll / nnDistAll, :106-120)."""
         return lib().aps_gplan_knn_idx_device(self._h), lib().aps_gplan_knn_dist_device(self._h)
 
     def prepare(self):
+        """K1: single + L2 normalisation with eps inside the sqrt (:80-84), tensor operands, train view."""
         check(lib().aps_gplan_prepare(self._h))
 
     def knn(self, q0=0, q1=None):
+        """K2/K3 (or K4 for binary): exact k nearest neighbours of query rows [q0, q1) against all F rows (:106-120)."""
         check(lib().aps_gplan_knn(self._h, int(q0), int(self.F if q1 is None else q1)))
 
     def filter(self, ratio, q0=0, q1=None):
+        """K5a: self / same-image removal and Lowe ratio test of rows [q0, q1) (:123-147) -> records."""
         check(lib().aps_gplan_filter(self._h, int(q0), int(self.F if q1 is None else q1), float(ratio)))
 
     def compact(self):
+        """K5b: scatter of all F records into the n x n cell in the reference's loop order (:149-159), CSR form."""
         check(lib().aps_gplan_compact(self._h))
 
     def download_knn(self, q0=0, q1=None):
+        """D2H of the kNN tables of rows [q0, q1): (idx uint32 1-based, dist float32), as flann_knn_win returns them."""
         q1 = self.F if q1 is None else q1
         idx = np.zeros((max(q1 - q0, 0), self.k), np.uint32)
         dist = np.zeros((max(q1 - q0, 0), self.k), np.float32)
@@ -558,6 +572,7 @@ class GlobalPlan:
         return idx, dist
 
     def download(self):
+        """D2H of the CSR match lists (pair_ptr, rows) -- the `matches` cell of featureMatchingGlobal.m:155-159."""
         h = C.c_void_p()
         check(lib().aps_gplan_download(self._h, C.byref(h)))
         try:
