@@ -153,3 +153,44 @@ def test_golden_semantics_vectors(orc):
     assert np.array_equal(o["pair_ptr"], g["gf_pair_ptr"]) and np.array_equal(o["rows"], g["gf_rows"]) and len(o["rows"]) > 30
     cand, lin = orc.select_partners(g["sp_counts"], int(g["sp_m"]))
     assert np.array_equal(cand, g["sp_cand"]) and np.array_equal(lin + 1, g["sp_lin"])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_shapes_differential(orc, seed):
+    """random small shapes, dimensions, k, thresholds and image counts (including empty images): oracle == restatement"""
+    rng = np.random.default_rng(1000 + seed)
+    # pairwise matcher, exact-arithmetic floats and short binary codes
+    for _ in range(4):
+        n1, n2, d = int(rng.integers(1, 90)), int(rng.integers(1, 90)), int(rng.choice([3, 8, 17, 32]))
+        A = rng.integers(-2, 3, (n1, d)).astype(np.float32)
+        B = rng.integers(-2, 3, (n2, d)).astype(np.float32)
+        k = min(n1, n2) // 2
+        B[:k] = A[rng.permutation(n1)[:k]]
+        thr, ratio, uniq = float(rng.choice([0.5, 3.5, 50.0])), float(rng.choice([0.3, 0.6, 0.9, 1.0])), bool(rng.integers(0, 2))
+        m, met = orc.match_features(A, B, thr, ratio, uniq)
+        em, emet = mr.match_features(A, B, thr, ratio, uniq)
+        assert np.array_equal(m, em) and np.array_equal(met, emet.astype(np.float64)), (n1, n2, d, thr, ratio, uniq)
+        nb = int(rng.choice([1, 2, 4]))
+        Ab = rng.integers(0, 256, (n1, nb), dtype=np.uint8)
+        Bb = rng.integers(0, 256, (n2, nb), dtype=np.uint8)
+        Bb[:k] = Ab[rng.permutation(n1)[:k]]
+        thr = float(rng.choice([5.0, 25.0, 100.0]))
+        m, met = orc.match_features(Ab, Bb, thr, ratio, uniq)
+        em, emet = mr.match_features(Ab, Bb, thr, ratio, uniq)
+        assert np.array_equal(m, em) and np.array_equal(met, emet.astype(np.float64)), (n1, n2, nb, thr, ratio, uniq)
+    # global path on binary codes (exact integer distances): whole function, CSR form
+    nimg = int(rng.integers(1, 6))
+    counts = [int(c) for c in rng.integers(0, 40, nimg)]
+    base = rng.integers(0, 256, (25, 2), dtype=np.uint8)
+    desc = [base[rng.integers(0, 25, c)] ^ (rng.random((c, 2)) < 0.1).astype(np.uint8) for c in counts]
+    k, ratio = int(rng.choice([2, 3, 4, 6])), float(rng.choice([0.5, 0.8, 1.0]))
+    o = orc.feature_matching_global(desc, k, ratio)
+    pp, rows = mr.feature_matching_global(desc, k, ratio)
+    assert np.array_equal(o["pair_ptr"], pp) and np.array_equal(o["rows"], rows), (counts, k, ratio)
+    # partner selection
+    n = int(rng.integers(1, 20))
+    Cm = np.triu(rng.integers(0, 3, (n, n)), 1)
+    msel = int(rng.integers(1, 8))
+    cand, lin = orc.select_partners(Cm, msel)
+    ec, el = mr.select_partners(Cm, msel)
+    assert np.array_equal(cand, ec) and np.array_equal(lin + 1, el)
