@@ -9,7 +9,10 @@ a B200, and fails loudly otherwise.
 from . import _lib  # noqa: F401
 from ._lib import ApsError, Context, build_library, library_path  # noqa: F401
 from .host import (  # noqa: F401
+    ApsSemanticsWarning,
     GlobalPlan,
+    PairwisePlan,
+    RECORD_PAD,
     binaryFeatures,
     featureMatchingGlobal,
     estimateTransformationRANSAC,
@@ -19,6 +22,7 @@ from .host import (  # noqa: F401
     ransacSampleTable,
     flann_knn_win,
     matchFeaturesScratch,
+    merge_pairwise_csr,
     merge_pairwise_shards,
     nearest2HammingExhaustiveMEX,
     nearest2HammingExhaustiveOMPMEX,

@@ -110,6 +110,13 @@ def lib():
         "aps_gplan_download_knn": (i32, [vp, i64, i64, vp, vp]),
         "aps_gplan_download": (i32, [vp, pp]),
         "aps_gplan_pair_counts_device": (i32, [vp, pp]),
+        "aps_pplan_create": (i32, [vp, C.POINTER(i64), i32, i32, i32, pp]),
+        "aps_pplan_destroy": (None, [vp]),
+        "aps_pplan_total": (i64, [vp]),
+        "aps_pplan_desc_device": (vp, [vp]),
+        "aps_pplan_upload": (i32, [vp, pp, i32]),
+        "aps_pplan_prepare": (i32, [vp]),
+        "aps_pplan_match": (i32, [vp, dbl, dbl, i32, i32, pp]),
         "aps_debug_tc_slots": (i32, [vp, i64, i64]),
         "aps_debug_tc_scores": (i32, [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
     }

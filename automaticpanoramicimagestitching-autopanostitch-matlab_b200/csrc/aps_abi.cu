@@ -668,7 +668,8 @@ struct aps_gplan {
   // results
   DevBuf<uint32_t> knn_idx;
   DevBuf<float> knn_dist;
-  DevBuf<int32_t> records;  // target[F] then partner[F]
+  DevBuf<int2> records;     // [F + APS_RECORD_PAD]: (target image + 1 | 0, partner's local index) per query row; the
+                            // padding lets equal-sized rank slices of an in-place all-gather run past F
   DevBuf<int64_t> dir_counts, pair_counts, pair_ptr, rank;
   DevBuf<uint32_t> rows;
   bool compacted = false;
@@ -723,7 +724,7 @@ extern "C" int aps_gplan_create(aps_ctx* c, const int64_t* counts, int n, int D,
   A(p->img_of_row.alloc((size_t)F, s));
   A(p->knn_idx.alloc((size_t)F * k, s));
   A(p->knn_dist.alloc((size_t)F * k, s));
-  A(p->records.alloc((size_t)F * 2, s));
+  A(p->records.alloc((size_t)F + APS_RECORD_PAD, s));
   A(p->dir_counts.alloc((size_t)n * n, s));
   A(p->pair_counts.alloc((size_t)n * n, s));
   A(p->pair_ptr.alloc((size_t)n * n + 1, s));
@@ -732,7 +733,7 @@ extern "C" int aps_gplan_create(aps_ctx* c, const int64_t* counts, int n, int D,
   if (rc == APS_OK && cudaMemcpyAsync(p->d_off.p, p->off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s) != cudaSuccess)
     rc = APS_ERR_CUDA;
   if (rc == APS_OK) rc = aps_k_fill_img_of_row(s, p->d_off.p, n, p->maxcount, p->img_of_row.p);
-  if (rc == APS_OK && F > 0 && cudaMemsetAsync(p->records.p, 0, (size_t)F * 8, s) != cudaSuccess) rc = APS_ERR_CUDA;
+  if (rc == APS_OK && F > 0 && cudaMemsetAsync(p->records.p, 0, ((size_t)F + APS_RECORD_PAD) * 8, s) != cudaSuccess) rc = APS_ERR_CUDA;
   if (rc != APS_OK) {
     delete p;
     return rc;
@@ -820,7 +821,7 @@ extern "C" int aps_gplan_filter(aps_gplan* p, int64_t q0, int64_t q1, double rat
   APS_CTX(c);
   if (q0 < 0 || q1 > p->F || q0 > q1) APS_FAIL(APS_ERR_ARGS, "", "query range out of bounds");
   return aps_k_global_filter(c->stream, p->knn_idx.p, p->knn_dist.p, p->k, q0, q1, p->img_of_row.p, p->d_off.p,
-                             (float)ratio, p->records.p, (uint32_t*)(p->records.p + p->F));
+                             (float)ratio, p->records.p);
 }
 
 extern "C" int aps_gplan_download_knn(aps_gplan* p, int64_t q0, int64_t q1, uint32_t* idx, float* dist) {
@@ -841,8 +842,7 @@ extern "C" int aps_gplan_compact(aps_gplan* p) {
   if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
   aps_ctx* c = p->c;
   APS_CTX(c);
-  APS_TRY(aps_k_global_compact(c->stream, p->records.p, (const uint32_t*)(p->records.p + p->F), p->img_of_row.p,
-                               p->d_off.p, p->n, p->F, p->dir_counts.p, p->pair_counts.p, p->pair_ptr.p, p->rank.p,
+  APS_TRY(aps_k_global_compact(c->stream, p->records.p, p->img_of_row.p, p->d_off.p, p->n, p->F, p->dir_counts.p, p->pair_counts.p, p->pair_ptr.p, p->rank.p,
                                p->rows.p));
   p->compacted = true;
   return APS_OK;
@@ -928,23 +928,28 @@ struct PairwiseSets {
   std::vector<int> big;  // per image: max|.| > 2
 };
 
-static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* desc, const int64_t* counts, int n,
-                            int D, int dtype, int layout, bool tensor) {
+// allocation of the pooled raw matrix + bookkeeping
+static int pairwise_alloc(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, int n, int D, int dtype) {
   ps.off.assign(n + 1, 0);
+  ps.big.assign(n, 0);
   for (int i = 0; i < n; ++i) ps.off[i + 1] = ps.off[i] + counts[i];
   const int64_t F = ps.off[n];
-  DevBuf<uint8_t> tmp;
-  const int esz = dtype == APS_F32 ? 4 : 1;
-  char* base = nullptr;
   if (dtype == APS_F32) {
     APS_TRY(floatset_alloc(c, ps.rawset, F, D));
-    base = (char*)ps.rawset.raw.p;
   } else {
     ps.nb16 = (D + 15) / 16 * 16;
     APS_TRY(ps.u8raw.alloc((size_t)F * D, c->stream));
     APS_TRY(ps.u8pad.alloc((size_t)F * ps.nb16, c->stream));
-    base = (char*)ps.u8raw.p;
   }
+  return APS_OK;
+}
+
+// H2D of the per-image matrices into the pooled row-major matrix (vertcat of the cell)
+static int pairwise_upload(aps_ctx* c, PairwiseSets& ps, const void* const* desc, const int64_t* counts, int n, int D,
+                           int dtype, int layout) {
+  const int64_t F = ps.off[n];
+  const int esz = dtype == APS_F32 ? 4 : 1;
+  char* base = dtype == APS_F32 ? (char*)ps.rawset.raw.p : (char*)ps.u8raw.p;
   DevBuf<uint8_t> stage;
   if (layout == APS_COL_MAJOR && F > 0) APS_TRY(stage.alloc((size_t)F * D * esz, c->stream));
   for (int i = 0; i < n; ++i) {
@@ -960,6 +965,13 @@ static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* des
       APS_TRY(aps_k_transpose_in(c->stream, st, counts[i], D, esz, dst));
     }
   }
+  return APS_OK;
+}
+
+// K1 of the pairwise path: per-image magnitude test (normalise iff max|.| > 2 is a per-PAIR decision,
+// matchFeaturesScratch.m:105-110), row norms, tensor operands of the raw and (when needed) the normalised view
+static int pairwise_finish(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, int n, int D, int dtype, bool tensor) {
+  const int64_t F = ps.off[n];
   if (dtype == APS_U8) {
     APS_TRY(pad_rows(c->stream, ps.u8raw.p, F, D, ps.nb16, ps.u8pad.p));
     return APS_OK;
@@ -980,21 +992,21 @@ static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* des
   APS_CUDA(cudaMemcpyAsync(hf.data(), imgflags.p, hf.size() * 4, cudaMemcpyDeviceToHost, c->stream));
   APS_CUDA(cudaStreamSynchronize(c->stream));
   ps.big.assign(n, 0);
-  bool any_big = false, all_exact = true, any_small = false;
+  bool any_big = false, all_exact = true;
   for (int i = 0; i < n; ++i) {
     if (counts[i] == 0) continue;
     float maxabs;
     memcpy(&maxabs, &hf[(size_t)i * 8 + 3], 4);
     ps.big[i] = maxabs > 2.0f;
     any_big |= ps.big[i] != 0;
-    any_small |= ps.big[i] == 0;
     all_exact &= hf[(size_t)i * 8] != 0;
   }
-  (void)any_small;
   // flag words shared by all images of a view (exactness must hold on both sides of every pair)
-  APS_TRY(floatset_reset_flags(c, ps.rawset));
   {
     int32_t fl[8] = {all_exact ? 1 : 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i)   // max over the images of the magnitude words (bit patterns of non-negative floats)
+      for (int w = 1; w < 4; ++w)
+        if (counts[i] > 0 && hf[(size_t)i * 8 + w] > fl[w]) fl[w] = hf[(size_t)i * 8 + w];
     APS_CUDA(cudaMemcpyAsync(ps.rawset.flags.p, fl, sizeof fl, cudaMemcpyHostToDevice, c->stream));
     APS_CUDA(cudaStreamSynchronize(c->stream));
   }
@@ -1015,6 +1027,13 @@ static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* des
     APS_TRY(floatset_prepare(c, ps.normset, APS_NORM_PAIRWISE, tensor, 0, /*sort*/ false));
   }
   return APS_OK;
+}
+
+static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* desc, const int64_t* counts, int n,
+                            int D, int dtype, int layout, bool tensor) {
+  APS_TRY(pairwise_alloc(c, ps, counts, n, D, dtype));
+  APS_TRY(pairwise_upload(c, ps, desc, counts, n, D, dtype, layout));
+  return pairwise_finish(c, ps, counts, n, D, dtype, tensor);
 }
 
 // one pair on the device: results into caller regions; count stays on the device
@@ -1271,7 +1290,18 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       tp.Fq_total = side.N; tp.Ft_total = side.N; tp.Dp = (D + 63) / 64 * 64;
       tp.q0 = 0; tp.q1 = 0; tp.t0 = 0; tp.t1 = 0; tp.nslot = 1; tp.kcand = KCP;
       tp.cand_idx = cidx.p; tp.cand_score = cscore.p; tp.dump = nullptr;
+      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+      if (c->timing) {
+        APS_CUDA(cudaEventCreate(&ev0));
+        APS_CUDA(cudaEventCreate(&ev1));
+        APS_CUDA(cudaEventRecord(ev0, s));
+      }
       APS_TRY(aps_k_knn_tc_units(s, c->sm_count, tp, d_units.p, (int64_t)units.size()));
+      if (c->timing) {
+        APS_CUDA(cudaEventRecord(ev1, s));
+        c->tc_events.push_back(ev0);
+        c->tc_events.push_back(ev1);
+      }
       aps_pair_tables ptr_ = pt;  // re-rank may skip rows the ratio / threshold test provably rejects
       ptr_.prune = 1;
       ptr_.prune_r2 = max_ratio * max_ratio;
@@ -1326,15 +1356,86 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   return APS_OK;
 }
 
-static int feature_matching_pairwise_impl(aps_ctx* c, const void* const* desc, const int64_t* counts, int n, int D,
-                                          int dtype, int layout, double match_threshold, double max_ratio,
-                                          int pair_first, int pair_stride, aps_matchlist** out) {
+// staged pairwise pipeline: descriptors resident on the device, prepared once, matched per rank share
+struct aps_pplan {
+  aps_ctx* c = nullptr;
+  int n = 0, D = 0, dtype = 0;
+  std::vector<int64_t> counts;
+  int64_t F = 0, maxc = 0;
+  bool tensor = false, prepared = false;
+  PairwiseSets ps;
+};
+
+extern "C" int aps_pplan_create(aps_ctx* c, const int64_t* counts, int n, int D, int dtype, aps_pplan** out) {
   APS_CTX(c);
-  if (!out) APS_FAIL(APS_ERR_ARGS, "", "out is NULL");
+  if (!out || n < 0 || (n > 0 && !counts)) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
   *out = nullptr;
-  if (n < 0 || (n > 0 && !counts) || pair_stride < 1 || pair_first < 0 || pair_first >= pair_stride)
-    APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
   if (dtype != APS_F32 && dtype != APS_U8) APS_FAIL(APS_ERR_TYPE, "", "descriptors must be single or uint8");
+  aps_pplan* p = new (std::nothrow) aps_pplan();
+  if (!p) APS_FAIL(APS_ERR_ALLOC, "", "out of host memory");
+  p->c = c;
+  p->n = n;
+  p->D = D;
+  p->dtype = dtype;
+  p->counts.assign(counts, counts + n);
+  for (int i = 0; i < n; ++i) {
+    if (counts[i] < 0) {
+      delete p;
+      APS_FAIL(APS_ERR_ARGS, "", "negative feature count");
+    }
+    p->F += counts[i];
+    if (counts[i] > p->maxc) p->maxc = counts[i];
+  }
+  if (p->F > 0 && D <= 0) {
+    delete p;
+    APS_FAIL(APS_ERR_DIM, "", "descriptor dimension must be positive");
+  }
+  if (p->F >= ((int64_t)1 << 31) - 512) {
+    delete p;
+    APS_FAIL(APS_ERR_ARGS, "", "more than 2^31 descriptors are not supported");
+  }
+  p->tensor = dtype == APS_F32 && tc_wanted(c, D, p->maxc, p->maxc * (int64_t)n, 2);
+  int rc = pairwise_alloc(c, p->ps, p->counts.data(), n, D, dtype);
+  if (rc != APS_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return APS_OK;
+}
+extern "C" void aps_pplan_destroy(aps_pplan* p) {
+  if (!p) return;
+  cudaSetDevice(p->c->device);
+  delete p;
+}
+extern "C" int64_t aps_pplan_total(const aps_pplan* p) { return p ? p->F : 0; }
+extern "C" void* aps_pplan_desc_device(aps_pplan* p) {
+  if (!p) return nullptr;
+  return p->dtype == APS_F32 ? (void*)p->ps.rawset.raw.p : (void*)p->ps.u8raw.p;
+}
+extern "C" int aps_pplan_upload(aps_pplan* p, const void* const* desc, int layout) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  APS_CTX(p->c);
+  p->prepared = false;
+  return pairwise_upload(p->c, p->ps, desc, p->counts.data(), p->n, p->D, p->dtype, layout);
+}
+extern "C" int aps_pplan_prepare(aps_pplan* p) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  APS_CTX(p->c);
+  APS_TRY(pairwise_finish(p->c, p->ps, p->counts.data(), p->n, p->D, p->dtype, p->tensor));
+  p->prepared = true;
+  return APS_OK;
+}
+
+extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_ratio, int pair_first, int pair_stride,
+                               aps_matchlist** out) {
+  if (!p || !out) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  *out = nullptr;
+  if (pair_stride < 1 || pair_first < 0 || pair_first >= pair_stride) APS_FAIL(APS_ERR_ARGS, "", "bad pair share");
+  const int n = p->n, D = p->D, dtype = p->dtype;
+  const int64_t* counts = p->counts.data();
   c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
   aps_matchlist* m = new (std::nothrow) aps_matchlist();
   if (!m) APS_FAIL(APS_ERR_ALLOC, "", "out of host memory");
@@ -1342,24 +1443,18 @@ static int feature_matching_pairwise_impl(aps_ctx* c, const void* const* desc, c
   m->has_metric = true;
   const size_t cells = (size_t)n * n;
   m->pair_ptr.assign(cells + 1, 0);
-  int64_t F = 0, maxc = 0;
-  for (int i = 0; i < n; ++i) {
-    F += counts[i];
-    if (counts[i] > maxc) maxc = counts[i];
-  }
-  if (F == 0 || n < 2) {
+  if (p->F == 0 || n < 2) {
     *out = m;
     return APS_OK;
   }
-  if (F >= ((int64_t)1 << 31) - 512) {
+  if (!p->prepared) {
     delete m;
-    APS_FAIL(APS_ERR_ARGS, "", "more than 2^31 descriptors are not supported");
+    APS_FAIL(APS_ERR_ARGS, "", "aps_pplan_prepare() has not run since the last upload");
   }
   int rc = APS_OK;
   {
-    const bool tensor = dtype == APS_F32 && tc_wanted(c, D, maxc, maxc * (int64_t)n, 2);
-    PairwiseSets ps;
-    rc = pairwise_prepare(c, ps, desc, counts, n, D, dtype, layout, tensor);
+    const bool tensor = p->tensor;
+    PairwiseSets& ps = p->ps;
     // pair list in column-major cell order (featureMatchingPairwise.m:48): j outer, i < j inner; this rank's
     // share = every pair_stride-th pair (the reference's parfor distributes the same list over workers)
     std::vector<PairRef> all, mine_raw, mine_norm;
@@ -1413,6 +1508,26 @@ static int feature_matching_pairwise_impl(aps_ctx* c, const void* const* desc, c
   }
   *out = m;
   return APS_OK;
+}
+
+static int feature_matching_pairwise_impl(aps_ctx* c, const void* const* desc, const int64_t* counts, int n, int D,
+                                          int dtype, int layout, double match_threshold, double max_ratio,
+                                          int pair_first, int pair_stride, aps_matchlist** out) {
+  APS_CTX(c);
+  if (!out) APS_FAIL(APS_ERR_ARGS, "", "out is NULL");
+  *out = nullptr;
+  if (n < 0 || (n > 0 && !counts) || pair_stride < 1 || pair_first < 0 || pair_first >= pair_stride)
+    APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  aps_pplan* p = nullptr;
+  APS_TRY(aps_pplan_create(c, counts, n, D, dtype, &p));
+  int rc = APS_OK;
+  if (p->F > 0 && n >= 2) {
+    rc = aps_pplan_upload(p, desc, layout);
+    if (rc == APS_OK) rc = aps_pplan_prepare(p);  // an error here must not reach the pair classification (ps.big)
+  }
+  if (rc == APS_OK) rc = aps_pplan_match(p, match_threshold, max_ratio, pair_first, pair_stride, out);
+  aps_pplan_destroy(p);
+  return rc;
 }
 
 extern "C" int aps_feature_matching_pairwise(aps_ctx* c, const void* const* desc, const int64_t* counts, int n,

@@ -16,8 +16,7 @@
 // K5a  featureMatchingGlobal.m:123-147.  idx/dist row-major [.. x k], rows indexed from q0.
 __global__ void k_global_filter(const uint32_t* __restrict__ idx, const float* __restrict__ dist, int k, int64_t q0,
                                 int64_t q1, const int32_t* __restrict__ img_of_row,
-                                const int64_t* __restrict__ img_off, float ratio_thr, int32_t* __restrict__ target,
-                                uint32_t* __restrict__ partner) {
+                                const int64_t* __restrict__ img_off, float ratio_thr, int2* __restrict__ records) {
   int64_t q = q0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= q1) return;
   const int32_t qi = img_of_row[q];
@@ -50,16 +49,14 @@ __global__ void k_global_filter(const uint32_t* __restrict__ idx, const float* _
       p = (uint32_t)((int64_t)(s0 - 1) - img_off[ti] + 1);
     }
   }
-  target[q] = t;
-  partner[q] = p;
+  records[q] = make_int2(t, (int32_t)p);  // one 8-byte record per query: (target image + 1 | 0, partner's local index)
 }
 
 int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, int k, int64_t q0, int64_t q1,
-                        const int32_t* img_of_row, const int64_t* img_off, float ratio_thr, int32_t* target,
-                        uint32_t* partner) {
+                        const int32_t* img_of_row, const int64_t* img_off, float ratio_thr, int2* records) {
   if (q1 <= q0) return APS_OK;
   k_global_filter<<<(unsigned)aps_ceil_div(q1 - q0, 256), 256, 0, s>>>(idx, dist, k, q0, q1, img_of_row, img_off,
-                                                                      ratio_thr, target, partner);
+                                                                      ratio_thr, records);
   APS_LAUNCHED();
   return APS_OK;
 }
@@ -68,7 +65,7 @@ int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, 
 // K5b  compaction.  Cell (a,b), a<b, holds first the accepted queries of image a (ascending local
 // index) then those of image b -- i.e. ascending GLOBAL query order.  One warp walks one image's
 // queries in order and hands out, per target image, consecutive ranks (warp match + popc).
-__global__ void k_rank_per_image(const int32_t* __restrict__ target, const int64_t* __restrict__ img_off, int n,
+__global__ void k_rank_per_image(const int2* __restrict__ records, const int64_t* __restrict__ img_off, int n,
                                  int64_t* __restrict__ dir_counts, int64_t* __restrict__ rank) {
   extern __shared__ int cnt[];  // [n]
   const int i = blockIdx.x, lane = threadIdx.x;
@@ -77,7 +74,7 @@ __global__ void k_rank_per_image(const int32_t* __restrict__ target, const int64
   const int64_t b = img_off[i], e = img_off[i + 1];
   for (int64_t base = b; base < e; base += 32) {
     const int64_t q = base + lane;
-    const int t = (q < e) ? target[q] : 0;
+    const int t = (q < e) ? records[q].x : 0;
     const bool active = t > 0;
     const unsigned amask = __ballot_sync(0xffffffffu, active);
     int myrank = 0, cbase = 0;
@@ -100,7 +97,7 @@ __global__ void k_rank_per_image(const int32_t* __restrict__ target, const int64
 // Same result with 8 warps per image (n <= 1024 targets): pass 1 counts per (warp sub-range, target), a
 // prefix over the sub-ranges gives every warp its starting rank, pass 2 hands the ranks out.
 constexpr int RPI_WARPS = 8;
-__global__ void __launch_bounds__(32 * RPI_WARPS) k_rank_per_image_mw(const int32_t* __restrict__ target,
+__global__ void __launch_bounds__(32 * RPI_WARPS) k_rank_per_image_mw(const int2* __restrict__ records,
                                                                        const int64_t* __restrict__ img_off, int n,
                                                                        int64_t* __restrict__ dir_counts,
                                                                        int64_t* __restrict__ rank) {
@@ -115,7 +112,7 @@ __global__ void __launch_bounds__(32 * RPI_WARPS) k_rank_per_image_mw(const int3
   for (int pass = 0; pass < 2; ++pass) {
     for (int64_t base = wb; base < we; base += 32) {
       const int64_t q = base + lane;
-      const int t = (q < we) ? target[q] : 0;
+      const int t = (q < we) ? records[q].x : 0;
       const bool active = t > 0;
       const unsigned amask = __ballot_sync(0xffffffffu, active);
       int myrank = 0, cbase = 0;
@@ -182,17 +179,18 @@ __global__ void k_pair_counts_scan(const int64_t* __restrict__ dir_counts, int n
   }
 }
 
-__global__ void k_scatter_rows(const int32_t* __restrict__ target, const uint32_t* __restrict__ partner,
+__global__ void k_scatter_rows(const int2* __restrict__ records,
                                const int32_t* __restrict__ img_of_row, const int64_t* __restrict__ img_off, int n,
                                int64_t F, const int64_t* __restrict__ dir_counts,
                                const int64_t* __restrict__ pair_ptr, const int64_t* __restrict__ rank,
                                uint32_t* __restrict__ rows) {
   int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= F) return;
-  const int t1 = target[q];
+  const int2 rec = records[q];
+  const int t1 = rec.x;
   if (t1 <= 0) return;
   const int i = img_of_row[q], t = t1 - 1;
-  const uint32_t li = (uint32_t)(q - img_off[i] + 1), lj = partner[q];
+  const uint32_t li = (uint32_t)(q - img_off[i] + 1), lj = (uint32_t)rec.y;
   const int a = min(i, t), b = max(i, t);
   int64_t pos = pair_ptr[a + (int64_t)b * n] + rank[q];
   if (i > t) pos += dir_counts[(int64_t)a * n + b];  // the lower image's queries come first
@@ -217,19 +215,19 @@ int aps_k_fill_img_of_row(cudaStream_t s, const int64_t* img_off, int n, int64_t
   return APS_OK;
 }
 
-int aps_k_global_compact(cudaStream_t s, const int32_t* target, const uint32_t* partner,
+int aps_k_global_compact(cudaStream_t s, const int2* records,
                           const int32_t* img_of_row, const int64_t* img_off, int n, int64_t F, int64_t* dir_counts,
                           int64_t* pair_counts, int64_t* pair_ptr, int64_t* rank, uint32_t* rows) {
   if (n == 0) return APS_OK;
   if (n <= 1024)
-    k_rank_per_image_mw<<<n, 32 * RPI_WARPS, (size_t)RPI_WARPS * n * sizeof(int), s>>>(target, img_off, n, dir_counts, rank);
+    k_rank_per_image_mw<<<n, 32 * RPI_WARPS, (size_t)RPI_WARPS * n * sizeof(int), s>>>(records, img_off, n, dir_counts, rank);
   else
-    k_rank_per_image<<<n, 32, (size_t)n * sizeof(int), s>>>(target, img_off, n, dir_counts, rank);
+    k_rank_per_image<<<n, 32, (size_t)n * sizeof(int), s>>>(records, img_off, n, dir_counts, rank);
   APS_LAUNCHED();
   k_pair_counts_scan<<<1, 1024, 0, s>>>(dir_counts, n, pair_counts, pair_ptr);
   APS_LAUNCHED();
   if (F > 0) {
-    k_scatter_rows<<<(unsigned)aps_ceil_div(F, 256), 256, 0, s>>>(target, partner, img_of_row, img_off, n, F,
+    k_scatter_rows<<<(unsigned)aps_ceil_div(F, 256), 256, 0, s>>>(records, img_of_row, img_off, n, F,
                                                                  dir_counts, pair_ptr, rank, rows);
     APS_LAUNCHED();
   }

@@ -169,27 +169,52 @@ def featureMatchingGlobal(input, allDescriptors, numImg, ctx=None):
     return matches
 
 
-def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metric=False, shard=None):
+class ApsSemanticsWarning(UserWarning):
+    """The call was served with semantics that differ from what the reference's defaults select."""
+
+
+def _warn_semantics(input, method):
+    """PP/inputs.m:47-49 defaults: useMATLABFeatureMatch=1 (MathWorks matchFeatures, closed source),
+    Matchingmethod='Approximate', ApproxFloatNNMethod='subsetpdist2'.  Nothing here may change results silently."""
+    import warnings
+
+    if int(_field(input, "apsAcceptScratchSemantics", 0)):
+        return
+    if int(_field(input, "useMATLABFeatureMatch", 0)) == 1:
+        warnings.warn("input.useMATLABFeatureMatch=1 selects MathWorks matchFeatures in the reference (closed source); "
+                      "this GPU path runs the matchFeaturesScratch semantics (featureMatchingPairwise.m:108-117). "
+                      "Set input.apsAcceptScratchSemantics=1 to acknowledge.", ApsSemanticsWarning, stacklevel=3)
+    if method == "approximate":
+        warnings.warn("Matchingmethod='Approximate': float descriptors are matched by the EXACT search (a superset in "
+                      "quality of the reference's subset / KD-tree / PCA searches, matchFeaturesScratch.m:128-163); "
+                      "binary descriptors run the exhaustive search exactly as the reference does (:611). "
+                      "Set input.apsAcceptScratchSemantics=1 to acknowledge.", ApsSemanticsWarning, stacklevel=3)
+
+
+def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metric=False, shard=None, csr=False):
     """matches = featureMatchingPairwise(input, allDescriptors, numImg)  (featureMatchingPairwise.m:1-63)
 
-    Runs getMatches' matchFeaturesScratch branch (:108-117) with Method 'Exhaustive' and Unique=true
-    for every i<j.  The MathWorks matchFeatures branch (input.useMATLABFeatureMatch=1) is closed
-    source and the approximate modes are out of scope: both raise.
+    Runs getMatches' matchFeaturesScratch branch (:108-117) with Unique=true for every i<j.
+    input.useMATLABFeatureMatch=1 (the reference default, PP/inputs.m:47) selects MathWorks' closed-source
+    matchFeatures there; here it is served by the matchFeaturesScratch semantics and an ApsSemanticsWarning
+    says so (silence it with input.apsAcceptScratchSemantics=1).  Matchingmethod='Approximate' is served by
+    the exact search, with the same warning.
     shard=(first, stride): compute only every stride-th pair of the column-major pair list (one share
-    per GPU rank); cells of other shares come back empty and are merged by `merge_pairwise_shards`."""
+    per GPU rank); cells of other shares come back empty and are merged by `merge_pairwise_shards`.
+    csr=True returns the compacted lists as they leave the C ABI: (pair_ptr [n*n+1], rows [M x 2] uint32, metric [M])."""
     ctx = ctx or default_context()
     if not (np.isscalar(numImg) and np.isfinite(numImg) and numImg > 0):
         raise ValueError("numImg must be a positive finite scalar")
     method = str(_field(input, "Matchingmethod", "Exhaustive")).lower()
     if method not in ("exhaustive", "approximate"):
         raise ValueError(f"Unknown Method: {method}")  # matchFeaturesScratch.m:164-165
-    # 'Approximate' (the reference's inputs.m default): binary descriptors already run the exhaustive OMP MEX
-    # there (matchFeaturesScratch.m:611, the "LSH" is a stub); for float descriptors the PCA / KD-tree /
-    # random-subset searches (:128-163) approximate exactly what the exhaustive engine returns, so it serves both.
+    _warn_semantics(input, method)
     thr = float(_field(input, "Matchingthreshold", required=True))
     ratio = float(_field(input, "Ratiothreshold", required=True))
     n, first, mats, counts, D, is_binary = _describe(allDescriptors, numImg)
     if first is None:
+        if csr:
+            return np.zeros(n * n + 1, np.int64), np.zeros((0, 2), np.uint32), np.zeros(0)
         m = [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]
         return (m, [[None] * n for _ in range(n)]) if return_metric else m
     ptrs, cnt, layout, keep = _desc_args(mats, counts)
@@ -198,17 +223,39 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
     check(lib().aps_feature_matching_pairwise_shard(ctx.handle, ptrs, cnt, n, int(D), APS_U8 if is_binary else APS_F32,
                                                     layout, thr, ratio, int(first), int(stride), C.byref(h)))
     try:
+        if csr:
+            return _csr_from_matchlist(h, n)
         matches, metrics, _, _ = _cells_from_matchlist(h, n, want_metric=True)
     finally:
         lib().aps_matchlist_free(h)
-    # featureMatchingPairwise fills EVERY upper-triangle cell (possibly 0 x 2), :62
+    _fill_upper_cells(matches, n)
+    return (matches, metrics) if return_metric else matches
+
+
+def _fill_upper_cells(matches, n):
+    """featureMatchingPairwise fills EVERY upper-triangle cell (possibly 0 x 2), featureMatchingPairwise.m:62."""
     empty = np.zeros((0, 2))
     for j in range(n):
-        col = [matches[i][j] for i in range(j)]
-        for i, m in enumerate(col):
-            if m.size == 0:
+        for i in range(j):
+            if matches[i][j].size == 0:
                 matches[i][j] = empty
-    return (matches, metrics) if return_metric else matches
+
+
+def merge_pairwise_csr(n, counts, rows_all, metric_all=None):
+    """Merges the exchanged per-rank CSR lists (multigpu.exchange_pairwise_lists): pair o of the column-major pair
+    list was computed by rank o % world; its rows sit in that rank's buffer at the offset its own counts imply."""
+    world = counts.shape[0]
+    offs = np.concatenate([np.zeros((world, 1), np.int64), np.cumsum(counts, axis=1)], axis=1)
+    out = [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]
+    rows_f = rows_all.astype(np.float64)
+    o = 0
+    for j in range(n):
+        for i in range(j):
+            r, c = o % world, i + j * n
+            out[i][j] = rows_f[r, offs[r, c]:offs[r, c + 1]]
+            o += 1
+    _fill_upper_cells(out, n)
+    return out
 
 
 def merge_pairwise_shards(shards):
@@ -506,6 +553,66 @@ def imageMatching(input, n, keypoints, matchesAll, imagesProcessed=None, samples
     return allMatches, numMatches, tforms
 
 
+RECORD_PAD = 16384  # APS_RECORD_PAD of include/apsmatch.h: rows the record buffer holds beyond F
+
+
+def _csr_from_matchlist(h, n):
+    L = lib()
+    total = L.aps_matchlist_total(h)
+    pp = np.ctypeslib.as_array(L.aps_matchlist_pair_ptr(h), shape=(n * n + 1,)).copy()
+    rows = (np.ctypeslib.as_array(L.aps_matchlist_rows(h), shape=(total, 2)).copy() if total
+            else np.zeros((0, 2), np.uint32))
+    mp = L.aps_matchlist_metric(h)
+    met = np.ctypeslib.as_array(mp, shape=(total,)).copy() if (total and mp) else np.zeros(0)
+    return pp, rows, met
+
+
+class PairwisePlan:
+    """Staged pairwise pipeline (aps_pplan_*): descriptors resident on the device, K1 once, then this rank's share of
+    the image-pair list -- what PP/featureMatching/featureMatchingPairwise.m:48-59 does with a parfor over the pairs
+    after broadcasting the descriptor cell to the workers."""
+
+    def __init__(self, ctx, counts, D, is_binary):
+        self.ctx, self.n, self.D = ctx, len(counts), int(D)
+        h = C.c_void_p()
+        cnt = (C.c_int64 * max(self.n, 1))(*[int(c) for c in counts])
+        check(lib().aps_pplan_create(ctx.handle, cnt, self.n, self.D, APS_U8 if is_binary else APS_F32, C.byref(h)))
+        self._h = h
+        self.F = int(lib().aps_pplan_total(h))
+
+    def upload(self, mats):
+        ptrs, _, layout, keep = _desc_args(list(mats), [0 if m is None else m.shape[0] for m in mats])
+        check(lib().aps_pplan_upload(self._h, ptrs, layout))
+        self._keep = keep
+
+    def desc_device(self):
+        return lib().aps_pplan_desc_device(self._h)
+
+    def prepare(self):
+        """K1 of the pairwise path: magnitude test per image (matchFeaturesScratch.m:105-110), norms, tensor operands."""
+        check(lib().aps_pplan_prepare(self._h))
+
+    def match(self, match_threshold, max_ratio, first=0, stride=1):
+        """This rank's share of the pair list -> CSR (pair_ptr [n*n+1], rows [M x 2] uint32, metric [M])."""
+        h = C.c_void_p()
+        check(lib().aps_pplan_match(self._h, float(match_threshold), float(max_ratio), int(first), int(stride), C.byref(h)))
+        try:
+            return _csr_from_matchlist(h, self.n)
+        finally:
+            lib().aps_matchlist_free(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().aps_pplan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class GlobalPlan:
     """Staged global pipeline (aps_gplan_*): the building block bench.py and the multi-GPU host use.
 
@@ -540,7 +647,7 @@ class GlobalPlan:
         return lib().aps_gplan_desc_device(self._h)
 
     def records_device(self):
-        """Device pointer of the per-query records: target[F] int32 then partner[F] uint32 (the accept / match of :140-152)."""
+        """Device pointer of the per-query records: [F + RECORD_PAD] x (int32 target image, uint32 partner) (the accept / match of :140-152)."""
         return lib().aps_gplan_records_device(self._h)
 
     def knn_device(self):

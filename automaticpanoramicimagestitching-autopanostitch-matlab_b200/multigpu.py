@@ -7,7 +7,7 @@ broadcast to the workers (PP/featureMatching/featureMatchingPairwise.m:54-59, PP
     cross-GPU top-k merge exists;
   * query rows are sharded in contiguous blocks of 128-row tiles (`shard_bounds`);
   * the only exchange on the data path is the per-query match records (8 bytes per query row:
-    int32 target image + uint32 partner index), each rank broadcasting its slice (`exchange_records`);
+    int32 target image + uint32 partner index): one in-place all-gather of equal slices (`exchange_records`);
   * compaction into the cell order is deterministic, so the lists are identical for every world size.
 Pure index arithmetic + collectives: testable on CPU with the gloo backend (tests/test_multigpu_cpu.py).
 """
@@ -16,23 +16,29 @@ from __future__ import annotations
 TILE_ROWS = 128
 
 
-def shard_bounds(F: int, world: int):
-    """[(q0, q1)] per rank: contiguous, disjoint, covering [0, F), aligned to 128-row tiles."""
+def shard_rows(F: int, world: int) -> int:
+    """Rows per rank: the SAME for every rank (a multiple of 128-row tiles), so that one in-place all-gather moves
+    every rank's slice; the last ranks' slices may be shorter or empty once clipped to F."""
     blocks = (F + TILE_ROWS - 1) // TILE_ROWS
-    out = []
-    for r in range(world):
-        b0, b1 = r * blocks // world, (r + 1) * blocks // world
-        out.append((min(F, b0 * TILE_ROWS), min(F, b1 * TILE_ROWS)))
-    return out
+    return ((blocks + world - 1) // world) * TILE_ROWS
 
 
-def exchange_records(rec, F: int, bounds, dist, group=None):
-    """rec: 1-D int32 tensor of 2*F entries (target[F] then partner[F], the layout of
-    aps_gplan_records_device).  After the call every rank holds every rank's slice."""
-    for r, (a, b) in enumerate(bounds):
-        if b > a:
-            dist.broadcast(rec[a:b], src=r, group=group)
-            dist.broadcast(rec[F + a:F + b], src=r, group=group)
+def shard_bounds(F: int, world: int):
+    """[(q0, q1)] per rank: contiguous, disjoint, covering [0, F), aligned to 128-row tiles, equal stride."""
+    S = shard_rows(F, world)
+    return [(min(F, r * S), min(F, (r + 1) * S)) for r in range(world)]
+
+
+def exchange_records(rec, F: int, world: int, rank: int, dist, group=None):
+    """rec: [F + pad, 2] int32 tensor over aps_gplan_records_device (one (target, partner) pair per query row,
+    pad >= world * 128).  ONE in-place all-gather of equal slices: after the call every rank holds every rank's
+    records (the only exchange on the data path)."""
+    S = shard_rows(F, world)
+    if world == 1 or S == 0:
+        return rec
+    if world * S > rec.shape[0]:
+        raise ValueError("record buffer too small for equal-sized rank slices")
+    dist.all_gather_into_tensor(rec[: world * S], rec[rank * S:(rank + 1) * S], group=group)
     return rec
 
 
@@ -87,18 +93,48 @@ def global_matching_step(plan, ratio, rank, world, dist=None, rec=None):
     plan.knn(q0, q1)
     plan.filter(ratio, q0, q1)
     if world > 1:
-        exchange_records(rec, plan.F, bounds, dist)
+        exchange_records(rec, plan.F, world, rank, dist)
     plan.compact()
 
 
-def pairwise_matching_sharded(host, input, allDescriptors, numImg, rank, world, dist=None, ctx=None):
+def pairwise_matching_sharded(host, input, allDescriptors, numImg, rank, world, dist=None, ctx=None, torch=None,
+                              device=None):
     """featureMatchingPairwise across `world` ranks: rank r computes every world-th image pair of the
     column-major pair list (block-cyclic, like the reference's parfor over the same list,
-    featureMatchingPairwise.m:48-59), the per-pair lists are exchanged and every rank returns the merged cell.
-    `host` is the package's host module (featureMatchingPairwise / merge_pairwise_shards)."""
-    mine = host.featureMatchingPairwise(input, allDescriptors, numImg, ctx=ctx, shard=(rank, world))
+    featureMatchingPairwise.m:48-59); the compacted per-rank lists are exchanged counts first, then rows and
+    metrics (all-gather of per-pair counts, then of the [M x 2] lists at the offsets the counts imply),
+    and every rank returns the merged cell.  `host` is the package's host module; `device` is where the exchange
+    buffers live ("cuda" for NCCL, "cpu" for gloo)."""
     if world == 1:
-        return mine
-    shards = [None] * world
-    dist.all_gather_object(shards, mine)  # match lists are small next to the descriptors (8-16 B per match)
-    return host.merge_pairwise_shards(shards)
+        return host.featureMatchingPairwise(input, allDescriptors, numImg, ctx=ctx, shard=(rank, world))
+    if torch is None:
+        import torch
+    n = int(numImg)
+    pp, rows, metric = host.featureMatchingPairwise(input, allDescriptors, numImg, ctx=ctx, shard=(rank, world), csr=True)
+    dev = device or ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    counts, rows_all, met_all = exchange_pairwise_lists(pp, rows, metric, world, dist, torch, dev)
+    return host.merge_pairwise_csr(n, counts, rows_all, met_all)
+
+
+def exchange_pairwise_lists(pair_ptr, rows, metric, world, dist, torch, device, group=None):
+    """Counts-then-lists exchange of one rank's compacted match lists.  pair_ptr [n*n + 1] int64, rows [M x 2] uint32,
+    metric [M] float64 (host arrays).  Returns (counts [world x n*n] int64, rows [world x Mmax x 2] uint32,
+    metric [world x Mmax] float64) as numpy arrays, identical on every rank."""
+    import numpy as np
+
+    cells = pair_ptr.size - 1
+    cnt = torch.from_numpy(np.diff(pair_ptr).astype(np.int64)).to(device)
+    counts = torch.empty((world, cells), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts.view(-1), cnt, group=group)
+    m_max = int(counts.sum(dim=1).max().item())
+    M = rows.shape[0]
+    r_loc = torch.zeros((max(m_max, 1), 2), dtype=torch.int32, device=device)
+    m_loc = torch.zeros((max(m_max, 1),), dtype=torch.float64, device=device)
+    if M:
+        r_loc[:M] = torch.from_numpy(np.ascontiguousarray(rows).view(np.int32)).to(device)
+        m_loc[:M] = torch.from_numpy(np.ascontiguousarray(metric)).to(device)
+    r_all = torch.empty((world,) + tuple(r_loc.shape), dtype=torch.int32, device=device)
+    m_all = torch.empty((world,) + tuple(m_loc.shape), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(r_all.view(-1), r_loc.view(-1), group=group)
+    dist.all_gather_into_tensor(m_all.view(-1), m_loc.view(-1), group=group)
+    return counts.cpu().numpy(), r_all.cpu().numpy().view(np.uint32), m_all.cpu().numpy()

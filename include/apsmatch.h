@@ -227,9 +227,11 @@ int aps_gplan_upload(aps_gplan* p, const void* const* desc, int layout); /* H2D 
 int aps_gplan_prepare(aps_gplan* p);                                     /* K1: A1 :80-97 */
 int aps_gplan_knn(aps_gplan* p, int64_t q0, int64_t q1);                 /* K2/K3/K4: A2 */
 int aps_gplan_filter(aps_gplan* p, int64_t q0, int64_t q1, double ratio); /* K5a: A3 :123-147 */
-/* Per-query records written by filter(): int32 target_img[F] (1-based, 0 = rejected) followed by
- * uint32 partner[F]; contiguous, 8*F bytes.  Rows outside [q0,q1) are left untouched, so ranks
- * can all-gather their slices in place. */
+/* Per-query records written by filter(): [F + APS_RECORD_PAD] interleaved pairs (int32 target image, 1-based,
+ * 0 = rejected ; uint32 partner = the match's local index in that image), 8 bytes per query row.  Rows outside
+ * [q0,q1) are left untouched, so ranks exchange their slices with ONE in-place all-gather; the padding lets
+ * equal-sized rank slices (multiples of 128 rows) run past F. */
+#define APS_RECORD_PAD 16384
 void* aps_gplan_records_device(aps_gplan* p);
 void* aps_gplan_knn_idx_device(aps_gplan* p);  /* uint32 [F][k] row-major, 1-based */
 void* aps_gplan_knn_dist_device(aps_gplan* p); /* float  [F][k] row-major */
@@ -238,6 +240,22 @@ int aps_gplan_download_knn(aps_gplan* p, int64_t q0, int64_t q1, uint32_t* idx, 
 int aps_gplan_compact(aps_gplan* p);                         /* K5b: A3 :149-159 on all F records */
 int aps_gplan_download(aps_gplan* p, aps_matchlist** out);   /* D2H of the CSR lists (synchronises) */
 int aps_gplan_pair_counts_device(aps_gplan* p, void** counts_i64); /* n*n int64, column-major, after compact() */
+
+/* ---- staged pairwise pipeline (multi-GPU building block of featureMatchingPairwise; bench.py times these) ----
+ * The reference broadcasts the descriptor cell to its parfor workers once and runs getMatches per pair
+ * (PP/featureMatching/featureMatchingPairwise.m:48-59).  Here: descriptors uploaded (or written by a device producer /
+ * an NCCL all-gather into aps_pplan_desc_device) once, K1 once (prepare), then match() computes this rank's share of
+ * the column-major pair list -- pairs whose ordinal is congruent to pair_first modulo pair_stride -- with the
+ * matchFeaturesScratch 'Exhaustive' semantics (:108-117, Unique = true). */
+typedef struct aps_pplan aps_pplan;
+int aps_pplan_create(aps_ctx* ctx, const int64_t* counts, int n, int D, int dtype, aps_pplan** out);
+void aps_pplan_destroy(aps_pplan* p);
+int64_t aps_pplan_total(const aps_pplan* p);
+void* aps_pplan_desc_device(aps_pplan* p);   /* pooled ROW-major raw descriptors [F x D] */
+int aps_pplan_upload(aps_pplan* p, const void* const* desc, int layout);
+int aps_pplan_prepare(aps_pplan* p);
+int aps_pplan_match(aps_pplan* p, double match_threshold, double max_ratio, int pair_first, int pair_stride,
+                    aps_matchlist** out);
 
 /* ---- diagnostics (tests only): raw output of the tcgen05 candidate kernel -----------------------
  * Q [nq x D], T [nt x D] ROW-major float (used as given, no normalisation).  scores [nq x nt]

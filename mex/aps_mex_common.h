@@ -27,40 +27,58 @@ static inline aps_ctx* aps_mex_ctx(void) {
   }
   return g_aps_ctx;
 }
-// allDescriptors{i}: numeric matrix, or a binaryFeatures object (its .Features, featureMatchingGlobal.m:56-75)
-static inline const mxArray* aps_mex_features(const mxArray* cell_elem) {
+// allDescriptors{i}: numeric matrix, or a binaryFeatures object (its .Features, featureMatchingGlobal.m:56-75).
+// *is_binary: the element is a binaryFeatures OBJECT -- the reference decides "binary" by class alone (:56); a plain
+// uint8 matrix is cast to single, L2-normalised and searched with float L2 there (:76-84).
+static inline const mxArray* aps_mex_features(const mxArray* cell_elem, bool* is_binary = nullptr) {
+  if (is_binary) *is_binary = false;
   if (!cell_elem) return nullptr;
-  if (mxIsClass(cell_elem, "binaryFeatures")) return mxGetProperty(cell_elem, 0, "Features");
+  if (mxIsClass(cell_elem, "binaryFeatures")) {
+    if (is_binary) *is_binary = true;
+    return mxGetProperty(cell_elem, 0, "Features");
+  }
   return cell_elem;
 }
+template <class T>
+static inline const void* aps_mex_to_single(const mxArray* f, std::vector<std::vector<float>>& converted) {
+  const T* s = (const T*)mxGetData(f);
+  converted.emplace_back(s, s + mxGetNumberOfElements(f));  // single(allDesc), featureMatchingGlobal.m:81
+  return converted.back().data();
+}
 // Collects the cell array into pointer / count vectors; returns dtype (APS_F32 / APS_U8) and D.
+// Binary (APS_U8, Hamming) iff the first non-empty element is a binaryFeatures object (featureMatchingGlobal.m:56);
+// every other numeric class -- plain uint8 included -- is converted to single (:76-81).
 static inline void aps_mex_collect(const mxArray* cellArr, int n, std::vector<const void*>& ptrs,
                                    std::vector<int64_t>& counts, int& dtype, int& D,
                                    std::vector<std::vector<float>>& converted) {
   ptrs.assign(n, nullptr);
   counts.assign(n, 0);
+  converted.reserve((size_t)n);  // pointers into `converted` must stay valid
   dtype = -1;
   D = 0;
   for (int i = 0; i < n; ++i) {
-    const mxArray* f = (mwSize)i < mxGetNumberOfElements(cellArr) ? aps_mex_features(mxGetCell(cellArr, i)) : nullptr;
+    bool isbin = false;
+    const mxArray* f = (mwSize)i < mxGetNumberOfElements(cellArr) ? aps_mex_features(mxGetCell(cellArr, i), &isbin) : nullptr;
     if (!f || mxIsEmpty(f)) continue;
     if (mxGetNumberOfDimensions(f) != 2 || mxIsComplex(f))
       mexErrMsgIdAndTxt("flann_knn:type", "descriptors must be real 2D matrices");
-    int dt;
-    if (mxIsUint8(f)) dt = APS_U8;
-    else if (mxIsSingle(f) || mxIsDouble(f)) dt = APS_F32;
-    else mexErrMsgIdAndTxt("flann_knn:type", "Descriptors must be single (float) or uint8 (binary)");
+    if (isbin && !mxIsUint8(f)) mexErrMsgIdAndTxt("flann_knn:type", "binaryFeatures.Features must be uint8");
+    if (!isbin && !mxIsNumeric(f) && !mxIsLogical(f))
+      mexErrMsgIdAndTxt("flann_knn:type", "Descriptors must be single (float) or uint8 (binary)");
+    const int dt = isbin ? APS_U8 : APS_F32;
     if (dtype < 0) { dtype = dt; D = (int)mxGetN(f); }
     if (dt != dtype) mexErrMsgIdAndTxt("flann_knn:type", "all descriptor matrices must have the same class");
     if ((int)mxGetN(f) != D) mexErrMsgIdAndTxt("flann_knn:dim", "all descriptor matrices must have the same width");
     counts[i] = (int64_t)mxGetM(f);
-    if (mxIsDouble(f)) {  // single(allDesc), featureMatchingGlobal.m:81
-      const double* s = mxGetPr(f);
-      converted.emplace_back(s, s + mxGetNumberOfElements(f));
-      ptrs[i] = converted.back().data();
-    } else {
-      ptrs[i] = mxGetData(f);
-    }
+    if (isbin || mxIsSingle(f)) ptrs[i] = mxGetData(f);
+    else if (mxIsDouble(f)) ptrs[i] = aps_mex_to_single<double>(f, converted);
+    else if (mxIsUint8(f) || mxIsLogical(f)) ptrs[i] = aps_mex_to_single<uint8_t>(f, converted);
+    else if (mxIsClass(f, "int8")) ptrs[i] = aps_mex_to_single<int8_t>(f, converted);
+    else if (mxIsClass(f, "uint16")) ptrs[i] = aps_mex_to_single<uint16_t>(f, converted);
+    else if (mxIsClass(f, "int16")) ptrs[i] = aps_mex_to_single<int16_t>(f, converted);
+    else if (mxIsClass(f, "uint32")) ptrs[i] = aps_mex_to_single<uint32_t>(f, converted);
+    else if (mxIsClass(f, "int32")) ptrs[i] = aps_mex_to_single<int32_t>(f, converted);
+    else mexErrMsgIdAndTxt("flann_knn:type", "unsupported descriptor class");
   }
 }
 // CSR match list -> n x n cell of [M x 2] double (featureMatchingGlobal.m:155-159; untouched cells stay [])

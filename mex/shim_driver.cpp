@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "mex.h"
 
@@ -20,7 +21,99 @@ static int expect_error(const char* want, int nlhs, int nrhs, const mxArray** in
   return 1;
 }
 
+// ---- file mode: `gate file in.bin out.bin` ---------------------------------------------------------------------
+// in.bin : int32 nmat ; per matrix int32 cls (0 single, 1 uint8, 2 double, 4 uint8 wrapped in a binaryFeatures
+//          object), int32 rows, int32 cols, column-major payload ; int32 nscalars ; doubles.
+// out.bin: int32 nout ; per output int32 cls (0 single, 1 uint8, 2 double, 3 uint32, -1 empty), rows, cols, payload.
+// tests/test_mex_gateways.py builds the inputs, runs the gateway on the GPU and compares the outputs with the oracle.
+static mxArray* read_matrix(FILE* f) {
+  int32_t h[3];
+  if (std::fread(h, 4, 3, f) != 3) return nullptr;
+  const mxClassID cls = h[0] == 0 ? mxSINGLE_CLASS : (h[0] == 2 ? mxDOUBLE_CLASS : mxUINT8_CLASS);
+  mxArray* a = mxCreateNumericMatrix((mwSize)h[1], (mwSize)h[2], cls, mxREAL);
+  const size_t bytes = (size_t)h[1] * h[2] * mxshim_elem_size(cls);
+  if (bytes && std::fread(mxGetData(a), 1, bytes, f) != bytes) return nullptr;
+  if (h[0] == 4) {
+    mxArray* o = new mxArray();
+    o->cls = mxUNKNOWN_CLASS;
+    o->dims = {1, 1};
+    o->class_name = "binaryFeatures";
+    o->properties.push_back({"Features", a});
+    return o;
+  }
+  return a;
+}
+static void write_matrix(FILE* f, const mxArray* a) {
+  int32_t h[3] = {-1, 0, 0};
+  if (a && !mxIsCell(a)) {
+    h[0] = mxIsSingle(a) ? 0 : mxIsUint8(a) ? 1 : mxIsDouble(a) ? 2 : mxIsUint32(a) ? 3 : -1;
+    h[1] = (int32_t)mxGetM(a);
+    h[2] = (int32_t)mxGetN(a);
+  }
+  std::fwrite(h, 4, 3, f);
+  if (h[0] >= 0) std::fwrite(mxGetData(a), mxshim_elem_size(mxGetClassID(a)), (size_t)h[1] * h[2], f);
+}
+static int file_mode(const char* in_path, const char* out_path) {
+  FILE* f = std::fopen(in_path, "rb");
+  if (!f) return 2;
+  int32_t nmat = 0, nsc = 0;
+  if (std::fread(&nmat, 4, 1, f) != 1) return 2;
+  std::vector<mxArray*> mats;
+  for (int i = 0; i < nmat; ++i) mats.push_back(read_matrix(f));
+  if (std::fread(&nsc, 4, 1, f) != 1) return 2;
+  std::vector<double> sc((size_t)nsc);
+  if (nsc && std::fread(sc.data(), 8, (size_t)nsc, f) != (size_t)nsc) return 2;
+  std::fclose(f);
+  mxArray* out[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nout = 0;
+  std::vector<const mxArray*> outs;
+  try {
+#if defined(GATE_FLANN)   // scalars: k, use_bf ; matrices: train [, query]
+    std::vector<const mxArray*> in(mats.begin(), mats.end());
+    in.push_back(mxCreateDoubleScalar(sc[0]));
+    if (sc.size() > 1 && sc[1] != 0.0) in.push_back(mxCreateString("bf"));
+    mexFunction(2, out, (int)in.size(), in.data());
+    outs = {out[0], out[1]};
+#elif defined(GATE_HAMMING)
+    const mxArray* in[] = {mats[0], mats[1]};
+    mexFunction(3, out, 2, in);
+    outs = {out[0], out[1], out[2]};
+#elif defined(GATE_BATCHED)  // scalars: mode (0 global, 1 pairwise), then (k, ratio, useBF) or (MatchThreshold, MaxRatio)
+    mxArray* cells = mxCreateCellMatrix(1, (mwSize)nmat);
+    for (int i = 0; i < nmat; ++i) mxSetCell(cells, (mwIndex)i, mats[i]);
+    std::vector<const mxArray*> in = {mxCreateString(sc[0] == 0.0 ? "global" : "pairwise"), cells,
+                                      mxCreateDoubleScalar((double)nmat)};
+    for (size_t i = 1; i < sc.size(); ++i) in.push_back(mxCreateDoubleScalar(sc[i]));
+    mexFunction(1, out, (int)in.size(), in.data());
+    for (int j = 0; j < nmat; ++j)   // upper-triangle cells in column-major order
+      for (int i = 0; i < j; ++i) outs.push_back(mxGetCell(out[0], (mwIndex)(i + j * nmat)));
+#elif defined(GATE_MATCHF)   // scalars: kind, MatchThreshold, MaxRatio, Unique
+    mxArray* uq = mxCreateLogicalMatrix(1, 1);
+    ((unsigned char*)mxGetData(uq))[0] = sc[3] != 0.0;
+    const mxArray* in[] = {mats[0], mats[1], mxCreateDoubleScalar(sc[0]), mxCreateDoubleScalar(sc[1]),
+                           mxCreateDoubleScalar(sc[2]), uq};
+    mexFunction(2, out, 6, in);
+    outs = {out[0], out[1]};
+#else
+    (void)out;
+    return 3;
+#endif
+  } catch (const mexShimError& e) {
+    std::printf("ERROR %s: %s\n", e.id.c_str(), e.what());
+    return 1;
+  }
+  nout = (int)outs.size();
+  FILE* g = std::fopen(out_path, "wb");
+  if (!g) return 2;
+  std::fwrite(&nout, 4, 1, g);
+  for (const mxArray* a : outs) write_matrix(g, a);
+  std::fclose(g);
+  std::printf("OK\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 3 && !std::strcmp(argv[1], "file")) return file_mode(argv[2], argv[3]);
   const bool gpu = argc > 1 && !std::strcmp(argv[1], "gpu");
   int bad = 0;
 #if defined(GATE_FLANN)

@@ -42,6 +42,14 @@
 #define ORC_EPS32 1.1920928955078125e-07f /* eps('single') = 2^-23 */
 
 int orc_version(void) { return 1; }
+/* bench.py's CPU arms use every host core even when the launcher (torch.distributed.run) exported OMP_NUM_THREADS=1 */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

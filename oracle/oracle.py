@@ -86,6 +86,12 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the oracle's parallel loops (bench.py: all host cores, whatever OMP_NUM_THREADS says)."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

@@ -19,10 +19,22 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and "sample" in d["config"]
+    assert set(d["config"]) == {"workload", "F", "k", "ratio", "pairs_per_step"} and d["config"]["workload"].startswith("C2")
+    assert "sample" in d["cpu_baseline"] and d["cpu_baseline"]["cores"] == os.cpu_count()
     assert d["reference_exhaustive_blas"]["value"] > 0
     if "reference_default_engine" in d:   # needs the OpenCV python module
         assert 0.0 < d["reference_default_engine"]["recall_at_k_vs_exact"] <= 1.0
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the reference arm must still use every host core, and at
+    N > 1 it times the config the GPU arm runs there (C3)."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == os.cpu_count() and d["config"]["workload"].startswith("C3") and d["scaling"] == "strong"
 
 
 def test_reference_arm_other_ranks_exit_quietly():
