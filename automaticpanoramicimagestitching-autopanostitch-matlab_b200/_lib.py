@@ -36,13 +36,32 @@ def sources():
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """nvcc-compiles csrc/*.cu for sm_100a into libapsmatch.so next to this file (in-tree)."""
+    """nvcc-compiles csrc/*.cu for sm_100a into libapsmatch.so next to this file (in-tree): one object per
+    translation unit (compiled in parallel, rebuilt only when the source or a header changed), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+
     srcs = sources()
-    deps = srcs + glob.glob(os.path.join(_HERE, "csrc", "*.cuh")) + [os.path.join(_HERE, "..", "include", "apsmatch.h")]
-    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
-        return _SO
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + srcs
-    subprocess.run(cmd, check=True)
+    hdrs = glob.glob(os.path.join(_HERE, "csrc", "*.cuh")) + [os.path.join(_HERE, "..", "include", "apsmatch.h")]
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
+    jobs = []
+    for src in srcs:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            jobs.append((src, obj))
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(job):
+        cmd = ["nvcc"] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", job[1], job[0]]
+        subprocess.run(cmd, check=True)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            list(ex.map(compile_one, jobs))
+    objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    if jobs or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(o) for o in objs):
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", _SO] + objs, check=True)
     return _SO
 
 
@@ -71,6 +90,8 @@ def lib():
         "aps_ctx_set_float_engine": (i32, [vp, i32]),
         "aps_ctx_set_pairwise_epilogue": (i32, [vp, i32]),
         "aps_ctx_last_stats": (i32, [vp, C.POINTER(i64)]),
+        "aps_ctx_set_pairwise_screen": (i32, [vp, i32]),
+        "aps_ctx_pairwise_stats": (i32, [vp, C.POINTER(i64)]),
         "aps_ctx_enable_timing": (i32, [vp, i32]),
         "aps_ctx_tc_time": (i32, [vp, C.POINTER(dbl), C.POINTER(i64)]),
         "aps_launch_count": (i64, []),
@@ -118,6 +139,7 @@ def lib():
         "aps_pplan_prepare": (i32, [vp]),
         "aps_pplan_match": (i32, [vp, dbl, dbl, i32, i32, pp]),
         "aps_debug_tc_slots": (i32, [vp, i64, i64]),
+        "aps_debug_pair_screen": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, i32]),
         "aps_debug_tc_scores": (i32, [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -156,6 +178,15 @@ class Context:
     def set_pairwise_epilogue(self, mode: int):
         """-1 = auto (default), 0 = streaming top-4, 1 = branch-free segment selection (see include/apsmatch.h)."""
         check(lib().aps_ctx_set_pairwise_epilogue(self._h, int(mode)))
+
+    def set_pairwise_screen(self, on=True):
+        """Stage 1 of the batched pairwise path (fp16 tensor screen, see include/apsmatch.h); on by default."""
+        check(lib().aps_ctx_set_pairwise_screen(self._h, int(bool(on))))
+
+    def pairwise_stats(self):
+        a = (C.c_int64 * 4)()
+        check(lib().aps_ctx_pairwise_stats(self._h, a))
+        return {"pairs_screened": a[0], "pairs_to_exact": a[1], "entries_screened": a[2]}
 
     def enable_timing(self, on=True):
         check(lib().aps_ctx_enable_timing(self._h, int(bool(on))))

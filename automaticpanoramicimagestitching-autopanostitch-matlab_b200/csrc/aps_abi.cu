@@ -134,11 +134,23 @@ extern "C" int aps_ctx_set_pairwise_epilogue(aps_ctx* c, int mode) {
   return APS_OK;
 }
 
+extern "C" int aps_ctx_set_pairwise_screen(aps_ctx* c, int mode) {
+  if (!c || mode < 0 || mode > 1) APS_FAIL(APS_ERR_ARGS, "", "pairwise screen must be 0 (off) or 1 (on)");
+  c->pairwise_screen = mode;
+  return APS_OK;
+}
+extern "C" int aps_ctx_pairwise_stats(aps_ctx* c, int64_t stats[4]) {
+  if (!c || !stats) APS_FAIL(APS_ERR_ARGS, "", "bad args");
+  for (int i = 0; i < 4; ++i) stats[i] = c->pair_stats[i];
+  return APS_OK;
+}
+
 extern "C" int aps_ctx_last_stats(aps_ctx* c, int64_t stats[4]) {
   if (!c || !stats) APS_FAIL(APS_ERR_ARGS, "", "bad args");
   APS_CUDA(cudaSetDevice(c->device));
   APS_CUDA(cudaStreamSynchronize(c->stream));
   if (c->stats[2] == 2) c->stats[1] = c->h_flags[32];  // fallback-row count of the last tensor search
+  if (c->h_flags[36] == 1) c->stats[3] = c->h_flags[35] != 0;  // "operands exact in bf16" flag of the last global search
   for (int i = 0; i < 4; ++i) stats[i] = c->stats[i];
   return APS_OK;
 }
@@ -802,10 +814,13 @@ extern "C" int aps_gplan_knn(aps_gplan* p, int64_t q0, int64_t q1) {
   if (q0 < 0 || q1 > p->F || q0 > q1) APS_FAIL(APS_ERR_ARGS, "", "query range out of bounds");
   if (q0 == q1) return APS_OK;
   c->stats[0] = c->stats[1] = c->stats[2] = c->stats[3] = 0;
+  c->h_flags[36] = 0;
   if (p->dtype == APS_F32) {
     FloatSide s = p->fs.side();
     APS_TRY(float_knn(c, s, q0, q1, s, 0, p->F, p->D, p->k, /*metric*/ 0, /*bias*/ 0, p->fs.flags.p, 0,
                       p->knn_idx.p, p->knn_dist.p, p->tensor));
+    APS_CUDA(cudaMemcpyAsync(c->h_flags + 35, p->fs.flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->h_flags[36] = 1;
   } else {
     APS_TRY(aps_k_knn_hamming(c->stream, p->u8pad.p, q0, q1 - q0, p->u8pad.p, 0, p->F, p->nb16, p->k, 0,
                               p->knn_idx.p, p->knn_dist.p));
@@ -926,6 +941,10 @@ struct PairwiseSets {
   int nb16 = 0;
   std::vector<int64_t> off;
   std::vector<int> big;  // per image: max|.| > 2
+  // stage 1 (aps_pair_screen.cu): fp16 operand rows and per-image (min, max) squared norms of both views
+  DevBuf<uint16_t> xh_raw, xh_norm;
+  DevBuf<float2> bounds_raw, bounds_norm;
+  DevBuf<int64_t> d_img_off;
 };
 
 // allocation of the pooled raw matrix + bookkeeping
@@ -1018,6 +1037,12 @@ static int pairwise_finish(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, 
     APS_TRY(aps_k_prepare_operands(c->stream, ps.rawset.raw.p, ps.rawset.raw.p, ps.rawset.sq.p, ps.rawset.invn.p, F,
                                    D, Dp, ps.rawset.flags.p, 1, ps.rawset.xb.p, ps.rawset.colscale.p, ps.rawset.colbias.p));
     APS_TRY(floatset_finish_train(c, ps.rawset, /*sort*/ false));  // image ranges must stay contiguous
+    APS_TRY(ps.d_img_off.alloc((size_t)n + 1, c->stream));
+    APS_CUDA(cudaMemcpyAsync(ps.d_img_off.p, ps.off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    APS_TRY(ps.xh_raw.alloc((size_t)F * Dp, c->stream));
+    APS_TRY(ps.bounds_raw.alloc((size_t)n, c->stream));
+    APS_TRY(aps_k_prepare_operands_f16(c->stream, ps.rawset.raw.p, F, D, Dp, ps.xh_raw.p));
+    APS_TRY(aps_k_image_sq_bounds(c->stream, ps.rawset.sq.p, ps.d_img_off.p, n, ps.bounds_raw.p));
   }
   if (any_big) {
     APS_TRY(floatset_alloc(c, ps.normset, F, D));
@@ -1025,6 +1050,13 @@ static int pairwise_finish(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, 
     APS_CUDA(cudaMemcpyAsync(ps.normset.raw.p, ps.rawset.raw.p, (size_t)F * D * 4, cudaMemcpyDeviceToDevice, c->stream));
     // normalised rows: scale-only scoring (bias would have to be scaled per query row)
     APS_TRY(floatset_prepare(c, ps.normset, APS_NORM_PAIRWISE, tensor, 0, /*sort*/ false));
+    if (tensor) {
+      const int Dp = (D + 63) / 64 * 64;
+      APS_TRY(ps.xh_norm.alloc((size_t)F * Dp, c->stream));
+      APS_TRY(ps.bounds_norm.alloc((size_t)n, c->stream));
+      APS_TRY(aps_k_prepare_operands_f16(c->stream, ps.normset.xn.p, F, D, Dp, ps.xh_norm.p));
+      APS_TRY(aps_k_image_sq_bounds(c->stream, ps.normset.sq.p, ps.d_img_off.p, n, ps.bounds_norm.p));
+    }
   }
   return APS_OK;
 }
@@ -1356,6 +1388,75 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   return APS_OK;
 }
 
+// Stage 1 of the batched pairwise path (aps_pair_screen.cu): every pair of `pairs` is screened on the tensor cores
+// with fp16 operands; pairs in which no query row can pass the ratio / threshold test are dropped from the list
+// (their cell is empty: zero matches), the others go on to the exact pipeline.
+static int pairwise_screen_stage(aps_ctx* c, PairwiseSets& ps, std::vector<PairRef>& pairs, const int64_t* counts, int D,
+                                 bool norm, double match_threshold, double max_ratio) {
+  const int np = (int)pairs.size();
+  if (np == 0) return APS_OK;
+  cudaStream_t s = c->stream;
+  const int Dp = (D + 63) / 64 * 64;
+  FloatSet& S = norm ? ps.normset : ps.rawset;
+  const void* xh = norm ? (const void*)ps.xh_norm.p : (const void*)ps.xh_raw.p;
+  const float2* bounds = norm ? ps.bounds_norm.p : ps.bounds_raw.p;
+  if (!xh || !bounds) return APS_OK;
+  std::vector<int32_t> tab((size_t)np * 5);
+  std::vector<int64_t> off2((size_t)(np + 1) * 2, 0);
+  int32_t *qoff = tab.data(), *qcnt = qoff + np, *toff = qcnt + np, *tcnt = toff + np, *timg = tcnt + np;
+  int64_t *eoff = off2.data(), *uoff = eoff + (np + 1);
+  for (int p = 0; p < np; ++p) {
+    qoff[p] = (int32_t)ps.off[pairs[p].i];
+    qcnt[p] = (int32_t)counts[pairs[p].i];
+    toff[p] = (int32_t)ps.off[pairs[p].j];
+    tcnt[p] = (int32_t)counts[pairs[p].j];
+    timg[p] = pairs[p].j;
+    eoff[p + 1] = eoff[p] + counts[pairs[p].i];
+    uoff[p + 1] = uoff[p] + (counts[pairs[p].i] + 255) / 256;
+  }
+  const int64_t E = eoff[np], U = uoff[np];
+  DevBuf<int32_t> d_tab, d_surv;
+  DevBuf<int64_t> d_off2;
+  DevBuf<aps_tc_unit> d_units;
+  DevBuf<uint32_t> scr;
+  APS_TRY(d_tab.alloc(tab.size(), s));
+  APS_TRY(d_off2.alloc(off2.size(), s));
+  APS_TRY(d_surv.alloc((size_t)np, s));
+  APS_TRY(d_units.alloc((size_t)U, s));
+  APS_TRY(scr.alloc((size_t)E, s));
+  APS_CUDA(cudaMemcpyAsync(d_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s));
+  APS_CUDA(cudaMemcpyAsync(d_off2.p, off2.data(), off2.size() * 8, cudaMemcpyHostToDevice, s));
+  aps_pair_screen_tables t;
+  t.qoff = d_tab.p; t.qcnt = d_tab.p + np; t.toff = d_tab.p + 2 * (size_t)np; t.tcnt = d_tab.p + 3 * (size_t)np;
+  t.timg = d_tab.p + 4 * (size_t)np; t.eoff = d_off2.p; t.uoff = d_off2.p + (np + 1); t.npairs = np;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (c->timing) {
+    APS_CUDA(cudaEventCreate(&ev0));
+    APS_CUDA(cudaEventCreate(&ev1));
+    APS_CUDA(cudaEventRecord(ev0, s));
+  }
+  APS_TRY(aps_k_pair_screen(s, c->sm_count, xh, S.N, Dp, t, d_units.p, U, scr.p));
+  if (c->timing) {
+    APS_CUDA(cudaEventRecord(ev1, s));
+    c->tc_events.push_back(ev0);
+    c->tc_events.push_back(ev1);
+  }
+  APS_TRY(aps_k_pair_screen_decide(s, scr.p, S.sq.p, t, bounds, S.flags.p, Dp, max_ratio * max_ratio, match_threshold,
+                                   d_surv.p));
+  std::vector<int32_t> surv((size_t)np);
+  APS_CUDA(cudaMemcpyAsync(surv.data(), d_surv.p, (size_t)np * 4, cudaMemcpyDeviceToHost, s));
+  APS_CUDA(cudaStreamSynchronize(s));   // also covers the pageable host tables above
+  std::vector<PairRef> keep;
+  for (int p = 0; p < np; ++p)
+    if (surv[p] > 0) keep.push_back(pairs[p]);
+  c->pair_stats[0] += np;
+  c->pair_stats[1] += (int64_t)keep.size();
+  c->pair_stats[2] += E;
+  c->stats[2] = 2;
+  pairs.swap(keep);
+  return APS_OK;
+}
+
 // staged pairwise pipeline: descriptors resident on the device, prepared once, matched per rank share
 struct aps_pplan {
   aps_ctx* c = nullptr;
@@ -1467,6 +1568,11 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
       if (counts[pr.i] == 0 || counts[pr.j] == 0) continue;  // matchFeaturesScratch.m:84-88
       const bool norm = dtype == APS_F32 && (ps.big[pr.i] || ps.big[pr.j]);  // :105-110 is a per-pair decision
       (norm ? mine_norm : mine_raw).push_back(pr);
+    }
+    c->pair_stats[0] = c->pair_stats[1] = c->pair_stats[2] = c->pair_stats[3] = 0;
+    if (tensor && c->pairwise_screen) {
+      rc = pairwise_screen_stage(c, ps, mine_raw, counts, D, false, match_threshold, max_ratio);
+      if (rc == APS_OK) rc = pairwise_screen_stage(c, ps, mine_norm, counts, D, true, match_threshold, max_ratio);
     }
     std::vector<int32_t> cnt(NP, 0);
     std::vector<std::vector<uint32_t>> prow(NP);
@@ -1620,5 +1726,67 @@ extern "C" int aps_debug_tc_scores(aps_ctx* c, const float* Q, int64_t nq, const
   if (cand_idx) APS_CUDA(cudaMemcpyAsync(cand_idx, cidx.p, (size_t)nq * nslot * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
   if (cand_score) APS_CUDA(cudaMemcpyAsync(cand_score, cscore.p, (size_t)nq * nslot * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
   APS_CUDA(cudaStreamSynchronize(c->stream));
+  return APS_OK;
+}
+
+// diagnostics: the fp16 screen of ONE (query set, train set) pair, with the raw accumulator registers
+extern "C" int aps_debug_pair_screen(aps_ctx* c, const float* A, int64_t N1, const float* B, int64_t N2, int D,
+                                     float* b1b2, uint32_t* dump, int dump_tiles) {
+  APS_CTX(c);
+  if (!A || !B || N1 <= 0 || N2 <= 0 || D <= 0 || !b1b2) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  const int Dp = (D + 63) / 64 * 64;
+  if (!aps_k_knn_tc_supported(Dp)) APS_FAIL(APS_ERR_DIM, "", "unsupported descriptor length %d", D);
+  cudaStream_t s = c->stream;
+  const int64_t F = N1 + N2;
+  DevBuf<float> raw;
+  DevBuf<uint16_t> xh;
+  DevBuf<uint32_t> scr, ddump;
+  DevBuf<aps_tc_unit> units;
+  DevBuf<int32_t> tab;
+  DevBuf<int64_t> off2;
+  APS_TRY(raw.alloc((size_t)F * D, s));
+  APS_TRY(xh.alloc((size_t)F * Dp, s));
+  APS_TRY(scr.alloc((size_t)N1, s));
+  const int64_t U = (N1 + 255) / 256;
+  APS_TRY(units.alloc((size_t)U, s));
+  if (dump && dump_tiles > 0) {
+    APS_TRY(ddump.alloc((size_t)N1 * dump_tiles * 64, s));
+    APS_CUDA(cudaMemsetAsync(ddump.p, 0, (size_t)N1 * dump_tiles * 64 * 4, s));
+  }
+  APS_CUDA(cudaMemcpyAsync(raw.p, A, (size_t)N1 * D * 4, cudaMemcpyHostToDevice, s));
+  APS_CUDA(cudaMemcpyAsync(raw.p + (size_t)N1 * D, B, (size_t)N2 * D * 4, cudaMemcpyHostToDevice, s));
+  APS_TRY(aps_k_prepare_operands_f16(s, raw.p, F, D, Dp, xh.p));
+  const int32_t htab[5] = {0, (int32_t)N1, (int32_t)N1, (int32_t)N2, 1};
+  const int64_t hoff[4] = {0, N1, 0, U};
+  APS_TRY(tab.alloc(5, s));
+  APS_TRY(off2.alloc(4, s));
+  APS_CUDA(cudaMemcpyAsync(tab.p, htab, sizeof htab, cudaMemcpyHostToDevice, s));
+  APS_CUDA(cudaMemcpyAsync(off2.p, hoff, sizeof hoff, cudaMemcpyHostToDevice, s));
+  aps_pair_screen_tables t;
+  t.qoff = tab.p; t.qcnt = tab.p + 1; t.toff = tab.p + 2; t.tcnt = tab.p + 3; t.timg = tab.p + 4;
+  t.eoff = off2.p; t.uoff = off2.p + 2; t.npairs = 1;
+  APS_TRY(aps_k_pair_screen(s, c->sm_count, xh.p, F, Dp, t, units.p, U, scr.p, ddump.p, ddump.p ? dump_tiles : 0));
+  std::vector<uint32_t> h((size_t)N1);
+  APS_CUDA(cudaMemcpyAsync(h.data(), scr.p, (size_t)N1 * 4, cudaMemcpyDeviceToHost, s));
+  if (ddump.p) APS_CUDA(cudaMemcpyAsync(dump, ddump.p, (size_t)N1 * dump_tiles * 64 * 4, cudaMemcpyDeviceToHost, s));
+  APS_CUDA(cudaStreamSynchronize(s));
+  for (int64_t i = 0; i < N1; ++i) {   // unpack the two fp16 values (pure bit manipulation, no arithmetic)
+    for (int w = 0; w < 2; ++w) {
+      const uint16_t hb = (uint16_t)(h[(size_t)i] >> (16 * w));
+      const uint32_t sign = (uint32_t)(hb & 0x8000u) << 16, ex = (hb >> 10) & 0x1fu, man = hb & 0x3ffu;
+      uint32_t f;
+      if (ex == 0) {
+        if (man == 0) f = sign;
+        else {
+          int e = -1;
+          uint32_t m = man;
+          do { ++e; m <<= 1; } while (!(m & 0x400u));
+          f = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 0x3ffu) << 13);
+        }
+      } else if (ex == 31) f = sign | 0x7f800000u | (man << 13);
+      else f = sign | ((ex + 112u) << 23) | (man << 13);
+      memcpy(&b1b2[2 * i + w], &f, 4);
+    }
+  }
   return APS_OK;
 }

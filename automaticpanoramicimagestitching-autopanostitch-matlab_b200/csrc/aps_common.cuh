@@ -45,6 +45,8 @@ struct aps_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int float_engine = 0;  // 0 auto, 1 exact only, 2 tensor required
+  int pairwise_screen = 1;     // 1: fp16 tensor screen before the exact pairwise pipeline (aps_pair_screen.cu), 0: off
+  int64_t pair_stats[4] = {0, 0, 0, 0};  // last pairwise match: pairs screened, pairs surviving, entries screened, -
   int pairwise_epilogue = -1;  // -1 auto, 0 streaming top-4, 1 branch-free segment selection (aps_ctx_set_pairwise_epilogue)
   int64_t stats[4] = {0, 0, 0, 0};
   bool timing = false;
@@ -188,6 +190,29 @@ struct aps_pair_tables {
   // grows by the 7 key bits.
   int tile_mode;
 };
+
+// aps_pair_screen.cu : pairwise stage 1 -- fp16 tensor-core screen of every (query row, train image); see the file header
+struct aps_pair_screen_tables {   // per image pair p of the launch (device arrays)
+  const int32_t* qoff;   // first global row of the query image
+  const int32_t* qcnt;   // rows of the query image
+  const int32_t* toff;   // first global row of the train image
+  const int32_t* tcnt;   // rows of the train image
+  const int32_t* timg;   // train image index (per-image norm bounds)
+  const int64_t* eoff;   // [npairs + 1] entry offsets (sum of qcnt)
+  const int64_t* uoff;   // [npairs + 1] unit offsets (sum of ceil(qcnt / 256))
+  int npairs;
+};
+// bound of |fp16 tensor dot - exact dot| in units of |a||b|: operand rounding 2 * 2^-11, one rounding of the running
+// sum to fp16 per K = 16 instruction (2^-10 each, Dp / 16 of them), margin.  Checked against measurements by
+// tests/test_gpu_pair_screen.py.
+__host__ __device__ inline float aps_pair_screen_dot_eps(int Dp) { return (float)(Dp / 16) * 9.765625e-4f + 1.5e-3f; }
+int aps_k_prepare_operands_f16(cudaStream_t s, const float* src, int64_t F, int D, int Dp, void* xh);
+int aps_k_image_sq_bounds(cudaStream_t s, const float* sq, const int64_t* d_img_off, int n, float2* out);
+int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh, int64_t F, int Dp, const aps_pair_screen_tables& t,
+                      aps_tc_unit* d_units, int64_t n_units, uint32_t* out, uint32_t* dump = nullptr, int dump_tiles = 0);
+int aps_k_pair_screen_decide(cudaStream_t s, const uint32_t* scr, const float* sq, const aps_pair_screen_tables& t,
+                             const float2* img_bounds, const int32_t* flags, int Dp, double r2, double mt,
+                             int32_t* survivors);
 
 // K3 aps_rerank.cu : exact FP32 re-rank of the candidates + completeness proof.
 //   approx distance of a score: alpha[row] + beta[row]*score ; row proven iff

@@ -79,6 +79,14 @@ int aps_ctx_set_float_engine(aps_ctx* ctx, int engine);
  * images average at most 48 tiles of 128 descriptors, else 0.  Results are identical (both feed the exact re-rank
  * and its completeness proof); only speed and the share of rows sent to the exact fallback differ. */
 int aps_ctx_set_pairwise_epilogue(aps_ctx* ctx, int mode);
+/* Stage 1 of the batched pairwise path (float descriptors): 1 = on [default] -- every (query row, train image) is first
+ * screened on the tensor cores with fp16 operands and fp16 accumulators; image pairs in which no query row can pass
+ * the ratio / threshold test of matchFeaturesScratch.m:174-178 (proven from error-bounded distance bounds) skip the
+ * exact search, their cell is empty.  0 = off: every pair goes through the exact pipeline.  Results are identical.
+ * aps_ctx_pairwise_stats: [0] image pairs screened, [1] pairs that went on to the exact pipeline, [2] (query row,
+ * train image) entries screened, [3] reserved -- of the last aps_pplan_match / aps_feature_matching_pairwise call. */
+int aps_ctx_set_pairwise_screen(aps_ctx* ctx, int mode);
+int aps_ctx_pairwise_stats(aps_ctx* ctx, int64_t stats[4]);
 /* Counters of the last float search on this context: [0] rows searched, [1] rows whose
  * candidate set could not be PROVEN complete and were re-searched exactly, [2] engine used
  * (1 exact, 2 tcgen05), [3] 1 if operands were exactly representable in bf16. */
@@ -264,6 +272,11 @@ int aps_pplan_match(aps_pplan* p, double match_threshold, double max_ratio, int 
  * candidate lists the kernel keeps per query row (one per column segment its work unit was split
  * into; 0-based train rows, 0xFFFFFFFF = empty).  Any of the three outputs may be NULL; nseg is ignored. */
 int aps_debug_tc_slots(aps_ctx* ctx, int64_t nq, int64_t nt);
+/* The fp16 screen of one pair: A [N1 x D], B [N2 x D] ROW-major float used as given.  b1b2 [N1 x 2] receives the two
+ * values the screen keeps per query row (largest dot, and the second of the 8 column-class maxima); dump (may be NULL)
+ * [N1 x dump_tiles x 64] the raw accumulator registers (two packed fp16 scores each) of the first dump_tiles tiles. */
+int aps_debug_pair_screen(aps_ctx* ctx, const float* A, int64_t N1, const float* B, int64_t N2, int D, float* b1b2,
+                          uint32_t* dump, int dump_tiles);
 int aps_debug_tc_scores(aps_ctx* ctx, const float* Q, int64_t nq, const float* T, int64_t nt, int D, int nseg,
                         float* scores, uint32_t* cand_idx, float* cand_score);
 

@@ -1,0 +1,105 @@
+"""GPU: stage 1 of the batched pairwise path (csrc/aps_pair_screen.cu) -- fp16 tensor-core screen of every
+(query row, train image).  Checked here: the accumulator layout the epilogue assumes, the error bound the rejection
+proof uses (measured error must stay below HALF of aps_pair_screen_dot_eps), the two values kept per row, and that the
+match lists with the screen on are the lists with the screen off (which the other tests pin to the oracle)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def dot_eps(D):
+    Dp = (D + 63) // 64 * 64
+    return (Dp // 16) * 2.0 ** -10 + 1.5e-3          # aps_pair_screen_dot_eps (csrc/aps_common.cuh)
+
+
+def _screen(aps, A, B, dump_tiles):
+    L = aps._lib.lib()
+    ctx = aps._lib.default_context()
+    A, B = np.ascontiguousarray(A, np.float32), np.ascontiguousarray(B, np.float32)
+    out = np.zeros((A.shape[0], 2), np.float32)
+    dump = np.zeros((A.shape[0], dump_tiles, 64), np.uint32)
+    aps._lib.check(L.aps_debug_pair_screen(ctx.handle, A.ctypes.data, A.shape[0], B.ctypes.data, B.shape[0], A.shape[1],
+                                           out.ctypes.data, dump.ctypes.data, dump_tiles))
+    return out, dump
+
+
+def _cases(rng, N1, N2, D):
+    def unit(x):
+        return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+    yield "unit gaussian", unit(rng.standard_normal((N1, D))), unit(rng.standard_normal((N2, D)))
+    yield "positive, |.| <= 2 (monotone partial sums)", rng.uniform(0, 2, (N1, D)), rng.uniform(0, 2, (N2, D))
+    yield "mixed magnitudes", rng.standard_normal((N1, D)) * rng.uniform(1e-3, 0.6, (N1, 1)), rng.uniform(-2, 2, (N2, D))
+    s = unit(np.abs(rng.standard_normal((N1, D))))
+    yield "near duplicates", s, np.vstack([s + rng.normal(0, 0.02, s.shape), unit(np.abs(rng.standard_normal((N2 - N1, D))))])
+
+
+@pytest.mark.parametrize("D", [64, 128, 61])
+def test_accumulator_layout_and_error_bound(aps, D):
+    rng = np.random.default_rng(D)
+    N1, N2 = 256, 1000                       # train rows start at pooled row 256: tile-aligned, last tile partial
+    tiles = (N2 + 127) // 128
+    for name, A, B in _cases(rng, N1, N2, D):
+        A, B = A.astype(np.float32), B.astype(np.float32)
+        out, dump = _screen(aps, A, B, tiles)
+        S = dump.view(np.float16).reshape(N1, tiles * 128)[:, :N2].astype(np.float64)    # element 2j / 2j+1 = lo / hi half
+        exact = A.astype(np.float64) @ B.astype(np.float64).T
+        scale = np.linalg.norm(A.astype(np.float64), axis=1)[:, None] * np.linalg.norm(B.astype(np.float64), axis=1)[None, :]
+        err = np.abs(S - exact) / np.maximum(scale, 1e-30)
+        print(f"D={D} {name}: max |fp16 tensor dot - exact| / (|a||b|) = {err.max():.2e} (bound {dot_eps(D):.2e})")
+        assert err.max() <= 0.5 * dot_eps(D), (name, err.max(), dot_eps(D))
+        # the two values kept per row: best over all columns, second of the 8 column classes (column mod 8)
+        cls = np.full((N1, 8), -65504.0)
+        for c in range(8):
+            cls[:, c] = S[:, c::8].max(axis=1)
+        srt = np.sort(cls, axis=1)
+        assert np.array_equal(out[:, 0].astype(np.float64), srt[:, -1]), name
+        assert np.array_equal(out[:, 1].astype(np.float64), srt[:, -2]), name
+
+
+def test_partial_tiles_are_masked(aps):
+    """Train image starting and ending inside a tile: foreign columns (the query rows themselves: dot(a, a) = 1 would
+    win) must never be selected."""
+    rng = np.random.default_rng(9)
+    D, N1, N2 = 64, 300, 777
+    A = rng.standard_normal((N1, D)).astype(np.float32)
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    B = rng.standard_normal((N2, D)).astype(np.float32)
+    B /= np.linalg.norm(B, axis=1, keepdims=True)
+    out, _ = _screen(aps, A, B, 1)
+    dots = (A.astype(np.float16).astype(np.float64) @ B.astype(np.float16).astype(np.float64).T)
+    best = dots.max(axis=1)
+    assert np.abs(out[:, 0] - best).max() <= dot_eps(D)      # a masked-in foreign column would show here
+    assert (out[:, 0] < 0.9).all() and (out[:, 1] <= out[:, 0]).all()
+
+
+def test_screen_on_equals_screen_off(aps, orc):
+    ctx = aps._lib.default_context()
+    inp = {"Matchingmethod": "Exhaustive", "Matchingthreshold": 1.5, "Ratiothreshold": 0.7, "useMATLABFeatureMatch": 0}
+    for cid, n, kp in ((5, 24, 1500), (5, 7, 4096), (1, 5, 2048), (6, 5, 1200)):
+        desc, _ = aps.synth.make_config(cid, n=n, kp=kp)
+        ctx.set_pairwise_screen(True)
+        on, mon = aps.featureMatchingPairwise(inp, desc, len(desc), ctx=ctx, return_metric=True)
+        st = ctx.pairwise_stats()
+        ctx.set_pairwise_screen(False)
+        try:
+            off, moff = aps.featureMatchingPairwise(inp, desc, len(desc), ctx=ctx, return_metric=True)
+        finally:
+            ctx.set_pairwise_screen(True)
+        npairs = sum(1 for j in range(len(desc)) for i in range(j) if desc[i].shape[0] and desc[j].shape[0])
+        print(f"config {cid} n={n} kp={kp}: {st}")
+        assert st["pairs_screened"] == npairs and st["pairs_to_exact"] <= npairs
+        if cid == 5 and n == 24:
+            assert st["pairs_to_exact"] < 0.4 * npairs       # only ring neighbours hold planted overlaps
+        for j in range(len(desc)):
+            for i in range(j):
+                assert on[i][j].shape == off[i][j].shape and np.array_equal(on[i][j], off[i][j]), (cid, i, j)
+                if on[i][j].shape[0]:
+                    assert np.array_equal(np.asarray(mon[i][j]), np.asarray(moff[i][j]))
+        if n <= 7:   # and against the oracle on every pair of the small sets
+            ref = orc.feature_matching_pairwise(desc, 1.5, 0.7)["cells"]
+            for j in range(len(desc)):
+                for i in range(j):
+                    exp = ref.get((i, j))
+                    assert (exp is None and on[i][j].shape[0] == 0) or np.array_equal(on[i][j], exp.astype(np.float64)), (cid, i, j)
