@@ -943,6 +943,7 @@ struct PairwiseSets {
   std::vector<int> big;  // per image: max|.| > 2
   // stage 1 (aps_pair_screen.cu): fp16 operand rows and per-image (min, max) squared norms of both views
   DevBuf<uint16_t> xh_raw, xh_norm;
+  DevBuf<float> ones;    // [F + 256] column scales of the fp16 operand rows (they hold the values themselves: scale 1)
   DevBuf<float2> bounds_raw, bounds_norm;
   DevBuf<int64_t> d_img_off;
 };
@@ -1002,11 +1003,12 @@ static int pairwise_finish(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, 
   std::vector<int32_t> init((size_t)n * 8, 0);
   for (int i = 0; i < n; ++i) init[(size_t)i * 8] = 1;
   APS_CUDA(cudaMemcpyAsync(imgflags.p, init.data(), init.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  for (int i = 0; i < n; ++i)
-    if (counts[i] > 0)
-      APS_TRY(aps_k_prepare_norm(c->stream, ps.rawset.raw.p + (size_t)ps.off[i] * D, counts[i], D, APS_NORM_NONE,
-                                 ps.rawset.raw.p + (size_t)ps.off[i] * D, ps.rawset.sq.p + ps.off[i],
-                                 ps.rawset.invn.p + ps.off[i], imgflags.p + (size_t)i * 8));
+  int64_t maxc = 0;
+  for (int i = 0; i < n; ++i) maxc = counts[i] > maxc ? counts[i] : maxc;
+  APS_TRY(ps.d_img_off.alloc((size_t)n + 1, c->stream));
+  APS_CUDA(cudaMemcpyAsync(ps.d_img_off.p, ps.off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  APS_TRY(aps_k_prepare_norm_images(c->stream, ps.rawset.raw.p, ps.d_img_off.p, n, maxc, D, APS_NORM_NONE, ps.rawset.raw.p,
+                                    ps.rawset.sq.p, ps.rawset.invn.p, imgflags.p));
   std::vector<int32_t> hf((size_t)n * 8);
   APS_CUDA(cudaMemcpyAsync(hf.data(), imgflags.p, hf.size() * 4, cudaMemcpyDeviceToHost, c->stream));
   APS_CUDA(cudaStreamSynchronize(c->stream));
@@ -1037,10 +1039,10 @@ static int pairwise_finish(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, 
     APS_TRY(aps_k_prepare_operands(c->stream, ps.rawset.raw.p, ps.rawset.raw.p, ps.rawset.sq.p, ps.rawset.invn.p, F,
                                    D, Dp, ps.rawset.flags.p, 1, ps.rawset.xb.p, ps.rawset.colscale.p, ps.rawset.colbias.p));
     APS_TRY(floatset_finish_train(c, ps.rawset, /*sort*/ false));  // image ranges must stay contiguous
-    APS_TRY(ps.d_img_off.alloc((size_t)n + 1, c->stream));
-    APS_CUDA(cudaMemcpyAsync(ps.d_img_off.p, ps.off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     APS_TRY(ps.xh_raw.alloc((size_t)F * Dp, c->stream));
     APS_TRY(ps.bounds_raw.alloc((size_t)n, c->stream));
+    APS_TRY(ps.ones.alloc((size_t)F + 256, c->stream));
+    APS_TRY(aps_k_fill_f32(c->stream, ps.ones.p, F + 256, 1.0f));
     APS_TRY(aps_k_prepare_operands_f16(c->stream, ps.rawset.raw.p, F, D, Dp, ps.xh_raw.p));
     APS_TRY(aps_k_image_sq_bounds(c->stream, ps.rawset.sq.p, ps.d_img_off.p, n, ps.bounds_raw.p));
   }
@@ -1317,7 +1319,14 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       APS_CUDA(cudaMemcpyAsync(d_units.p, units.data(), units.size() * sizeof(aps_tc_unit), cudaMemcpyHostToDevice, s));
       APS_CUDA(cudaStreamSynchronize(s));  // host tables are pageable
       aps_tc_problem tp;
-      tp.Qb = side.xb; tp.Tb = side.xb_t; tp.colscale = side.colscale_t; tp.colbias = side.colbias_t;
+      // fp16 operand rows (built for the screen; |x| <= 2 in this path) when present: 4x smaller operand-rounding
+      // term in the proof's eps than bf16, so far fewer rows end in the exact fallback
+      const void* xh = norm ? (const void*)ps.xh_norm.p : (const void*)ps.xh_raw.p;
+      tp.Qb = xh ? (const __nv_bfloat16*)xh : side.xb;
+      tp.Tb = xh ? (const __nv_bfloat16*)xh : side.xb_t;
+      tp.operand_fp16 = xh ? 1 : 0;
+      tp.colscale = xh ? ps.ones.p : side.colscale_t;
+      tp.colbias = side.colbias_t;
       tp.tile_bounds = side.tile_bounds; tp.bias = bias_mode;
       tp.Fq_total = side.N; tp.Ft_total = side.N; tp.Dp = (D + 63) / 64 * 64;
       tp.q0 = 0; tp.q1 = 0; tp.t0 = 0; tp.t1 = 0; tp.nslot = 1; tp.kcand = KCP;
@@ -1339,6 +1348,7 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       ptr_.prune_r2 = max_ratio * max_ratio;
       ptr_.prune_mt = match_threshold;
       ptr_.tile_mode = KCP == 3 ? aps_k_knn_tc_tile_mode_segment() : 0;
+      ptr_.operand_fp16 = tp.operand_fp16;
       APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, /*metric*/ 1, 0, E, 0, nlist, KCP, cidx.p,
                            cscore.p, S.flags.p, bias_mode, S.flags.p, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &ptr_));
       APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, 1, pt, fb.p, fb.p + E, E, i2.p, dd.p));

@@ -101,6 +101,9 @@ int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const flo
 // flags[2] = max bits sq, flags[3] = max bits |raw| (for the max|.|>2 test of matchFeaturesScratch.m:105)
 int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int norm_mode, float* xn, float* sq,
                        float* invn, int32_t* flags);
+// the same for every image of a pooled matrix in one launch: image i = rows [img_off[i], img_off[i+1]), flags + 8*i
+int aps_k_prepare_norm_images(cudaStream_t s, const float* raw, const int64_t* d_img_off, int n, int64_t maxcount, int D,
+                              int norm_mode, float* xn, float* sq, float* invn, int32_t* flags);
 // pass 2: bf16 operands [F x Dp] (Dp multiple of 64, zero padded) + per-column (scale,bias)
 //   exact_flag (device int): 1 -> operand = bf16(raw), scale = invn ; 0 -> operand = bf16(xn), scale = 1
 //   bias_mode: 0 -> bias 0 ; 1 -> bias = -sq/2 (SSD on un-normalised rows)
@@ -152,6 +155,7 @@ struct aps_tc_problem {
   float* cand_score;    // same shape: score (dot*scale+bias), -inf for empty slots
   float* dump;          // optional [ (q1-q0) x (t1-t0) ] raw scores (tests only), else nullptr
   const int32_t* nrows_dev = nullptr;  // second pass: Qb holds *nrows_dev gathered rows (q0 = 0, q1 = upper bound)
+  int operand_fp16 = 0;                // 1: Qb / Tb hold fp16 rows (pairwise path, |x| <= 2): kind::f16 with F16 inputs, F32 accumulate
   const int32_t* exact_flag = nullptr; // device flag "operands are exact in bf16" (K1): when given, the first pass keeps 6
                                        // candidates per list instead of 8 for exact operands (lists stay 8 wide, two
                                        // entries empty): eps is ~1e-4 then, and 6 still prove a top-5
@@ -189,6 +193,8 @@ struct aps_pair_tables {
   // is then bounded by the list's third entry -- or by its second when the two best share a segment -- and eps
   // grows by the 7 key bits.
   int tile_mode;
+  // 1: the tensor pass ran on fp16 operands (10-bit mantissa): the operand-rounding term of eps is 2.0e-3 instead of 7.9e-3
+  int operand_fp16;
 };
 
 // aps_pair_screen.cu : pairwise stage 1 -- fp16 tensor-core screen of every (query row, train image); see the file header
@@ -206,6 +212,7 @@ struct aps_pair_screen_tables {   // per image pair p of the launch (device arra
 // sum to fp16 per K = 16 instruction (2^-10 each, Dp / 16 of them), margin.  Checked against measurements by
 // tests/test_gpu_pair_screen.py.
 __host__ __device__ inline float aps_pair_screen_dot_eps(int Dp) { return (float)(Dp / 16) * 9.765625e-4f + 1.5e-3f; }
+int aps_k_fill_f32(cudaStream_t s, float* dst, int64_t n, float v);
 int aps_k_prepare_operands_f16(cudaStream_t s, const float* src, int64_t F, int D, int Dp, void* xh);
 int aps_k_image_sq_bounds(cudaStream_t s, const float* sq, const int64_t* d_img_off, int n, float2* out);
 int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh, int64_t F, int Dp, const aps_pair_screen_tables& t,

@@ -39,12 +39,14 @@ __device__ __forceinline__ float ssd_seq(const float* __restrict__ a, const floa
 
 // error bound of the approximate distance; flags: [0] operands exact in bf16, [1] bits of max|sq-1|,
 // [2] bits of max sq.  See DESIGN.md "Exactness of the tensor-core search".
-__device__ __forceinline__ float eps_bound(const int32_t* __restrict__ flags, int bias_mode) {
-  const bool exact = flags[0] != 0;
+__device__ __forceinline__ float eps_bound(const int32_t* __restrict__ flags, int bias_mode, bool operand_fp16 = false) {
+  const bool exact = flags[0] != 0 && !operand_fp16;  // flags[0] speaks about bf16; fp16 operands always take their bound
   const float dev = __int_as_float(flags[1]);
   const float maxsq = fmaxf(__int_as_float(flags[2]), 1.0f);
   const float slop = 1.0e-4f * maxsq;                     // fp32 evaluation-order differences
-  const float bf = exact ? 0.0f : 7.9e-3f * maxsq;        // 2 * 2^-8 * (1+2^-9)^2 * |a||b|
+  // operand rounding: bf16 2 * 2^-8 * (1+2^-9)^2 * |a||b| ; fp16 2 * 2^-10 * (1+2^-11)^2 * |a||b| (values below the fp16
+  // normal range lose at most 2^-25 each: inside `slop` for |x| <= 2)
+  const float bf = exact ? 0.0f : (operand_fp16 ? 2.0e-3f : 7.9e-3f) * maxsq;
   return bias_mode ? (slop + bf) : (slop + bf + dev);     // normalised rows: |sq_b - 1| <= dev is ignored by the score
 }
 

@@ -125,6 +125,7 @@ struct KParams {
   int cand_stride;                // entries per list in cand_idx / cand_score (>= KCT; the rest is written empty)
   const int32_t* variant_flag;    // when set: this launch runs only if (*variant_flag != 0) == variant_want
   int variant_want;
+  uint32_t idesc;                 // tcgen05 instruction descriptor (bf16 or fp16 operands, f32 accumulators)
   const int32_t* nrows_dev;       // second-pass mode: the query matrix holds *nrows_dev gathered rows (device-side
                                   // count); every unit is split into tail_seg column segments
 };
@@ -273,7 +274,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t bs = 0, bph = 0, aph = 0, cs = 0, cph = 0;
       for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
         const Unit x = get_unit(P, u);
@@ -304,9 +305,9 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     // ===================================== MMA issuers =======================================
     // One issuing thread per row block: each waits only for ITS epilogue group's accumulator slot, so a
     // slow group (insertion-heavy tile) does not stall the other group's MMAs (no head-of-line blocking).
-    if (lane == 0) {
+    if (elect_one()) {
       const int r = warp - 1;
-      const uint32_t idesc = make_idesc_bf16(TM, TN);
+      const uint32_t idesc = P.idesc;
       const uint32_t a_addr = smem_u32(smem_a + r * a_bytes);
       uint32_t bs = 0, bph = 0, aph = 0, tcount = 0;
       for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -718,6 +719,7 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.cand_stride = KC;
   P.variant_flag = nullptr;
   P.variant_want = 0;
+  P.idesc = make_idesc_bf16(TM, TN);
   P.nrows_dev = p.nrows_dev;
   if (p.nrows_dev) {  // second pass: every unit in MAX_SEG column segments (more candidate lists per row)
     P.units_full = 0;
@@ -795,10 +797,12 @@ int aps_k_knn_tc_units(cudaStream_t s, int sm_count, const aps_tc_problem& p, co
   }
   if (n_units <= 0) return APS_OK;
   CUtensorMap map_q, map_t;
-  APS_TRY(make_map(&map_q, p.Qb, p.Fq_total, p.Dp, TM));
-  APS_TRY(make_map(&map_t, p.Tb, p.Ft_total, p.Dp, TN));
+  const CUtensorMapDataType dt = p.operand_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  APS_TRY(make_map(&map_q, p.Qb, p.Fq_total, p.Dp, TM, dt));
+  APS_TRY(make_map(&map_t, p.Tb, p.Ft_total, p.Dp, TN, dt));
   KParams P;
   memset(&P, 0, sizeof P);
+  P.idesc = p.operand_fp16 ? make_idesc_f16_f32acc(TM, TN) : make_idesc_bf16(TM, TN);
   P.nrows_dev = nullptr;
   P.dp = p.Dp;
   P.nslot = 1;

@@ -55,6 +55,7 @@ struct SParams {
   uint32_t* dump;       // tests: raw accumulator registers [entries][dump_tiles][64], else nullptr
   int dump_tiles;
   uint32_t idesc;       // tcgen05 instruction descriptor (kind::f16: F16 operands, F16 accumulators)
+  int variant;          // experiments (APS_SCREEN_VARIANT): 1 = epilogue skips the TMEM loads, 2 = polling waits
 };
 
 // 64 TMEM columns of 16-bit accumulators -> 32 registers of two packed fp16 (columns 2j, 2j+1 -> register j)
@@ -83,6 +84,19 @@ static __device__ __forceinline__ void tmem_wait_ld2(uint32_t (&a)[32], uint32_t
                     "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
                :
                : "memory");
+}
+static __device__ __forceinline__ void mbar_poll(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 static __device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b) {
   uint32_t d;
@@ -124,7 +138,7 @@ k_pair_screen(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t bs = 0, bph = 0, ucount = 0;
       for (int64_t u = blockIdx.x; u < P.n_units; u += gridDim.x, ++ucount) {
         const aps_tc_unit x = P.units[u];
@@ -147,7 +161,9 @@ k_pair_screen(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp <= RB) {
     // ===================================== MMA issuers =======================================
-    if (lane == 0) {
+    // elect.sync instead of "lane == 0": the compiler then knows exactly one thread runs the loop and keeps the
+    // descriptors in uniform registers (a lane-id guard costs a ~20-instruction R2UR waterfall per tcgen05.mma)
+    if (elect_one()) {
       const int r = warp - 1;
       const uint32_t idesc = P.idesc;
       uint32_t bs = 0, bph = 0, tcount = 0, ucount = 0;
@@ -159,8 +175,8 @@ k_pair_screen(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int tl = x.t0 / TN, th = (x.t1 + TN - 1) / TN;
         for (int t = tl; t < th; ++t, ++tcount) {
           const uint32_t slot = (tcount % ACC_PHASES) * RB + r, acph = (tcount / ACC_PHASES) & 1;
-          mbar_wait(&bars->acc_empty[slot], acph ^ 1);
-          mbar_wait(&bars->b_full[bs], bph);
+          if (P.variant & 2) { mbar_poll(&bars->acc_empty[slot], acph ^ 1); mbar_poll(&bars->b_full[bs], bph); }
+          else { mbar_wait(&bars->acc_empty[slot], acph ^ 1); mbar_wait(&bars->b_full[bs], bph); }
           tc_fence_after();
           const uint32_t b_addr = smem_u32(smem_b + bs * b_bytes);
           const uint32_t d_tmem = tmem_base + slot * ACC_COLS;
@@ -189,13 +205,18 @@ k_pair_screen(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint32_t m[4] = {NEG2, NEG2, NEG2, NEG2};   // class maxima: m[i].lo = columns == 2i (mod 8), m[i].hi = 2i+1 (mod 8)
       for (int t = tl; t < th; ++t, ++tcount) {
         const uint32_t slot = (tcount % ACC_PHASES) * RB + grp, acph = (tcount / ACC_PHASES) & 1;
-        mbar_wait(&bars->acc_full[slot], acph);
+        if (P.variant & 2) mbar_poll(&bars->acc_full[slot], acph); else mbar_wait(&bars->acc_full[slot], acph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * ACC_COLS;
         uint32_t va[32], vb[32];
-        tmem_ld64p(taddr, va);
-        tmem_ld64p(taddr + 64, vb);
-        tmem_wait_ld2(va, vb);
+        if (P.variant & 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { va[j] = NEG2; vb[j] = NEG2; }
+        } else {
+          tmem_ld64p(taddr, va);
+          tmem_ld64p(taddr + 64, vb);
+          tmem_wait_ld2(va, vb);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);   // registers hold the tile: the slot can be refilled
@@ -260,6 +281,10 @@ __global__ void k_prepare_operands_f16(const float* __restrict__ src, int64_t F,
     for (int j = 0; j < 8; ++j) v[j] = __float2half_rn(c0 + j < D ? src[r * D + c0 + j] : 0.0f);
     *reinterpret_cast<uint4*>(xh + r * Dp + c0) = *reinterpret_cast<const uint4*>(v);
   }
+}
+
+__global__ void k_fill_f32(float* __restrict__ dst, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = v;
 }
 
 // per image: (min, max) of the squared row norms
@@ -338,6 +363,13 @@ int aps_k_prepare_operands_f16(cudaStream_t s, const float* src, int64_t F, int 
   return APS_OK;
 }
 
+int aps_k_fill_f32(cudaStream_t s, float* dst, int64_t n, float v) {
+  if (n <= 0) return APS_OK;
+  k_fill_f32<<<(unsigned)aps_min64(aps_ceil_div(n, 256), 148 * 8), 256, 0, s>>>(dst, n, v);
+  APS_LAUNCHED();
+  return APS_OK;
+}
+
 int aps_k_image_sq_bounds(cudaStream_t s, const float* sq, const int64_t* d_img_off, int n, float2* out) {
   if (n == 0) return APS_OK;
   k_image_sq_bounds<<<n, 256, 0, s>>>(sq, d_img_off, out);
@@ -368,6 +400,8 @@ int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh, int64_t F, i
   P.dump_tiles = dump_tiles;
   P.idesc = make_idesc_f16_f16acc(TM, TN);
   if (const char* e = getenv("APS_SCREEN_IDESC")) P.idesc = (uint32_t)strtoul(e, nullptr, 16);   // experiments only
+  P.variant = 0;
+  if (const char* e = getenv("APS_SCREEN_VARIANT")) P.variant = atoi(e);
   const size_t smem = 1024 + (size_t)P.a_bufs * RB * TM * Dp * 2 + (size_t)P.b_stages * TN * Dp * 2 + sizeof(Bars);
   APS_CUDA(cudaFuncSetAttribute(k_pair_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);

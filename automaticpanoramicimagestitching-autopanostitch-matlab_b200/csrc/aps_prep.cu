@@ -63,15 +63,23 @@ int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const flo
 // pass 1.  One block = RB rows staged in shared memory; the per-row sums are SEQUENTIAL float32
 // (one thread per row, one rounding per operation, no FMA) so that the normalised values carry
 // the same bits as the oracle's / the reference's single-precision arithmetic.
+// img_off != nullptr: blockIdx.y = image, rows [img_off[y], img_off[y+1]) with its own flag words flags + 8*y (the
+// per-image magnitude test of the pairwise path in ONE launch)
 __global__ void k_prepare_norm(const float* __restrict__ raw, int64_t F, int D, int RB, int norm_mode,
                                float* __restrict__ xn, float* __restrict__ sq, float* __restrict__ invn,
-                               int32_t* __restrict__ flags) {
+                               int32_t* __restrict__ flags, const int64_t* __restrict__ img_off) {
   extern __shared__ float tile[];  // [RB][D+1]
   __shared__ float s_norm[64];
   __shared__ int s_exact;
   __shared__ int s_maxdev, s_maxsq, s_maxabs;
   const int ld = D + 1;
-  const int64_t r0 = (int64_t)blockIdx.x * RB;
+  int64_t r0 = (int64_t)blockIdx.x * RB;
+  if (img_off) {
+    F = img_off[blockIdx.y + 1];
+    r0 += img_off[blockIdx.y];
+    flags += 8 * blockIdx.y;
+    if (r0 >= F) return;
+  }
   const int nr = (int)min((int64_t)RB, F - r0);
   if (threadIdx.x == 0) {
     s_exact = 1;
@@ -147,7 +155,23 @@ int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int n
     return APS_ERR_DIM;
   }
   size_t smem = (size_t)RB * (D + 1) * sizeof(float);
-  k_prepare_norm<<<(unsigned)aps_ceil_div(F, RB), 256, smem, s>>>(raw, F, D, RB, norm_mode, xn, sq, invn, flags);
+  k_prepare_norm<<<(unsigned)aps_ceil_div(F, RB), 256, smem, s>>>(raw, F, D, RB, norm_mode, xn, sq, invn, flags, nullptr);
+  APS_LAUNCHED();
+  return APS_OK;
+}
+
+int aps_k_prepare_norm_images(cudaStream_t s, const float* raw, const int64_t* d_img_off, int n, int64_t maxcount, int D,
+                              int norm_mode, float* xn, float* sq, float* invn, int32_t* flags) {
+  if (n == 0 || maxcount == 0) return APS_OK;
+  int RB = 11000 / (D + 1);
+  if (RB > 64) RB = 64;
+  if (RB < 1) {
+    aps_set_error(APS_ERR_DIM, "", "descriptor dimension %d too large", D);
+    return APS_ERR_DIM;
+  }
+  size_t smem = (size_t)RB * (D + 1) * sizeof(float);
+  dim3 grid((unsigned)aps_ceil_div(maxcount, RB), (unsigned)n);
+  k_prepare_norm<<<grid, 256, smem, s>>>(raw, 0, D, RB, norm_mode, xn, sq, invn, flags, d_img_off);
   APS_LAUNCHED();
   return APS_OK;
 }

@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   const int ncand = nseg * kcand;
   // tile mode: keys carry the column in their 7 low mantissa bits: |key - score| <= 2^-16 |score| <= 1.5e-5 * (|a.b| + |bias|)
   // <= 2.3e-5 * max|x|^2, times |beta| = 2
-  const float eps = eps_bound(flags, bias_mode) +
+  const float eps = eps_bound(flags, bias_mode, pt.operand_fp16 != 0) +
                     (pt.tile_mode ? 5.0e-5f * fmaxf(__int_as_float(flags[2]), 1.0f) : 0.0f);
-  const bool exact = flags[0] != 0;
+  const bool exact = flags[0] != 0 && !pt.operand_fp16;  // (bf16 path) operand = raw row, per-row scale: beta carries 1/norm; pairwise: invn = 1
   const float a2 = sqQ[q];
   // s~ = alpha + beta*score
   const float alpha = bias_mode ? a2 : __fadd_rn(a2, 1.0f);

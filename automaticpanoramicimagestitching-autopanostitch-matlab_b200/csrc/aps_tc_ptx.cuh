@@ -14,6 +14,18 @@ constexpr int KSLAB = 64;      // 16-bit elements per 128-byte swizzle row
 // ---- PTX helpers -------------------------------------------------------------------------------
 static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One thread of a fully active warp.  Guarding the single-thread TMA / tcgen05.mma issue loops with elect.sync instead of
+// "lane == 0" lets the compiler keep descriptors and addresses in uniform registers; a lane-id guard makes it wrap
+// every UTCHMMA / UTMALDG in a ~20-instruction R2UR "waterfall" loop (profiles/r2_ncu_history.txt).
+static __device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 static __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -129,6 +141,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 
+// instruction descriptor: kind::f16, A/B = F16, D = F32
+__host__ __device__ constexpr uint32_t make_idesc_f16_f32acc(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // instruction descriptor: kind::f16, A/B = F16, D = F16 (packed half accumulators), both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc_f16_f16acc(int M, int N) {
   return (0u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

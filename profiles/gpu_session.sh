@@ -11,6 +11,11 @@ for what in "$@"; do
     ref)     timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; head -c 1500 gpurun_out/bench_ref.json;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?";;
     launches_c5) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_c5.csv python profiles/prof_pairwise.py 300 4096 1 > gpurun_out/launches_c5.log 2>&1; echo "launches_c5 rc=$?"; tail -2 gpurun_out/launches_c5.log;;
+    ncu_screen) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pair_screen$ -c 1 \
+               --metrics sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor_subpipe_hmma.sum,sm__mem_tensor_reads.sum,sm__mem_tensor_writes.sum,sm__inst_executed_pipe_tmem.sum \
+               -o gpurun_out/prof_screen -f python profiles/prof_pairwise.py 120 4096 1 > gpurun_out/ncu_screen.log 2>&1; echo "ncu_screen rc=$?"; tail -3 gpurun_out/ncu_screen.log;;
+    pairtests) timeout 900 python -m pytest tests -m gpu -x -q -k "pair or match_features or screen or c5 or gateway_batched" > gpurun_out/pairtests.log 2>&1; echo "pairtests rc=$?"; tail -5 gpurun_out/pairtests.log;;
+    bench_c5) timeout 400 python bench.py --config c5 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "bench c5 rc=$?"; head -c 2200 gpurun_out/bench_c5.json; tail -3 gpurun_out/bench_c5.err;;
     ncu_tc)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_knn_tc -s 2 -c 1 \
                --metrics sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor_subpipe_hmma.sum,sm__mem_tensor_reads.sum,sm__mem_tensor_writes.sum,sm__inst_executed_pipe_tmem.sum \
                -o gpurun_out/prof_tc -f python profiles/prof_step.py 20 8192 2 2 > gpurun_out/ncu_tc.log 2>&1; echo "ncu_tc rc=$?"; tail -3 gpurun_out/ncu_tc.log;;
