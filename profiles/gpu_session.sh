@@ -7,6 +7,8 @@ for what in "$@"; do
     tests)   timeout 900 python -m pytest tests -m gpu -x -q --durations=15 > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -25 gpurun_out/tests.log;;
     bench)   for c in c2 c3 c4 c5; do
                timeout 400 python bench.py --config $c > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; echo "bench $c rc=$?"; head -c 1800 gpurun_out/bench_$c.json; tail -3 gpurun_out/bench_$c.err; done;;
+    record)  for c in c2 c3 c4 c5 c6; do
+               timeout 400 python bench.py --config $c > gpurun_out/r2_bench_${c}_1gpu.json 2> gpurun_out/r2_bench_${c}_1gpu.err; echo "bench $c rc=$?"; head -c 700 gpurun_out/r2_bench_${c}_1gpu.json; echo; tail -2 gpurun_out/r2_bench_${c}_1gpu.err; done;;
     bench2)  timeout 400 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench rc=$?"; head -c 2500 gpurun_out/bench_c2.json; tail -3 gpurun_out/bench_c2.err;;
     ref)     timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; head -c 1500 gpurun_out/bench_ref.json;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?";;
