@@ -90,6 +90,7 @@ def lib():
         "aps_ctx_set_float_engine": (i32, [vp, i32]),
         "aps_ctx_set_pairwise_epilogue": (i32, [vp, i32]),
         "aps_ctx_last_stats": (i32, [vp, C.POINTER(i64)]),
+        "aps_ctx_first_pass_unproven": (i64, [vp]),
         "aps_ctx_set_pairwise_screen": (i32, [vp, i32]),
         "aps_ctx_pairwise_stats": (i32, [vp, C.POINTER(i64)]),
         "aps_ctx_enable_timing": (i32, [vp, i32]),
@@ -205,6 +206,10 @@ class Context:
         check(lib().aps_ctx_last_stats(self._h, a))
         return {"rows": a[0], "fallback_rows": a[1], "engine": {0: "none", 1: "exact", 2: "tcgen05"}.get(a[2], a[2]),
                 "bf16_exact_operands": bool(a[3])}
+
+    def first_pass_unproven(self):
+        """Rows the first completeness proof of the last float search left to the second tensor pass."""
+        return int(lib().aps_ctx_first_pass_unproven(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

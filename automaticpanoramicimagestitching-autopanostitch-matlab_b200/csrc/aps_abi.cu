@@ -145,6 +145,13 @@ extern "C" int aps_ctx_pairwise_stats(aps_ctx* c, int64_t stats[4]) {
   return APS_OK;
 }
 
+extern "C" int64_t aps_ctx_first_pass_unproven(aps_ctx* c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  return c->h_flags[34];
+}
+
 extern "C" int aps_ctx_last_stats(aps_ctx* c, int64_t stats[4]) {
   if (!c || !stats) APS_FAIL(APS_ERR_ARGS, "", "bad args");
   APS_CUDA(cudaSetDevice(c->device));
@@ -239,6 +246,7 @@ struct FloatSide {          // one prepared descriptor set
   const float4* tile_bounds = nullptr;
   const int32_t* perm = nullptr;  // sorted position -> original row (nullptr: identity)
   int64_t N = 0;
+  int fp16 = 0;                   // operand rows are fp16 (flags[0] = exact in fp16) instead of bf16
 };
 
 static bool tc_wanted(const aps_ctx* c, int D, int64_t nq, int64_t nt, int k) {
@@ -249,6 +257,26 @@ static bool tc_wanted(const aps_ctx* c, int D, int64_t nq, int64_t nt, int k) {
   if (!aps_k_knn_tc_supported(Dp)) return false;
   if (c->float_engine == 2) return true;
   return nq * nt >= (int64_t)1 << 22;  // tiny problems: launch-bound either way, stay exact
+}
+
+// Rows the first proof left open: a SHORT list goes straight to the exact engine (its train range is split over 32
+// CTAs per 8 rows, aps_knn_exact.cu) -- a second tensor pass over a handful of rows keeps only 4 CTAs busy for a whole
+// sweep; a LONG list (real-valued descriptors with tightly packed neighbours) takes the 32-candidate tensor pass.
+__global__ void k_route_unproven(int32_t* __restrict__ fb, int32_t* __restrict__ n1, int32_t* __restrict__ fb2,
+                                 int32_t* __restrict__ n2, int short_list, int32_t* __restrict__ report) {
+  __shared__ int n;
+  if (threadIdx.x == 0) {
+    n = *n1;
+    *report = n;
+  }
+  __syncthreads();
+  if (n > short_list) return;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) fb2[i] = fb[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *n2 = n;
+    *n1 = 0;
+  }
 }
 
 // metric 0: FLANN-order squared L2 (global path) ; metric 1: SSD (pairwise path)
@@ -293,7 +321,11 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   p.cand_idx = cidx.p;
   p.cand_score = cscore.p;
   p.dump = nullptr;
-  p.exact_flag = flags_dev;  // exact bf16 operands (integer SIFT): 6 candidates per list are enough to prove a top-5
+  p.operand_fp16 = (Q.fp16 && T.fp16) ? 2 : 0;
+  aps_pair_tables gpt;       // global searches: only the operand kind travels in here (eoff == nullptr)
+  memset(&gpt, 0, sizeof gpt);
+  gpt.operand_fp16 = p.operand_fp16;
+  p.exact_flag = flags_dev;  // exact operands (integer SIFT): 6 candidates per list are enough to prove a top-5
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (c->timing) {
     APS_CUDA(cudaEventCreate(&ev0));
@@ -308,13 +340,13 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   const int64_t rows_full = nslot > 1 ? aps_k_knn_tc_full_rows(c->sm_count, nq, t0, t1) : 0;
   if (rows_full > 0)
     APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, rows_full, t0, 1, kcand, cidx.p,
-                         cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq, nullptr,
-                         nullptr, nullptr, T.perm, nslot * kcand));
+                         cscore.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq, &gpt,
+                         nullptr, nullptr, T.perm, nslot * kcand, /*kcap_exact*/ 6));
   if (nq > rows_full)
     APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0 + rows_full, nq - rows_full, t0, nslot,
                          kcand, cidx.p + (size_t)rows_full * nslot * kcand, cscore.p + (size_t)rows_full * nslot * kcand,
-                         flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq, nullptr, nullptr,
-                         nullptr, T.perm));
+                         flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb.p, fb.p + nq, &gpt, nullptr,
+                         nullptr, T.perm, 0, /*kcap_exact*/ 6));
   // Rows that could not be proven complete (device-side list, no host round trip) get a SECOND tensor pass with
   // 4 column segments = 32 candidates per row: with inexact (non bf16-representable) operands the error bound
   // is ~0.016 in squared distance and 8 candidates often do not reach beyond it; 32 usually do.
@@ -323,6 +355,10 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   APS_TRY(fb2.alloc((size_t)nq + 1, c->stream));
   APS_CUDA(cudaMemsetAsync(fb2.p + nq, 0, sizeof(int32_t), c->stream));
   if (nslot2 > nslot) {
+    k_route_unproven<<<1, 256, 0, c->stream>>>(fb.p, fb.p + nq, fb2.p, fb2.p + nq, /*short_list*/ 2048,
+                                               c->d_scratch_flags + 8);
+    APS_LAUNCHED();
+    APS_CUDA(cudaMemcpyAsync(c->h_flags + 34, c->d_scratch_flags + 8, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     DevBuf<__nv_bfloat16> qb2;
     DevBuf<uint32_t> cidx2;
     DevBuf<float> cscore2;
@@ -341,13 +377,12 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
     p2.nrows_dev = fb.p + nq;
     APS_TRY(aps_k_knn_tc(c->stream, c->sm_count, p2, nullptr, nullptr));
     APS_TRY(aps_k_rerank(c->stream, Q.xn, Q.sq, Q.invn, T.xn, T.sq, D, metric, q0, nq, t0, nslot2, kcand, cidx2.p,
-                         cscore2.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb2.p, fb2.p + nq, nullptr,
+                         cscore2.p, flags_dev, bias_mode, flags_dev, k, out_row0, idx, dist, fb2.p, fb2.p + nq, &gpt,
                          fb.p, fb.p + nq, T.perm));
     // still unproven: exact CUDA-core search
     APS_TRY(aps_k_knn_exact(c->stream, Q.xn, Q.sq, fb2.p, fb2.p + nq, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
                             out_row0, idx, dist));
     APS_CUDA(cudaMemcpyAsync(c->h_flags + 32, fb2.p + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    APS_CUDA(cudaMemcpyAsync(c->h_flags + 34, fb.p + nq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   } else {
     APS_TRY(aps_k_knn_exact(c->stream, Q.xn, Q.sq, fb.p, fb.p + nq, q0, nq, T.xn, T.sq, t0, t1, D, k, metric,
                             out_row0, idx, dist));
@@ -369,6 +404,7 @@ struct FloatSet {
   DevBuf<int32_t> perm, sort_scratch;
   DevBuf<float4> tile_bounds;
   bool sorted = false;
+  bool fp16 = false;  // tensor operands in fp16: 4x smaller rounding term than bf16; needs |x| inside the fp16 range
   int64_t N = 0;
   int D = 0;
   FloatSide side() const {
@@ -386,6 +422,7 @@ struct FloatSet {
     s.tile_bounds = tile_bounds.p;
     s.perm = sorted ? perm.p : nullptr;
     s.N = N;
+    s.fp16 = fp16 ? 1 : 0;
     return s;
   }
 };
@@ -434,14 +471,14 @@ static int floatset_prepare(aps_ctx* c, FloatSet& fs, int norm_mode, bool tensor
   if (fs.N == 0) return APS_OK;
   if (norm_mode != APS_NORM_NONE && !fs.xn.p) APS_TRY(fs.xn.alloc((size_t)fs.N * fs.D, c->stream));
   float* xn = (norm_mode != APS_NORM_NONE) ? fs.xn.p : fs.raw.p;
-  APS_TRY(aps_k_prepare_norm(c->stream, fs.raw.p, fs.N, fs.D, norm_mode, xn, fs.sq.p, fs.invn.p, fs.flags.p));
+  APS_TRY(aps_k_prepare_norm(c->stream, fs.raw.p, fs.N, fs.D, norm_mode, xn, fs.sq.p, fs.invn.p, fs.flags.p, fs.fp16));
   if (tensor) {
     const int Dp = (fs.D + 63) / 64 * 64;
     APS_TRY(fs.xb.alloc((size_t)fs.N * Dp, c->stream));
     APS_TRY(fs.colscale.alloc((size_t)fs.N + 256, c->stream));
     APS_TRY(fs.colbias.alloc((size_t)fs.N + 256, c->stream));  // +256: whole-tile bulk loads
     APS_TRY(aps_k_prepare_operands(c->stream, fs.raw.p, xn, fs.sq.p, fs.invn.p, fs.N, fs.D, Dp, fs.flags.p,
-                                   bias_mode, fs.xb.p, fs.colscale.p, fs.colbias.p));
+                                   bias_mode, fs.xb.p, fs.colscale.p, fs.colbias.p, fs.fp16));
     APS_TRY(floatset_finish_train(c, fs, sort));
   }
   return APS_OK;
@@ -726,6 +763,7 @@ extern "C" int aps_gplan_create(aps_ctx* c, const int64_t* counts, int n, int D,
   auto A = [&](int r) { if (rc == APS_OK) rc = r; };
   if (dtype == APS_F32) {
     p->tensor = tc_wanted(c, D, F, F, k);
+    p->fs.fp16 = true;  // rows are L2-normalised (|x| <= 1) or, when exact, small integers: always inside the fp16 range
     A(floatset_alloc(c, p->fs, F, D));
   } else {
     p->nb16 = (D + 15) / 16 * 16;

@@ -99,17 +99,18 @@ int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const flo
 // pass 1: xn = normalised rows (norm_mode), sq[r] = sum(xn^2) (sequential f32), invn[r] = 1/norm (1 when
 // norm_mode NONE), flags[0] &= all raw values exactly representable in bf16, flags[1] = max bits |sq-1|,
 // flags[2] = max bits sq, flags[3] = max bits |raw| (for the max|.|>2 test of matchFeaturesScratch.m:105)
+// fp16 = 1: flags[0] speaks about exact representability in fp16 (the operand type the caller will build)
 int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int norm_mode, float* xn, float* sq,
-                       float* invn, int32_t* flags);
+                       float* invn, int32_t* flags, int fp16 = 0);
 // the same for every image of a pooled matrix in one launch: image i = rows [img_off[i], img_off[i+1]), flags + 8*i
 int aps_k_prepare_norm_images(cudaStream_t s, const float* raw, const int64_t* d_img_off, int n, int64_t maxcount, int D,
-                              int norm_mode, float* xn, float* sq, float* invn, int32_t* flags);
+                              int norm_mode, float* xn, float* sq, float* invn, int32_t* flags, int fp16 = 0);
 // pass 2: bf16 operands [F x Dp] (Dp multiple of 64, zero padded) + per-column (scale,bias)
 //   exact_flag (device int): 1 -> operand = bf16(raw), scale = invn ; 0 -> operand = bf16(xn), scale = 1
 //   bias_mode: 0 -> bias 0 ; 1 -> bias = -sq/2 (SSD on un-normalised rows)
 int aps_k_prepare_operands(cudaStream_t s, const float* raw, const float* xn, const float* sq, const float* invn,
                            int64_t F, int D, int Dp, const int32_t* exact_flag, int bias_mode, __nv_bfloat16* xb,
-                           float* colscale, float* colbias);
+                           float* colscale, float* colbias, int fp16 = 0);  // fp16 = 1: the rows are written as fp16
 
 // train-side view of the tensor kernel (aps_prep.cu)
 int aps_k_sort_train_by_scale(cudaStream_t s, const __nv_bfloat16* xb, const float* colscale, const float* colbias,
@@ -155,7 +156,8 @@ struct aps_tc_problem {
   float* cand_score;    // same shape: score (dot*scale+bias), -inf for empty slots
   float* dump;          // optional [ (q1-q0) x (t1-t0) ] raw scores (tests only), else nullptr
   const int32_t* nrows_dev = nullptr;  // second pass: Qb holds *nrows_dev gathered rows (q0 = 0, q1 = upper bound)
-  int operand_fp16 = 0;                // 1: Qb / Tb hold fp16 rows (pairwise path, |x| <= 2): kind::f16 with F16 inputs, F32 accumulate
+  int operand_fp16 = 0;                // != 0: Qb / Tb hold fp16 rows (|x| within the fp16 range): kind::f16 with F16 inputs,
+                                       // F32 accumulate.  1 = operands never treated as exact, 2 = flags[0] says whether they are
   const int32_t* exact_flag = nullptr; // device flag "operands are exact in bf16" (K1): when given, the first pass keeps 6
                                        // candidates per list instead of 8 for exact operands (lists stay 8 wide, two
                                        // entries empty): eps is ~1e-4 then, and 6 still prove a top-5
@@ -193,7 +195,8 @@ struct aps_pair_tables {
   // is then bounded by the list's third entry -- or by its second when the two best share a segment -- and eps
   // grows by the 7 key bits.
   int tile_mode;
-  // 1: the tensor pass ran on fp16 operands (10-bit mantissa): the operand-rounding term of eps is 2.0e-3 instead of 7.9e-3
+  // != 0: the tensor pass ran on fp16 operands (10-bit mantissa): the operand-rounding term of eps is 2.0e-3 instead of
+  // 7.9e-3.  1 = never exact (pairwise: normalised rows are rounded), 2 = flags[0] tells (global path, set by K1)
   int operand_fp16;
 };
 
@@ -230,7 +233,8 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
                  int32_t* fb_count, const aps_pair_tables* pairs = nullptr, const int32_t* row_map = nullptr,
-                 const int32_t* nrows_dev = nullptr, const int32_t* perm = nullptr, int cand_stride = 0);
+                 const int32_t* nrows_dev = nullptr, const int32_t* perm = nullptr, int cand_stride = 0,
+                 int kcap_exact = 0);  // > 0: lists hold only this many entries when flags[0] (exact operands) is set
 
 // K5 aps_filter.cu
 int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, int k, int64_t q0, int64_t q1,

@@ -39,8 +39,10 @@ __device__ __forceinline__ float ssd_seq(const float* __restrict__ a, const floa
 
 // error bound of the approximate distance; flags: [0] operands exact in bf16, [1] bits of max|sq-1|,
 // [2] bits of max sq.  See DESIGN.md "Exactness of the tensor-core search".
-__device__ __forceinline__ float eps_bound(const int32_t* __restrict__ flags, int bias_mode, bool operand_fp16 = false) {
-  const bool exact = flags[0] != 0 && !operand_fp16;  // flags[0] speaks about bf16; fp16 operands always take their bound
+// operand_kind: 0 bf16 (flags[0] = rows exact in bf16), 1 fp16 never exact, 2 fp16 (flags[0] = rows exact in fp16)
+__device__ __forceinline__ float eps_bound(const int32_t* __restrict__ flags, int bias_mode, int operand_kind = 0) {
+  const bool operand_fp16 = operand_kind != 0;
+  const bool exact = flags[0] != 0 && operand_kind != 1;
   const float dev = __int_as_float(flags[1]);
   const float maxsq = fmaxf(__int_as_float(flags[2]), 1.0f);
   const float slop = 1.0e-4f * maxsq;                     // fp32 evaluation-order differences

@@ -694,8 +694,9 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
     return APS_ERR_ARGS;
   }
   CUtensorMap map_q, map_t;
-  APS_TRY(make_map(&map_q, p.Qb, p.Fq_total, p.Dp, TM));
-  APS_TRY(make_map(&map_t, p.Tb, p.Ft_total, p.Dp, TN));
+  const CUtensorMapDataType dt = p.operand_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  APS_TRY(make_map(&map_q, p.Qb, p.Fq_total, p.Dp, TM, dt));
+  APS_TRY(make_map(&map_t, p.Tb, p.Ft_total, p.Dp, TN, dt));
   KParams P;
   P.q0 = p.q0; P.q1 = p.q1; P.t0 = p.t0; P.t1 = p.t1;
   P.dp = p.Dp;
@@ -719,7 +720,7 @@ int aps_k_knn_tc(cudaStream_t s, int sm_count, const aps_tc_problem& p, cudaEven
   P.cand_stride = KC;
   P.variant_flag = nullptr;
   P.variant_want = 0;
-  P.idesc = make_idesc_bf16(TM, TN);
+  P.idesc = p.operand_fp16 ? make_idesc_f16_f32acc(TM, TN) : make_idesc_bf16(TM, TN);
   P.nrows_dev = p.nrows_dev;
   if (p.nrows_dev) {  // second pass: every unit in MAX_SEG column segments (more candidate lists per row)
     P.units_full = 0;

@@ -7,6 +7,8 @@
 //
 // HBM-bound streaming kernels: every element is read once and written once; algorithmic bytes per
 // descriptor row = D*4 (read) + D*4 (xn) + Dp*2 (bf16 operand) + 16 (sq, invn, scale/bias).
+#include <cuda_fp16.h>
+
 #include "aps_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -67,7 +69,7 @@ int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const flo
 // per-image magnitude test of the pairwise path in ONE launch)
 __global__ void k_prepare_norm(const float* __restrict__ raw, int64_t F, int D, int RB, int norm_mode,
                                float* __restrict__ xn, float* __restrict__ sq, float* __restrict__ invn,
-                               int32_t* __restrict__ flags, const int64_t* __restrict__ img_off) {
+                               int32_t* __restrict__ flags, const int64_t* __restrict__ img_off, int fp16) {
   extern __shared__ float tile[];  // [RB][D+1]
   __shared__ float s_norm[64];
   __shared__ int s_exact;
@@ -97,7 +99,7 @@ __global__ void k_prepare_norm(const float* __restrict__ raw, int64_t F, int D, 
   for (int i = threadIdx.x, r = first_r, c = first_c; i < nr * D; i += blockDim.x) {
     float v = raw[(r0 + r) * D + c];
     tile[r * ld + c] = v;
-    exact &= (__bfloat162float(__float2bfloat16_rn(v)) == v);
+    exact &= fp16 ? (__half2float(__float2half_rn(v)) == v) : (__bfloat162float(__float2bfloat16_rn(v)) == v);
     maxabs = fmaxf(maxabs, fabsf(v));
     APS_NEXT_RC()
   }
@@ -146,7 +148,7 @@ __global__ void k_prepare_norm(const float* __restrict__ raw, int64_t F, int D, 
 }
 
 int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int norm_mode, float* xn, float* sq,
-                       float* invn, int32_t* flags) {
+                       float* invn, int32_t* flags, int fp16) {
   if (F == 0) return APS_OK;
   int RB = 11000 / (D + 1);
   if (RB > 64) RB = 64;
@@ -155,13 +157,13 @@ int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int n
     return APS_ERR_DIM;
   }
   size_t smem = (size_t)RB * (D + 1) * sizeof(float);
-  k_prepare_norm<<<(unsigned)aps_ceil_div(F, RB), 256, smem, s>>>(raw, F, D, RB, norm_mode, xn, sq, invn, flags, nullptr);
+  k_prepare_norm<<<(unsigned)aps_ceil_div(F, RB), 256, smem, s>>>(raw, F, D, RB, norm_mode, xn, sq, invn, flags, nullptr, fp16);
   APS_LAUNCHED();
   return APS_OK;
 }
 
 int aps_k_prepare_norm_images(cudaStream_t s, const float* raw, const int64_t* d_img_off, int n, int64_t maxcount, int D,
-                              int norm_mode, float* xn, float* sq, float* invn, int32_t* flags) {
+                              int norm_mode, float* xn, float* sq, float* invn, int32_t* flags, int fp16) {
   if (n == 0 || maxcount == 0) return APS_OK;
   int RB = 11000 / (D + 1);
   if (RB > 64) RB = 64;
@@ -171,7 +173,7 @@ int aps_k_prepare_norm_images(cudaStream_t s, const float* raw, const int64_t* d
   }
   size_t smem = (size_t)RB * (D + 1) * sizeof(float);
   dim3 grid((unsigned)aps_ceil_div(maxcount, RB), (unsigned)n);
-  k_prepare_norm<<<grid, 256, smem, s>>>(raw, 0, D, RB, norm_mode, xn, sq, invn, flags, d_img_off);
+  k_prepare_norm<<<grid, 256, smem, s>>>(raw, 0, D, RB, norm_mode, xn, sq, invn, flags, d_img_off, fp16);
   APS_LAUNCHED();
   return APS_OK;
 }
@@ -182,7 +184,7 @@ __global__ void k_prepare_operands(const float* __restrict__ raw, const float* _
                                    const float* __restrict__ sq, const float* __restrict__ invn, int64_t F, int D,
                                    int Dp, const int32_t* __restrict__ exact_flag, int bias_mode,
                                    __nv_bfloat16* __restrict__ xb, float* __restrict__ colscale,
-                                   float* __restrict__ colbias) {
+                                   float* __restrict__ colbias, int fp16) {
   const int exact = *exact_flag;
   const float* src = exact ? raw : xn;
   const int chunks = Dp / 8;
@@ -194,7 +196,9 @@ __global__ void k_prepare_operands(const float* __restrict__ raw, const float* _
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int c = c0 + j;
-      v[j] = __float2bfloat16_rn(c < D ? src[r * D + c] : 0.0f);
+      const float f = c < D ? src[r * D + c] : 0.0f;
+      if (fp16) reinterpret_cast<__half*>(v)[j] = __float2half_rn(f);   // same 16-bit storage, kind::f16 with F16 inputs
+      else v[j] = __float2bfloat16_rn(f);
     }
     *reinterpret_cast<uint4*>(xb + r * Dp + c0) = *reinterpret_cast<const uint4*>(v);
     if (c0 == 0) {
@@ -206,11 +210,11 @@ __global__ void k_prepare_operands(const float* __restrict__ raw, const float* _
 
 int aps_k_prepare_operands(cudaStream_t s, const float* raw, const float* xn, const float* sq, const float* invn,
                            int64_t F, int D, int Dp, const int32_t* exact_flag, int bias_mode, __nv_bfloat16* xb,
-                           float* colscale, float* colbias) {
+                           float* colscale, float* colbias, int fp16) {
   if (F == 0) return APS_OK;
   int64_t total = F * (Dp / 8);
   unsigned grid = (unsigned)aps_min64(aps_ceil_div(total, 256), 148 * 16);
-  k_prepare_operands<<<grid, 256, 0, s>>>(raw, xn, sq, invn, F, D, Dp, exact_flag, bias_mode, xb, colscale, colbias);
+  k_prepare_operands<<<grid, 256, 0, s>>>(raw, xn, sq, invn, F, D, Dp, exact_flag, bias_mode, xb, colscale, colbias, fp16);
   APS_LAUNCHED();
   return APS_OK;
 }

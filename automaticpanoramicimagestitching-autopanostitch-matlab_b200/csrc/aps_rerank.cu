@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
                                                 int32_t* __restrict__ fb_count, aps_pair_tables pt,
                                                 const int32_t* __restrict__ row_map,
                                                 const int32_t* __restrict__ nrows_dev,
-                                                const int32_t* __restrict__ perm, int cand_stride) {
+                                                const int32_t* __restrict__ perm, int cand_stride,
+                                                int kcap_exact) {
   constexpr int RPW = 32 / G;  // rows per warp
   if (nrows_dev && (int64_t)blockIdx.x * (blockDim.x >> 5) * RPW >= (int64_t)(*nrows_dev)) return;  // second pass: short list
   const int lane = threadIdx.x & 31, sub = lane / G, sl = lane % G;
@@ -61,9 +62,9 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   const int ncand = nseg * kcand;
   // tile mode: keys carry the column in their 7 low mantissa bits: |key - score| <= 2^-16 |score| <= 1.5e-5 * (|a.b| + |bias|)
   // <= 2.3e-5 * max|x|^2, times |beta| = 2
-  const float eps = eps_bound(flags, bias_mode, pt.operand_fp16 != 0) +
+  const float eps = eps_bound(flags, bias_mode, pt.operand_fp16) +
                     (pt.tile_mode ? 5.0e-5f * fmaxf(__int_as_float(flags[2]), 1.0f) : 0.0f);
-  const bool exact = flags[0] != 0 && !pt.operand_fp16;  // (bf16 path) operand = raw row, per-row scale: beta carries 1/norm; pairwise: invn = 1
+  const bool exact = flags[0] != 0 && pt.operand_fp16 != 1;  // (bf16 path) operand = raw row, per-row scale: beta carries 1/norm; pairwise: invn = 1
   const float a2 = sqQ[q];
   // s~ = alpha + beta*score
   const float alpha = bias_mode ? a2 : __fadd_rn(a2, 1.0f);
@@ -108,8 +109,12 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
       W = fminf(W, w);
     }
   } else {
+    // entries a list can hold: the tensor pass keeps only kcap_exact of the kcand slots when the operands are exact
+    // (aps_knn_tc.cu, variant chosen by the same device flag).  Slots beyond that capacity say nothing; an EMPTY slot
+    // inside the capacity means every column of the list's range is a candidate (W = +inf).
+    const int cap = (kcap_exact > 0 && flags[0] != 0) ? kcap_exact : kcand;
     for (int s = 0; s < nseg; ++s) {
-      float m = (sl >= s * kcand && sl < (s + 1) * kcand) ? sapx : -CUDART_INF_F;
+      float m = (sl >= s * kcand && sl < s * kcand + cap) ? sapx : -CUDART_INF_F;
 #pragma unroll
       for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o, G));
       W = fminf(W, m);
@@ -221,7 +226,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                  const uint32_t* cand_idx, const float* cand_score, const int32_t* exact_flag, int bias_mode,
                  const int32_t* flags, int k, int64_t out_row0, uint32_t* idx, float* dist, int32_t* fb_rows,
                  int32_t* fb_count, const aps_pair_tables* pairs, const int32_t* row_map, const int32_t* nrows_dev,
-                 const int32_t* perm, int cand_stride) {
+                 const int32_t* perm, int cand_stride, int kcap_exact) {
   (void)exact_flag;
   if (nq == 0) return APS_OK;
   if (nseg * kcand > 32) {
@@ -242,7 +247,7 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
                                                                        nseg, kcand, cand_idx, cand_score, flags,     \
                                                                        bias_mode, k, out_row0, idx, dist, fb_rows,  \
                                                                        fb_count, pt, row_map, nrows_dev, perm,       \
-                                                                       cand_stride)
+                                                                       cand_stride, kcap_exact)
   if (ncand <= 8) APS_RERANK(8);
   else if (ncand <= 16) APS_RERANK(16);
   else APS_RERANK(32);

@@ -404,7 +404,8 @@ def run_ours(args, rank, world, local_rank):
                                 f"all-gather; e2e: every rank uploads its row block, NCCL all-gather of the blocks")
                    if world > 1 else "single GPU",
                    "engine": stats["engine"] if not is_binary else "hamming (CUDA cores, POPC)",
-                   "fallback_rows_last_step": stats["fallback_rows"], "bf16_exact_operands": stats["bf16_exact_operands"],
+                   "fallback_rows_last_step": stats["fallback_rows"], "first_proof_unproven_rows": ctx.first_pass_unproven(),
+                   "operands_exact_in_fp16": stats["bf16_exact_operands"],
                    "match_rows": m_rows, "knn_stage_ms": knn_ms}
         if is_binary:
             # dominant kernel: k_knn_hamming (the whole kNN stage is that one launch).  Algorithmic bytes per pair = the
@@ -417,7 +418,7 @@ def run_ours(args, rank, world, local_rank):
                     "note": "operand-stream equivalent (pairs x 32 B / time); POPC-pipe bound, see profiles/"}
             dtype = "u8"
         else:
-            details["arithmetic"] = "bf16 tcgen05 operands, f32 accumulate, exact f32 re-rank of the candidates"
+            details["arithmetic"] = "fp16 tcgen05 operands (kind::f16), f32 accumulate, exact f32 re-rank of the candidates"
             # dominant kernel: k_knn_tc.  Algorithmic FLOPs per launch = 2*D * (rows of this rank) * F
             flops_per_launch = 2.0 * D * float(q1 - q0) * float(F)
             tc_avg_ms = tc_ms_max / max(1, args.steps)       # all tensor launches of one step (first + second pass)
@@ -432,7 +433,7 @@ def run_ours(args, rank, world, local_rank):
                     "frac_of_sustained": achieved / peaks["sustained"], "kernel_ms": tc_avg_ms,
                     "tensor_launches_per_step": tc_launches / max(1, args.steps),
                     "kernel_share_of_step": tc_avg_ms / ms_per_step, "traffic": traffic}
-            dtype = "bf16"
+            dtype = "f16"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
@@ -508,8 +509,10 @@ def real_valued_step_ms(pkg, ctx, torch, stream, flush, steps=5):
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     st = ctx.last_stats()
+    first = ctx.first_pass_unproven()
     plan.close()
     return {"ms_per_step": sum(ms) / len(ms), "fallback_rows": st["fallback_rows"], "engine": st["engine"],
+            "first_proof_unproven_rows": first, "first_proof_unproven_frac": first / float(plan.F),
             "workload": CONFIGS["c6"][2]}
 
 

@@ -91,6 +91,9 @@ int aps_ctx_pairwise_stats(aps_ctx* ctx, int64_t stats[4]);
  * candidate set could not be PROVEN complete and were re-searched exactly, [2] engine used
  * (1 exact, 2 tcgen05), [3] 1 if operands were exactly representable in bf16. */
 int aps_ctx_last_stats(aps_ctx* ctx, int64_t stats[4]);
+/* Rows the FIRST completeness proof of the last float search left unproven (they got the second, 32-candidate tensor
+ * pass; aps_ctx_last_stats[1] counts what even that could not prove and the exact engine searched). */
+int64_t aps_ctx_first_pass_unproven(aps_ctx* ctx);
 /* Measurement hooks (bench.py): with timing enabled the float search brackets every launch of the
  * tcgen05 candidate kernel with CUDA events on the context's stream; aps_ctx_tc_time() synchronises,
  * returns the summed kernel time and launch count since the last call, and resets them.

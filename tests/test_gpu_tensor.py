@@ -188,3 +188,33 @@ def test_tensor_engine_real_valued_sift_second_pass(aps, orc):
     assert np.array_equal(idx, ref["knn_idx"])
     assert np.array_equal(dist.view(np.uint32), ref["knn_dist"].view(np.uint32))
     assert np.array_equal(pair_ptr, ref["pair_ptr"]) and np.array_equal(rows, ref["rows"])
+
+
+def test_exact_operand_variant_still_proves_completeness(aps, orc):
+    """Integer-valued descriptors are exact in the tensor operands and take the 6-candidate variant of the candidate
+    kernel (lists stay 8 wide, two slots unused).  The unused slots must not read as "every column was a candidate":
+    rows with more exact duplicates than a list holds cannot be proven from 6 candidates (the k-th distance ties with
+    the worst retained one), so they must take the second pass / the exact engine -- and the result is the oracle's."""
+    ctx = aps._lib.default_context()
+    rng = np.random.default_rng(23)
+    desc = [np.rint(np.abs(rng.standard_normal((3000, 128))) * 60).clip(0, 255).astype(np.float32) for _ in range(3)]
+    desc[0][200:212] = desc[0][200]           # 12 copies inside one image
+    desc[1][5:45] = desc[0][200]              # 40 more in another: more than the 32 candidates of the second pass
+    desc[2][7] = desc[0][200]
+    ref = orc.feature_matching_global(desc, 4, 0.8, return_knn=True)
+    ctx.set_float_engine(2)
+    try:
+        plan = aps.GlobalPlan(ctx, [d.shape[0] for d in desc], 128, False, 4)
+        plan.upload(desc)
+        plan.prepare()
+        plan.knn()
+        idx, dist = plan.download_knn()
+        stats = ctx.last_stats()
+        first = ctx.first_pass_unproven()
+        plan.close()
+    finally:
+        ctx.set_float_engine(0)
+    assert stats["engine"] == "tcgen05" and stats["bf16_exact_operands"]
+    assert first >= 53 and stats["fallback_rows"] >= 53          # the 53 duplicate rows at least
+    assert np.array_equal(idx, ref["knn_idx"])
+    assert np.array_equal(dist.view(np.uint32), ref["knn_dist"].view(np.uint32))
