@@ -355,7 +355,7 @@ static int float_knn(aps_ctx* c, const FloatSide& Q, int64_t q0, int64_t q1, con
   APS_TRY(fb2.alloc((size_t)nq + 1, c->stream));
   APS_CUDA(cudaMemsetAsync(fb2.p + nq, 0, sizeof(int32_t), c->stream));
   if (nslot2 > nslot) {
-    k_route_unproven<<<1, 256, 0, c->stream>>>(fb.p, fb.p + nq, fb2.p, fb2.p + nq, /*short_list*/ 2048,
+    k_route_unproven<<<1, 256, 0, c->stream>>>(fb.p, fb.p + nq, fb2.p, fb2.p + nq, /*short_list*/ 128,
                                                c->d_scratch_flags + 8);
     APS_LAUNCHED();
     APS_CUDA(cudaMemcpyAsync(c->h_flags + 34, c->d_scratch_flags + 8, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -203,7 +203,7 @@ __global__ void k_knn_exact_merge(const int32_t* __restrict__ rows, const int32_
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int64_t row = rows ? (int64_t)rows[i] : q0 + i;
-  int head[64];
+  unsigned char head[128];  // nsplit <= 128, k <= APS_MAX_K
   for (int s = 0; s < nsplit; ++s) head[s] = 0;
   for (int c = 0; c < k; ++c) {
     float bd = CUDART_INF_F;
@@ -240,12 +240,14 @@ int aps_k_knn_exact(cudaStream_t s, const float* Q, const float* sqQ, const int3
     return APS_ERR_DIM;
   }
   int64_t groups = aps_ceil_div(nq, RQ);
-  // a row LIST (device-side count, usually tiny): let up to 32 CTAs share each row group's train range
+  // a row LIST (device-side count, usually tiny): let up to 128 CTAs share each row group's train range -- the kernel
+  // is latency bound per CTA (load chunk, sync, compute, sync), so a short list wants many short sweeps (27 rows of
+  // C2: 0.46 ms with 32 splits, profiles/r2_ncu_history.txt)
   const int64_t split_cap = 2048;
   int nsplit = 1;
   if (rows) {
     const int64_t tiles = aps_ceil_div(t1 - t0, TJ);
-    nsplit = (int)(tiles < 32 ? (tiles < 1 ? 1 : tiles) : 32);
+    nsplit = (int)(tiles < 128 ? (tiles < 1 ? 1 : tiles) : 128);
   }
   DevBuf<uint32_t> pidx;
   DevBuf<float> pdist;
