@@ -1263,7 +1263,7 @@ struct PairRef {
 };
 
 static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRef>& pairs, const int64_t* counts, int D,
-                          int dtype, bool norm, bool tensor, double match_threshold, double max_ratio,
+                          int dtype, bool norm, bool tensor, int dist_metric, double match_threshold, double max_ratio,
                           std::vector<int32_t>& out_count, std::vector<std::vector<uint32_t>>& out_rows,
                           std::vector<std::vector<double>>& out_metric) {
   const int np = (int)pairs.size();
@@ -1387,14 +1387,14 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       ptr_.prune_mt = match_threshold;
       ptr_.tile_mode = KCP == 3 ? aps_k_knn_tc_tile_mode_segment() : 0;
       ptr_.operand_fp16 = tp.operand_fp16;
-      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, /*metric*/ 1, 0, E, 0, nlist, KCP, cidx.p,
+      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, dist_metric, 0, E, 0, nlist, KCP, cidx.p,
                            cscore.p, S.flags.p, bias_mode, S.flags.p, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &ptr_));
-      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, 1, pt, fb.p, fb.p + E, E, i2.p, dd.p));
+      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, dist_metric, pt, fb.p, fb.p + E, E, i2.p, dd.p));
       APS_CUDA(cudaMemcpyAsync(c->h_flags + 33, fb.p + E, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     } else {
       c->stats[2] = 1;
       APS_CUDA(cudaStreamSynchronize(s));
-      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, 1, pt, nullptr, nullptr, E, i2.p, dd.p));
+      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, dist_metric, pt, nullptr, nullptr, E, i2.p, dd.p));
     }
     APS_TRY(aps_k_pairs_k2_to_nn(s, pt, E, 0, 0, i2.p, dd.p, idx2.p, d1.p, d2.p));
     APS_TRY(aps_k_pairs_filter_unique(s, pt, E, B, idx2.p, d1.p, d2.p, 0, 0, match_threshold, max_ratio, best.p, keys.p,
@@ -1512,6 +1512,8 @@ struct aps_pplan {
   std::vector<int64_t> counts;
   int64_t F = 0, maxc = 0;
   bool tensor = false, prepared = false;
+  int method = APS_METHOD_EXHAUSTIVE;  // aps_pplan_set_method
+  int64_t subset = 12000;
   PairwiseSets ps;
 };
 
@@ -1576,12 +1578,30 @@ extern "C" int aps_pplan_prepare(aps_pplan* p) {
   return APS_OK;
 }
 
+extern "C" int aps_pplan_set_method(aps_pplan* p, int method, int64_t subset) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  if (method < APS_METHOD_EXHAUSTIVE || method > APS_METHOD_APPROX_KDTREE)
+    APS_FAIL(APS_ERR_METHOD, "", "Select a approximate method");   // matchFeaturesScratch.m:156-157
+  if (subset < 1) APS_FAIL(APS_ERR_ARGS, "", "subset must be positive");
+  p->method = method;
+  p->subset = subset;
+  return APS_OK;
+}
+
 extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_ratio, int pair_first, int pair_stride,
                                aps_matchlist** out) {
   if (!p || !out) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
   aps_ctx* c = p->c;
   APS_CTX(c);
   *out = nullptr;
+  // float descriptors: 1 = (a2 + b2) - 2 G of nearest2SSDExhaustive; 2 = Euclidean search squared afterwards ('kdtree'
+  // = exact KD-tree search, :142-148; 'subsetpdist2', :149-155, whose candidate subset is ALL of B while N2 <= subset)
+  const int metric = (p->dtype == APS_F32 && p->method != APS_METHOD_EXHAUSTIVE) ? 2 : 1;
+  if (p->dtype == APS_F32 && p->method == APS_METHOD_APPROX_SUBSETPDIST2 && p->maxc > p->subset)
+    APS_FAIL(APS_ERR_ARGS, "apsmatch:subset",
+             "'subsetpdist2' with more than %lld descriptors in an image draws a random subset (randperm, "
+             "matchFeaturesScratch.m:391-392), which is not built: use 'kdtree' (exact) or 'Exhaustive'",
+             (long long)p->subset);
   if (pair_stride < 1 || pair_first < 0 || pair_first >= pair_stride) APS_FAIL(APS_ERR_ARGS, "", "bad pair share");
   const int n = p->n, D = p->D, dtype = p->dtype;
   const int64_t* counts = p->counts.data();
@@ -1634,7 +1654,8 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
         int64_t e = 0;
         while (b < grp.size() && (b == a || e + counts[grp[b].i] <= ENTRY_BUDGET)) e += counts[grp[b++].i];
         std::vector<PairRef> batch(grp.begin() + a, grp.begin() + b);
-        rc = pairwise_batch(c, ps, batch, counts, D, dtype, g == 1, tensor, match_threshold, max_ratio, cnt, prow, pmet);
+        rc = pairwise_batch(c, ps, batch, counts, D, dtype, g == 1, tensor, metric, match_threshold, max_ratio, cnt, prow,
+                            pmet);
         a = b;
       }
     }

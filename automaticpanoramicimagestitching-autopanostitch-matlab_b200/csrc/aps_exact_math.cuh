@@ -37,6 +37,18 @@ __device__ __forceinline__ float ssd_seq(const float* __restrict__ a, const floa
   return __fsub_rn(__fadd_rn(a2, b2), __fmul_rn(2.0f, g));
 }
 
+// metric 2: plain squared Euclidean distance, sequential over the columns (the 'kdtree' / 'subsetpdist2' branches of
+// matchFeaturesScratch.m:142-155 search by EUCLIDEAN distance -- knnsearch / pdist2 -- and square it afterwards):
+// the caller ranks by sqrt_rn(s) and reports fmul_rn(r, r).
+__device__ __forceinline__ float l2sq_seq(const float* __restrict__ a, const float* __restrict__ b, int D) {
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float e = __fsub_rn(a[d], b[d]);
+    s = __fadd_rn(s, __fmul_rn(e, e));
+  }
+  return s;
+}
+
 // error bound of the approximate distance; flags: [0] operands exact in bf16, [1] bits of max|sq-1|,
 // [2] bits of max sq.  See DESIGN.md "Exactness of the tensor-core search".
 // operand_kind: 0 bf16 (flags[0] = rows exact in bf16), 1 fp16 never exact, 2 fp16 (flags[0] = rows exact in fp16)

@@ -62,120 +62,118 @@ int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass 1.  One block = RB rows staged in shared memory; the per-row sums are SEQUENTIAL float32
-// (one thread per row, one rounding per operation, no FMA) so that the normalised values carry
-// the same bits as the oracle's / the reference's single-precision arithmetic.
+// pass 1.  WARP-centric: each warp stages 32 rows in its own shared-memory tile with coalesced loads, then lane r
+// walks row r: the per-row sums are SEQUENTIAL float32 (one rounding per operation, no FMA) so that the normalised
+// values carry the same bits as the oracle's / the reference's single-precision arithmetic.  No block-wide barrier;
+// row stride D+1 floats makes the per-lane walks bank-conflict free.  HBM streaming: reads 4D, writes 4D + 8 per row.
 // img_off != nullptr: blockIdx.y = image, rows [img_off[y], img_off[y+1]) with its own flag words flags + 8*y (the
 // per-image magnitude test of the pairwise path in ONE launch)
-__global__ void k_prepare_norm(const float* __restrict__ raw, int64_t F, int D, int RB, int norm_mode,
-                               float* __restrict__ xn, float* __restrict__ sq, float* __restrict__ invn,
-                               int32_t* __restrict__ flags, const int64_t* __restrict__ img_off, int fp16) {
-  extern __shared__ float tile[];  // [RB][D+1]
-  __shared__ float s_norm[64];
-  __shared__ int s_exact;
-  __shared__ int s_maxdev, s_maxsq, s_maxabs;
+constexpr int PN_WARPS = 4;   // warps per block; shared memory = PN_WARPS * 32 * (D+1) * 4 bytes
+__global__ void __launch_bounds__(32 * PN_WARPS) k_prepare_norm(const float* __restrict__ raw, int64_t F, int D,
+                                                                int norm_mode, float* __restrict__ xn,
+                                                                float* __restrict__ sq, float* __restrict__ invn,
+                                                                int32_t* __restrict__ flags,
+                                                                const int64_t* __restrict__ img_off, int fp16) {
+  extern __shared__ float tile_all[];
   const int ld = D + 1;
-  int64_t r0 = (int64_t)blockIdx.x * RB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = tile_all + (size_t)warp * 32 * ld;
+  int64_t row_lo = 0;
   if (img_off) {
+    row_lo = img_off[blockIdx.y];
     F = img_off[blockIdx.y + 1];
-    r0 += img_off[blockIdx.y];
     flags += 8 * blockIdx.y;
-    if (r0 >= F) return;
   }
-  const int nr = (int)min((int64_t)RB, F - r0);
-  if (threadIdx.x == 0) {
-    s_exact = 1;
-    s_maxdev = 0;
-    s_maxsq = 0;
-    s_maxabs = 0;
-  }
-  __syncthreads();
   int exact = 1;
-  float maxabs = 0.f;
-  // (row, column) of element i advance by a fixed step per iteration: no division in the loops
-  const int step_r = (int)blockDim.x / D, step_c = (int)blockDim.x - step_r * D;
-  const int first_r = (int)threadIdx.x / D, first_c = (int)threadIdx.x - first_r * D;
-#define APS_NEXT_RC() { r += step_r; c += step_c; if (c >= D) { c -= D; ++r; } }
-  for (int i = threadIdx.x, r = first_r, c = first_c; i < nr * D; i += blockDim.x) {
-    float v = raw[(r0 + r) * D + c];
-    tile[r * ld + c] = v;
-    exact &= fp16 ? (__half2float(__float2half_rn(v)) == v) : (__bfloat162float(__float2bfloat16_rn(v)) == v);
-    maxabs = fmaxf(maxabs, fabsf(v));
-    APS_NEXT_RC()
-  }
-  if (!exact) atomicAnd(&s_exact, 0);
-  atomicMax(&s_maxabs, __float_as_int(maxabs));
-  __syncthreads();
-  if (threadIdx.x < nr) {
-    const float* x = tile + threadIdx.x * ld;
-    float sum = 0.f;
-    for (int c = 0; c < D; ++c) sum = __fadd_rn(sum, __fmul_rn(x[c], x[c]));
-    float n = 1.0f;
-    if (norm_mode == APS_NORM_GLOBAL) n = __fsqrt_rn(__fadd_rn(sum, APS_EPS32));      // featureMatchingGlobal.m:83-84
-    if (norm_mode == APS_NORM_PAIRWISE) n = __fadd_rn(__fsqrt_rn(sum), APS_EPS32);    // matchFeaturesScratch.m:232
-    s_norm[threadIdx.x] = n;
-  }
-  __syncthreads();
-  if (norm_mode != APS_NORM_NONE) {
-    for (int i = threadIdx.x, r = first_r, c = first_c; i < nr * D; i += blockDim.x) {
-      tile[r * ld + c] = __fdiv_rn(tile[r * ld + c], s_norm[r]);
-      APS_NEXT_RC()
+  float maxabs = 0.f, maxdev = 0.f, maxsq = 0.f;
+  const bool write_xn = (xn != raw) || norm_mode != APS_NORM_NONE;
+  for (int64_t r0 = row_lo + ((int64_t)blockIdx.x * PN_WARPS + warp) * 32; r0 < F; r0 += (int64_t)gridDim.x * PN_WARPS * 32) {
+    const int nr = (int)min((int64_t)32, F - r0);
+    const int64_t n_el = (int64_t)nr * D;
+    const float* src = raw + r0 * D;
+    // coalesced load of nr consecutive rows ((row, column) advance by a fixed step: no division in the loop)
+    const int step_r = 32 / D, step_c = 32 - step_r * D;
+    for (int i = lane, r = lane / D, c = lane - (lane / D) * D; i < n_el; i += 32) {
+      const float v = src[i];
+      tile[r * ld + c] = v;
+      exact &= fp16 ? (__half2float(__float2half_rn(v)) == v) : (__bfloat162float(__float2bfloat16_rn(v)) == v);
+      maxabs = fmaxf(maxabs, fabsf(v));
+      r += step_r; c += step_c; if (c >= D) { c -= D; ++r; }
     }
-    __syncthreads();
-  }
-  if (threadIdx.x < nr) {
-    const float* x = tile + threadIdx.x * ld;
-    float sum = 0.f;
-    for (int c = 0; c < D; ++c) sum = __fadd_rn(sum, __fmul_rn(x[c], x[c]));
-    sq[r0 + threadIdx.x] = sum;
-    invn[r0 + threadIdx.x] = __fdiv_rn(1.0f, s_norm[threadIdx.x]);
-    atomicMax(&s_maxdev, __float_as_int(fabsf(sum - 1.0f)));
-    atomicMax(&s_maxsq, __float_as_int(sum));
-  }
-  if (xn != raw || norm_mode != APS_NORM_NONE)
-    for (int i = threadIdx.x, r = first_r, c = first_c; i < nr * D; i += blockDim.x) {
-      xn[(r0 + r) * D + c] = tile[r * ld + c];
-      APS_NEXT_RC()
+    __syncwarp();
+    if (lane < nr) {
+      float* x = tile + lane * ld;
+      float sum = 0.f;
+      for (int c = 0; c < D; ++c) sum = __fadd_rn(sum, __fmul_rn(x[c], x[c]));
+      float n = 1.0f;
+      if (norm_mode == APS_NORM_GLOBAL) n = __fsqrt_rn(__fadd_rn(sum, APS_EPS32));      // featureMatchingGlobal.m:83-84
+      if (norm_mode == APS_NORM_PAIRWISE) n = __fadd_rn(__fsqrt_rn(sum), APS_EPS32);    // matchFeaturesScratch.m:232
+      if (norm_mode != APS_NORM_NONE) {
+        sum = 0.f;
+        for (int c = 0; c < D; ++c) {
+          const float v = __fdiv_rn(x[c], n);
+          x[c] = v;
+          sum = __fadd_rn(sum, __fmul_rn(v, v));
+        }
+      }
+      sq[r0 + lane] = sum;
+      invn[r0 + lane] = __fdiv_rn(1.0f, n);
+      maxdev = fmaxf(maxdev, fabsf(sum - 1.0f));
+      maxsq = fmaxf(maxsq, sum);
     }
-#undef APS_NEXT_RC
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (!s_exact) atomicAnd(&flags[0], 0);
-    atomicMax(&flags[1], s_maxdev);
-    atomicMax(&flags[2], s_maxsq);
-    atomicMax(&flags[3], s_maxabs);
+    __syncwarp();
+    if (write_xn) {
+      float* dst = xn + r0 * D;
+      for (int i = lane, r = lane / D, c = lane - (lane / D) * D; i < n_el; i += 32) {
+        dst[i] = tile[r * ld + c];
+        r += step_r; c += step_c; if (c >= D) { c -= D; ++r; }
+      }
+    }
+    __syncwarp();
   }
+  // one set of atomics per warp
+  exact = __all_sync(0xffffffffu, exact);
+  for (int o = 16; o > 0; o >>= 1) {
+    maxabs = fmaxf(maxabs, __shfl_xor_sync(0xffffffffu, maxabs, o));
+    maxdev = fmaxf(maxdev, __shfl_xor_sync(0xffffffffu, maxdev, o));
+    maxsq = fmaxf(maxsq, __shfl_xor_sync(0xffffffffu, maxsq, o));
+  }
+  if (lane == 0) {
+    if (!exact) atomicAnd(&flags[0], 0);
+    atomicMax(&flags[1], __float_as_int(maxdev));
+    atomicMax(&flags[2], __float_as_int(maxsq));
+    atomicMax(&flags[3], __float_as_int(maxabs));
+  }
+}
+
+static int prepare_norm_launch(cudaStream_t s, const float* raw, int64_t F, int64_t rows_per_y, unsigned ny, int D,
+                               int norm_mode, float* xn, float* sq, float* invn, int32_t* flags, const int64_t* img_off,
+                               int fp16) {
+  const size_t smem = (size_t)PN_WARPS * 32 * (D + 1) * sizeof(float);
+  if (smem > 200 * 1024) {
+    aps_set_error(APS_ERR_DIM, "", "descriptor dimension %d too large", D);
+    return APS_ERR_DIM;
+  }
+  APS_CUDA(cudaFuncSetAttribute(k_prepare_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t gx = aps_ceil_div(rows_per_y, (int64_t)PN_WARPS * 32);
+  const int64_t cap = aps_ceil_div((int64_t)148 * 8, (int64_t)ny);   // a few CTAs per SM; warps loop over the rest
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)(gx < 1 ? 1 : gx), ny);
+  k_prepare_norm<<<grid, 32 * PN_WARPS, smem, s>>>(raw, F, D, norm_mode, xn, sq, invn, flags, img_off, fp16);
+  APS_LAUNCHED();
+  return APS_OK;
 }
 
 int aps_k_prepare_norm(cudaStream_t s, const float* raw, int64_t F, int D, int norm_mode, float* xn, float* sq,
                        float* invn, int32_t* flags, int fp16) {
   if (F == 0) return APS_OK;
-  int RB = 11000 / (D + 1);
-  if (RB > 64) RB = 64;
-  if (RB < 1) {
-    aps_set_error(APS_ERR_DIM, "", "descriptor dimension %d too large", D);
-    return APS_ERR_DIM;
-  }
-  size_t smem = (size_t)RB * (D + 1) * sizeof(float);
-  k_prepare_norm<<<(unsigned)aps_ceil_div(F, RB), 256, smem, s>>>(raw, F, D, RB, norm_mode, xn, sq, invn, flags, nullptr, fp16);
-  APS_LAUNCHED();
-  return APS_OK;
+  return prepare_norm_launch(s, raw, F, F, 1, D, norm_mode, xn, sq, invn, flags, nullptr, fp16);
 }
 
 int aps_k_prepare_norm_images(cudaStream_t s, const float* raw, const int64_t* d_img_off, int n, int64_t maxcount, int D,
                               int norm_mode, float* xn, float* sq, float* invn, int32_t* flags, int fp16) {
   if (n == 0 || maxcount == 0) return APS_OK;
-  int RB = 11000 / (D + 1);
-  if (RB > 64) RB = 64;
-  if (RB < 1) {
-    aps_set_error(APS_ERR_DIM, "", "descriptor dimension %d too large", D);
-    return APS_ERR_DIM;
-  }
-  size_t smem = (size_t)RB * (D + 1) * sizeof(float);
-  dim3 grid((unsigned)aps_ceil_div(maxcount, RB), (unsigned)n);
-  k_prepare_norm<<<grid, 256, smem, s>>>(raw, 0, D, RB, norm_mode, xn, sq, invn, flags, d_img_off, fp16);
-  APS_LAUNCHED();
-  return APS_OK;
+  return prepare_norm_launch(s, raw, 0, maxcount, (unsigned)n, D, norm_mode, xn, sq, invn, flags, d_img_off, fp16);
 }
 
 // ------------------------------------------------------------------------------------------------

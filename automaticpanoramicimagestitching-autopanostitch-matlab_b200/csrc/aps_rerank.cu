@@ -145,11 +145,18 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
     }
   }
   const bool need = valid && below < k && !rej;
-  float d = CUDART_INF_F;
+  float d = CUDART_INF_F;   // ranking key
+  float ds = CUDART_INF_F;  // the same distance in the domain of the approximate scores (squared), for the proof
   if (need) {
     const float* a = Q + q * D;
     const float* b = T + (int64_t)ci * D;
-    d = (metric == 0) ? l2sq_flann(a, b, D) : ssd_seq(a, b, D, a2, sqT[ci]);
+    if (metric == 2) {      // Euclidean search ('kdtree' / 'subsetpdist2'): rank by r = sqrt(s), ties -> lower index
+      ds = l2sq_seq(a, b, D);
+      d = __fsqrt_rn(ds);
+    } else {
+      d = (metric == 0) ? l2sq_flann(a, b, D) : ssd_seq(a, b, D, a2, sqT[ci]);
+      ds = d;
+    }
   }
   const bool nan_seen = (__ballot_sync(0xffffffffu, need && !(d == d)) & segmask) != 0u;
   // rank by (distance, index)
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   const int nvalid = __popc(__ballot_sync(0xffffffffu, need) & segmask);
   if (need && rank < k) {
     idx[orow * k + rank] = (uint32_t)((int64_t)ci - t0 + 1);
-    dist[orow * k + rank] = d;
+    dist[orow * k + rank] = (metric == 2) ? __fmul_rn(d, d) : d;   // :146-147, :153-154: dBest = d.^2
   }
   if (row_ok && sl >= nvalid && sl < k) {  // fewer than k neighbours exist: flann_knn.cpp:216-219
     idx[orow * k + sl] = 0u;
@@ -172,10 +179,12 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   // completeness proof
   float dk = -CUDART_INF_F;  // k-th smallest exact distance (or -inf when fewer than k candidates)
   {
-    float mine = (need && rank == k - 1) ? d : -CUDART_INF_F;
+    float mine = (need && rank == k - 1) ? ds : -CUDART_INF_F;
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) mine = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, o, G));
     dk = mine;
+    // metric 2 ranks by sqrt_rn(s): an outsider must exceed s_k by more than what two roundings can merge
+    if (metric == 2 && dk > 0.f) dk = dk * (1.0f + 1.0e-6f);
   }
   bool proven;
   if (nvalid >= k)
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
           for (int64_t col = c_lo + sl; col < c_hi; col += G) {
             if ((uint32_t)col == segskip[2 * z] || (uint32_t)col == segskip[2 * z + 1]) continue;
             const float* b = T + col * D;
-            const float dd = (metric == 0) ? l2sq_flann(a, b, D) : ssd_seq(a, b, D, a2, sqT[col]);
+            const float dd = (metric == 0) ? l2sq_flann(a, b, D) : (metric == 2 ? l2sq_seq(a, b, D) : ssd_seq(a, b, D, a2, sqT[col]));
             if (!(dd == dd)) bad = true;
             dmin = fminf(dmin, dd);
           }

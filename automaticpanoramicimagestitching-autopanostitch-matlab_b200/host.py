@@ -173,22 +173,33 @@ class ApsSemanticsWarning(UserWarning):
     """The call was served with semantics that differ from what the reference's defaults select."""
 
 
-def _warn_semantics(input, method):
-    """PP/inputs.m:47-49 defaults: useMATLABFeatureMatch=1 (MathWorks matchFeatures, closed source),
-    Matchingmethod='Approximate', ApproxFloatNNMethod='subsetpdist2'.  Nothing here may change results silently."""
+APS_METHOD = {"exhaustive": 0, "subsetpdist2": 1, "kdtree": 2}
+
+
+def _resolve_method(input, method):
+    """(Matchingmethod, ApproxFloatNNMethod) -> aps_method (include/apsmatch.h), following matchFeaturesScratch.m:116-163.
+    PP/inputs.m:47-49 defaults: useMATLABFeatureMatch=1 (MathWorks matchFeatures, closed source), 'Approximate',
+    'subsetpdist2'.  Nothing here may change results silently: what is not built raises or warns."""
     import warnings
 
-    if int(_field(input, "apsAcceptScratchSemantics", 0)):
-        return
-    if int(_field(input, "useMATLABFeatureMatch", 0)) == 1:
+    accept = bool(int(_field(input, "apsAcceptScratchSemantics", 0)))
+    if int(_field(input, "useMATLABFeatureMatch", 0)) == 1 and not accept:
         warnings.warn("input.useMATLABFeatureMatch=1 selects MathWorks matchFeatures in the reference (closed source); "
                       "this GPU path runs the matchFeaturesScratch semantics (featureMatchingPairwise.m:108-117). "
                       "Set input.apsAcceptScratchSemantics=1 to acknowledge.", ApsSemanticsWarning, stacklevel=3)
-    if method == "approximate":
-        warnings.warn("Matchingmethod='Approximate': float descriptors are matched by the EXACT search (a superset in "
-                      "quality of the reference's subset / KD-tree / PCA searches, matchFeaturesScratch.m:128-163); "
-                      "binary descriptors run the exhaustive search exactly as the reference does (:611). "
-                      "Set input.apsAcceptScratchSemantics=1 to acknowledge.", ApsSemanticsWarning, stacklevel=3)
+    if method == "exhaustive":
+        return APS_METHOD["exhaustive"]
+    nn = str(_field(input, "ApproxFloatNNMethod", "pca2nn")).lower()     # parser default, matchFeaturesScratch.m:75
+    if nn in ("subsetpdist2", "kdtree"):
+        return APS_METHOD[nn]
+    if nn == "pca2nn":
+        if not accept:
+            raise ApsError(9, "apsmatch:method", "ApproxFloatNNMethod 'pca2nn' (PCA-48 + cosine GEMM, "
+                           "matchFeaturesScratch.m:130-141) is not built; use 'subsetpdist2' (the inputs.m default), "
+                           "'kdtree' or 'Exhaustive', or set input.apsAcceptScratchSemantics=1 to run the exact search instead")
+        warnings.warn("ApproxFloatNNMethod 'pca2nn' is served by the exhaustive search", ApsSemanticsWarning, stacklevel=3)
+        return APS_METHOD["exhaustive"]
+    raise ValueError("Select a approximate method")                      # :156-157
 
 
 def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metric=False, shard=None, csr=False):
@@ -197,8 +208,10 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
     Runs getMatches' matchFeaturesScratch branch (:108-117) with Unique=true for every i<j.
     input.useMATLABFeatureMatch=1 (the reference default, PP/inputs.m:47) selects MathWorks' closed-source
     matchFeatures there; here it is served by the matchFeaturesScratch semantics and an ApsSemanticsWarning
-    says so (silence it with input.apsAcceptScratchSemantics=1).  Matchingmethod='Approximate' is served by
-    the exact search, with the same warning.
+    says so (silence it with input.apsAcceptScratchSemantics=1).  Matchingmethod='Approximate' follows
+    input.ApproxFloatNNMethod: 'subsetpdist2' (the inputs.m default) and 'kdtree' are built (Euclidean searches,
+    include/apsmatch.h aps_method); 'pca2nn' raises.  Binary descriptors always run the exhaustive Hamming search, as the
+    reference does (matchFeaturesScratch.m:611).
     shard=(first, stride): compute only every stride-th pair of the column-major pair list (one share
     per GPU rank); cells of other shares come back empty and are merged by `merge_pairwise_shards`.
     csr=True returns the compacted lists as they leave the C ABI: (pair_ptr [n*n+1], rows [M x 2] uint32, metric [M])."""
@@ -208,7 +221,7 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
     method = str(_field(input, "Matchingmethod", "Exhaustive")).lower()
     if method not in ("exhaustive", "approximate"):
         raise ValueError(f"Unknown Method: {method}")  # matchFeaturesScratch.m:164-165
-    _warn_semantics(input, method)
+    aps_method = _resolve_method(input, method)
     thr = float(_field(input, "Matchingthreshold", required=True))
     ratio = float(_field(input, "Ratiothreshold", required=True))
     n, first, mats, counts, D, is_binary = _describe(allDescriptors, numImg)
@@ -220,8 +233,19 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
     ptrs, cnt, layout, keep = _desc_args(mats, counts)
     h = C.c_void_p()
     first, stride = shard if shard is not None else (0, 1)
-    check(lib().aps_feature_matching_pairwise_shard(ctx.handle, ptrs, cnt, n, int(D), APS_U8 if is_binary else APS_F32,
-                                                    layout, thr, ratio, int(first), int(stride), C.byref(h)))
+    if aps_method != APS_METHOD["exhaustive"] and not is_binary:
+        ph = C.c_void_p()
+        check(lib().aps_pplan_create(ctx.handle, cnt, n, int(D), APS_F32, C.byref(ph)))
+        try:
+            check(lib().aps_pplan_set_method(ph, aps_method, 12000))      # subset = 12000, matchFeaturesScratch.m:151
+            check(lib().aps_pplan_upload(ph, ptrs, layout))
+            check(lib().aps_pplan_prepare(ph))
+            check(lib().aps_pplan_match(ph, thr, ratio, int(first), int(stride), C.byref(h)))
+        finally:
+            lib().aps_pplan_destroy(ph)
+    else:
+        check(lib().aps_feature_matching_pairwise_shard(ctx.handle, ptrs, cnt, n, int(D), APS_U8 if is_binary else APS_F32,
+                                                        layout, thr, ratio, int(first), int(stride), C.byref(h)))
     try:
         if csr:
             return _csr_from_matchlist(h, n)
@@ -272,13 +296,17 @@ def merge_pairwise_shards(shards):
     return out
 
 
-def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRatio=0.6, Unique=True, ctx=None, **nv):
+def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRatio=0.6, Unique=True, ctx=None,
+                         ApproxFloatNNMethod="pca2nn", **nv):
     """[matches, matchMetric] = matchFeaturesScratch(F1, F2, 'Method','Exhaustive', ...)  (:1-215)
 
-    matches: [K x 2] uint32 (1-based rows of F1 / F2); matchMetric: [K x 1] (SSD, or percent Hamming)."""
+    matches: [K x 2] uint32 (1-based rows of F1 / F2); matchMetric: [K x 1] (SSD, or percent Hamming).
+    Method='Approximate' with float descriptors: ApproxFloatNNMethod 'subsetpdist2' / 'kdtree' (Euclidean searches,
+    :142-155) are built for Unique=true; 'pca2nn' (the parser default, :75) raises.  Binary: exhaustive (:611)."""
     ctx = ctx or default_context()
     if str(Method).lower() not in ("exhaustive", "approximate"):
-        raise ValueError(f"Unknown Method: {Method}")  # :164-165 ; 'Approximate' is served by the exact engine
+        raise ValueError(f"Unknown Method: {Method}")  # :164-165
+    approx = str(Method).lower() == "approximate"
     if not (MaxRatio > 0 and MaxRatio <= 1) or MatchThreshold < 0:
         raise ValueError("invalid MaxRatio / MatchThreshold")  # inputParser validators :60-62
     # normalizeInputs :237-292
@@ -310,6 +338,29 @@ def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRat
             return m[:K.value].copy(), met[:K.value].copy()
         else:
             A, B, is_binary = a, b, False
+    if approx and not is_binary:
+        nn = str(ApproxFloatNNMethod).lower()
+        if nn not in ("pca2nn", "kdtree", "subsetpdist2"):
+            raise ValueError("Select a approximate method")  # :156-157
+        if nn == "pca2nn":
+            raise ApsError(9, "apsmatch:method", "ApproxFloatNNMethod 'pca2nn' is not built (matchFeaturesScratch.m:130-141)")
+        if not Unique:
+            raise ApsError(9, "apsmatch:method", "approximate float matching is built for Unique=true only")
+        A = np.asarray(A, np.float32)
+        B = np.asarray(B, np.float32)
+        if A.shape[0] == 0 or B.shape[0] == 0:
+            return np.zeros((0, 2), np.uint32), np.zeros((0,), np.float64)
+        if A.shape[1] != B.shape[1]:
+            raise ValueError("Descriptor dimensions must match for non-binary.")
+        plan = PairwisePlan(ctx, [A.shape[0], B.shape[0]], A.shape[1], False)
+        try:
+            plan.set_method(nn)
+            plan.upload([A, B])
+            plan.prepare()
+            _, rows, met = plan.match(float(MatchThreshold), float(MaxRatio))
+        finally:
+            plan.close()
+        return rows.astype(np.uint32), met
     A, la = _as_matrix(A, np.uint8 if is_binary else np.float32)
     B, lb = _as_matrix(B, np.uint8 if is_binary else np.float32)
     if la != lb:
@@ -587,6 +638,10 @@ class PairwisePlan:
 
     def desc_device(self):
         return lib().aps_pplan_desc_device(self._h)
+
+    def set_method(self, method, subset=12000):
+        """'exhaustive' | 'subsetpdist2' | 'kdtree' (aps_method, include/apsmatch.h; matchFeaturesScratch.m:116-163)."""
+        check(lib().aps_pplan_set_method(self._h, APS_METHOD[str(method).lower()], int(subset)))
 
     def prepare(self):
         """K1 of the pairwise path: magnitude test per image (matchFeaturesScratch.m:105-110), norms, tensor operands."""

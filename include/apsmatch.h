@@ -265,6 +265,17 @@ int64_t aps_pplan_total(const aps_pplan* p);
 void* aps_pplan_desc_device(aps_pplan* p);   /* pooled ROW-major raw descriptors [F x D] */
 int aps_pplan_upload(aps_pplan* p, const void* const* desc, int layout);
 int aps_pplan_prepare(aps_pplan* p);
+/* Matchingmethod / ApproxFloatNNMethod of getMatches (featureMatchingPairwise.m:108-117 -> matchFeaturesScratch.m:116-163).
+ * Binary descriptors run the exhaustive Hamming search for every method, as the reference does (:611).  Float:
+ *   APS_METHOD_EXHAUSTIVE            nearest2SSDExhaustive, D2 = a2 + b2' - 2 A B'                          (:322-366)
+ *   APS_METHOD_APPROX_SUBSETPDIST2   pdist2(B(candB,:), A, 'euclidean', 'Smallest', 2), squared afterwards   (:149-155,
+ *                                    :370-409); candB = ALL rows of B while N2 <= subset (12000, the reference's constant;
+ *                                    PP/inputs.m:48 makes this the default) -- larger images need randperm: APS_ERR_ARGS
+ *   APS_METHOD_APPROX_KDTREE         knnsearch(createns(B,'kdtree'), A, 'K', 2): an EXACT Euclidean search, squared (:142-148)
+ * Both approximate modes are served by the exact search with the Euclidean metric: distance = fl(sqrt(s))^2 with
+ * s = sum((a-b).^2) in sequential float32, ranking by fl(sqrt(s)), ties -> lower index.  'pca2nn' is not built. */
+enum aps_method { APS_METHOD_EXHAUSTIVE = 0, APS_METHOD_APPROX_SUBSETPDIST2 = 1, APS_METHOD_APPROX_KDTREE = 2 };
+int aps_pplan_set_method(aps_pplan* p, int method, int64_t subset);
 int aps_pplan_match(aps_pplan* p, double match_threshold, double max_ratio, int pair_first, int pair_stride,
                     aps_matchlist** out);
 

@@ -1,25 +1,38 @@
 function matches = featureMatchingPairwise(input, allDescriptors, numImg)
     %FEATUREMATCHINGPAIRWISE  Drop-in replacement of PP/featureMatching/featureMatchingPairwise.m.
-    %   Runs getMatches' matchFeaturesScratch 'Exhaustive' branch (Unique = true) for every image pair
-    %   i<j on the GPU in one call.  (The MathWorks matchFeatures branch, input.useMATLABFeatureMatch = 1,
-    %   is closed source; with this file on the path the exhaustive scratch semantics are used.)
+    %   Runs getMatches' matchFeaturesScratch branch (Unique = true) for every image pair i<j on the GPU in one call.
+    %   input.Matchingmethod 'Exhaustive', or 'Approximate' with input.ApproxFloatNNMethod 'subsetpdist2' (the
+    %   inputs.m default) / 'kdtree' -- both Euclidean searches, matchFeaturesScratch.m:142-155; 'pca2nn' is not built.
+    %   (The MathWorks matchFeatures branch, input.useMATLABFeatureMatch = 1, is closed source; with this file on the
+    %   path the scratch semantics are used and a warning says so.)
     arguments
         input struct
         allDescriptors cell
         numImg (1, 1) {mustBeNumeric, mustBeFinite, mustBePositive}
     end
-    % PP/inputs.m:47-49 defaults select MathWorks matchFeatures (closed source) and 'Approximate': say so instead of
-    % changing the match lists silently; input.apsAcceptScratchSemantics = 1 acknowledges and silences this.
-    if ~(isfield(input, 'apsAcceptScratchSemantics') && input.apsAcceptScratchSemantics)
-        if isfield(input, 'useMATLABFeatureMatch') && input.useMATLABFeatureMatch == 1
-            warning('apsmatch:semantics', ['input.useMATLABFeatureMatch = 1 selects MathWorks matchFeatures in the ' ...
-                'reference; this GPU path runs the matchFeaturesScratch semantics (featureMatchingPairwise.m:108-117).']);
-        end
-        if isfield(input, 'Matchingmethod') && strcmpi(input.Matchingmethod, 'Approximate')
-            warning('apsmatch:semantics', ['Matchingmethod = ''Approximate'': float descriptors are matched by the ' ...
-                'exact search (matchFeaturesScratch.m:128-163 approximates it); binary descriptors run the ' ...
-                'exhaustive search as in the reference (:611).']);
+    % Nothing may change the match lists silently: input.apsAcceptScratchSemantics = 1 acknowledges.
+    accept = isfield(input, 'apsAcceptScratchSemantics') && input.apsAcceptScratchSemantics;
+    if ~accept && isfield(input, 'useMATLABFeatureMatch') && input.useMATLABFeatureMatch == 1
+        warning('apsmatch:semantics', ['input.useMATLABFeatureMatch = 1 selects MathWorks matchFeatures in the ' ...
+            'reference; this GPU path runs the matchFeaturesScratch semantics (featureMatchingPairwise.m:108-117).']);
+    end
+    method = 0;                                          % aps_method: 0 exhaustive, 1 subsetpdist2, 2 kdtree
+    if isfield(input, 'Matchingmethod') && strcmpi(input.Matchingmethod, 'Approximate')
+        nn = 'pca2nn';                                   % parser default, matchFeaturesScratch.m:75
+        if isfield(input, 'ApproxFloatNNMethod'); nn = lower(char(input.ApproxFloatNNMethod)); end
+        switch nn
+            case 'subsetpdist2'
+                method = 1;
+            case 'kdtree'
+                method = 2;
+            case 'pca2nn'
+                if ~accept
+                    error('apsmatch:method', ['ApproxFloatNNMethod pca2nn is not built; use subsetpdist2, kdtree or ' ...
+                        'Exhaustive (or input.apsAcceptScratchSemantics = 1 to run the exact search instead).']);
+                end
+            otherwise
+                error('Select a approximate method');
         end
     end
-    matches = aps_featureMatching_mex('pairwise', allDescriptors, numImg, input.Matchingthreshold, input.Ratiothreshold);
+    matches = aps_featureMatching_mex('pairwise', allDescriptors, numImg, input.Matchingthreshold, input.Ratiothreshold, method);
 end

@@ -7,10 +7,11 @@ function [matches, matchMetric] = matchFeaturesScratch(F1, F2, varargin)
     %   (SSD, or percent of mismatched bits).  Nearest-2 search, the "normalise iff max|.| > 2" rule, ratio and
     %   threshold tests and the greedy Unique pass (reference lines 105-126, 169-215) run on the GPU in
     %   aps_matchFeatures_mex; this file only parses the options and decides the descriptor kind (lines 237-292).
-    %   'Approximate' and every Approx* option are accepted and served by the exact search (a superset in quality;
-    %   the reference's binary 'Approximate' branch is itself the exhaustive OMP MEX, line 611).
-    opt = struct('Method', 'Exhaustive', 'MatchThreshold', 3.5, 'MaxRatio', 0.6, 'Unique', true);
-    accepted = {'ApproxNumTables', 'ApproxBitsPerKey', 'ApproxProbes', 'ApproxKDBucketSize', 'ApproxFloatNNMethod', ...
+    %   'Approximate': binary descriptors run the exhaustive search (the reference's own branch is the exhaustive OMP MEX,
+    %   line 611; the LSH options are accepted and ignored as there); float descriptors follow 'ApproxFloatNNMethod':
+    %   'subsetpdist2' and 'kdtree' (Euclidean searches, lines 142-155) are built, 'pca2nn' (the parser default) errors.
+    opt = struct('Method', 'Exhaustive', 'MatchThreshold', 3.5, 'MaxRatio', 0.6, 'Unique', true, 'ApproxFloatNNMethod', 'pca2nn');
+    accepted = {'ApproxNumTables', 'ApproxBitsPerKey', 'ApproxProbes', 'ApproxKDBucketSize', ...
                 'ApproxKDTreeLeafSize', 'Approx.NumTables', 'Approx.BitsPerKey', 'Approx.Probes'};
     if mod(numel(varargin), 2) ~= 0
         error('apsmatch:args', 'Options must be name-value pairs.');
@@ -48,8 +49,21 @@ function [matches, matchMetric] = matchFeaturesScratch(F1, F2, varargin)
         if ~isa(A, 'single') && ~isa(A, 'double'); A = single(A); end
         if ~isa(B, 'single') && ~isa(B, 'double'); B = single(B); end
     end
+    nnMethod = 0;                                        % aps_method: 0 exhaustive, 1 subsetpdist2, 2 kdtree
+    if kind == 0 && strcmp(method, 'approximate')
+        switch lower(char(opt.ApproxFloatNNMethod))
+            case 'subsetpdist2'
+                nnMethod = 1;
+            case 'kdtree'
+                nnMethod = 2;
+            case 'pca2nn'
+                error('apsmatch:method', 'ApproxFloatNNMethod pca2nn is not built; use subsetpdist2 or kdtree.');
+            otherwise
+                error('Select a approximate method');
+        end
+    end
     [matches, matchMetric] = aps_matchFeatures_mex(A, B, kind, double(opt.MatchThreshold), double(opt.MaxRatio), ...
-                                                   logical(opt.Unique));
+                                                   logical(opt.Unique), nnMethod);
 end
 
 function tf = isBits(F)

@@ -1,6 +1,6 @@
 // aps_featureMatching_mex.cpp -- batched gateway: the whole featureMatching/ stage in one device round trip.
 //   matches = aps_featureMatching_mex('global',   allDescriptors, numImg, k, ratioThr, useBF)
-//   matches = aps_featureMatching_mex('pairwise', allDescriptors, numImg, matchThreshold, maxRatio)
+//   matches = aps_featureMatching_mex('pairwise', allDescriptors, numImg, matchThreshold, maxRatio [, method])
 //   [cand, IuptriIdx] = aps_featureMatching_mex('partners', matchesAll | countMatrix, m)
 // Called by the drop-in matlab/featureMatchingGlobal.m / featureMatchingPairwise.m (same signatures as
 // PP/featureMatching/featureMatchingGlobal.m:1 and featureMatchingPairwise.m:1) and by the two-line patch of
@@ -57,8 +57,19 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
                                      nrhs > 5 ? (int)mxGetScalar(prhs[5]) : 0, &ml);
   } else if (mode == "pairwise") {
     if (nrhs < 5) mexErrMsgIdAndTxt("apsmatch:args", "pairwise: need MatchThreshold and MaxRatio");
-    rc = aps_feature_matching_pairwise(aps_mex_ctx(), ptrs.data(), counts.data(), n, D, dtype, APS_COL_MAJOR,
-                                       mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), &ml);
+    const int method = nrhs > 5 ? (int)mxGetScalar(prhs[5]) : APS_METHOD_EXHAUSTIVE;   // aps_method
+    if (method == APS_METHOD_EXHAUSTIVE || dtype == APS_U8) {
+      rc = aps_feature_matching_pairwise(aps_mex_ctx(), ptrs.data(), counts.data(), n, D, dtype, APS_COL_MAJOR,
+                                         mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), &ml);
+    } else {   // 'subsetpdist2' / 'kdtree' (matchFeaturesScratch.m:142-155): staged plan with the Euclidean metric
+      aps_pplan* plan = nullptr;
+      rc = aps_pplan_create(aps_mex_ctx(), counts.data(), n, D, dtype, &plan);
+      if (rc == APS_OK) rc = aps_pplan_set_method(plan, method, 12000);
+      if (rc == APS_OK) rc = aps_pplan_upload(plan, ptrs.data(), APS_COL_MAJOR);
+      if (rc == APS_OK) rc = aps_pplan_prepare(plan);
+      if (rc == APS_OK) rc = aps_pplan_match(plan, mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), 0, 1, &ml);
+      aps_pplan_destroy(plan);
+    }
   } else {
     mexErrMsgIdAndTxt("apsmatch:args", "unknown mode '%s'", mode.c_str());
     return;

@@ -1,5 +1,7 @@
 // aps_matchFeatures_mex.cpp -- gateway of the per-pair matcher behind matlab/matchFeaturesScratch.m.
-//   [matches, matchMetric] = aps_matchFeatures_mex(A, B, kind, matchThreshold, maxRatio, unique)
+//   [matches, matchMetric] = aps_matchFeatures_mex(A, B, kind, matchThreshold, maxRatio, unique [, method])
+//     method (float only, aps_method of include/apsmatch.h): 0 exhaustive [default], 1 'subsetpdist2', 2 'kdtree'
+//     (Euclidean searches of matchFeaturesScratch.m:142-155; Unique = true only)
 //     kind 0 : float descriptors  [N x D]     single / double   (nearest2SSDExhaustive + filters,
 //                                                                 PP/featureMatching/matchFeaturesScratch.m:105-126,169-215,322-366)
 //     kind 1 : packed binary      [N x nb]    uint8             (binaryFeatures.Features; nearest2HammingExhaustiveMEX, :295-319)
@@ -16,7 +18,9 @@ static void empty_result(int nlhs, mxArray* plhs[]) {  // :84-88
 }
 
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
-  if (nrhs != 6) mexErrMsgIdAndTxt("apsmatch:args", "usage: [matches, metric] = aps_matchFeatures_mex(A, B, kind, matchThreshold, maxRatio, unique)");
+  if (nrhs != 6 && nrhs != 7)
+    mexErrMsgIdAndTxt("apsmatch:args", "usage: [matches, metric] = aps_matchFeatures_mex(A, B, kind, matchThreshold, maxRatio, unique [, method])");
+  const int method = nrhs > 6 ? (int)mxGetScalar(prhs[6]) : APS_METHOD_EXHAUSTIVE;
   if (nlhs > 2) mexErrMsgIdAndTxt("apsmatch:args", "at most two outputs");
   const mxArray *A = prhs[0], *B = prhs[1];
   const int kind = (int)mxGetScalar(prhs[2]);
@@ -51,7 +55,26 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   std::vector<double> met((size_t)(N1 > 0 ? N1 : 1));
   int64_t K = 0;
   int rc;
-  if (kind == 2)
+  if (kind == 0 && method != APS_METHOD_EXHAUSTIVE) {   // two-image staged plan with the Euclidean metric
+    if (!unique) mexErrMsgIdAndTxt("apsmatch:method", "approximate float matching is built for Unique = true only");
+    const void* desc[2] = {pa, pb};
+    const int64_t counts[2] = {N1, N2};
+    aps_pplan* plan = nullptr;
+    aps_matchlist* ml = nullptr;
+    rc = aps_pplan_create(aps_mex_ctx(), counts, 2, D, APS_F32, &plan);
+    if (rc == APS_OK) rc = aps_pplan_set_method(plan, method, 12000);
+    if (rc == APS_OK) rc = aps_pplan_upload(plan, desc, APS_COL_MAJOR);
+    if (rc == APS_OK) rc = aps_pplan_prepare(plan);
+    if (rc == APS_OK) rc = aps_pplan_match(plan, thr, ratio, 0, 1, &ml);
+    aps_pplan_destroy(plan);
+    if (rc == APS_OK) {
+      K = aps_matchlist_total(ml);
+      const uint32_t* r = aps_matchlist_rows(ml);
+      const double* m = aps_matchlist_metric(ml);
+      for (int64_t i = 0; i < K; ++i) { rows[2 * i] = r[2 * i]; rows[2 * i + 1] = r[2 * i + 1]; met[i] = m[i]; }
+      aps_matchlist_free(ml);
+    }
+  } else if (kind == 2)
     rc = aps_match_features_bits(aps_mex_ctx(), (const uint8_t*)pa, N1, (const uint8_t*)pb, N2, D, APS_COL_MAJOR, thr, ratio,
                                  unique, rows.data(), met.data(), &K);
   else

@@ -609,6 +609,75 @@ int64_t orc_match_features(const void* A, int64_t N1, const void* B, int64_t N2,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * A10 (the two modes that are exact searches)  matchFeaturesScratch.m:142-155:
+ *   'kdtree'       nearest2KDTree :411-440    knnsearch(createns(B,'kdtree',...), A, 'K', 2) -- an EXACT Euclidean search
+ *   'subsetpdist2' nearest2SubsetPdist2 :370-409   pdist2(B(candB,:), A, 'euclidean', 'Smallest', 2), candB =
+ *                  randperm(N2, min(subset, N2)): while N2 <= subset (12000) every row of B is a candidate
+ *   both return EUCLIDEAN distances and the caller squares them: dBest = d1.^2, dSecond = d2.^2 (:146-147, :153-154).
+ *   Restated: s = sum((a-b).^2) sequential float32, r = sqrtf(s), ranking by (r, index) [knnsearch / pdist2 are
+ *   closed source: their summation order and tie order are unpinned; candB's permutation only reorders exact ties],
+ *   outputs d1 = r1*r1, d2 = r2*r2 in float32.  N2 == 1: second = +inf (deviation: pdist2 path pads with
+ *   d1 + eps(d1), :396-400; knnsearch errors).
+ * ---------------------------------------------------------------------------------------- */
+void orc_nearest2_euclid(const float* A, int64_t N1, const float* B, int64_t N2, int D, uint32_t* idx2, float* d1,
+                         float* d2) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < N1; ++i) {
+    const float* a = A + i * D;
+    float r1 = INFINITY, r2 = INFINITY;
+    uint32_t i1 = 0;
+    for (int64_t j = 0; j < N2; ++j) {
+      const float* b = B + j * D;
+      float s = 0.0f;
+      for (int d = 0; d < D; ++d) {
+        const float e = a[d] - b[d];
+        s = s + e * e;
+      }
+      const float r = sqrtf(s);
+      if (r < r1) {
+        r2 = r1;
+        r1 = r;
+        i1 = (uint32_t)(j + 1);
+      } else if (r < r2) {
+        r2 = r;
+      }
+    }
+    idx2[i] = i1;
+    d1[i] = i1 ? r1 * r1 : INFINITY;
+    d2[i] = isinf(r2) ? INFINITY : r2 * r2;
+  }
+}
+
+/* matchFeaturesScratch(F1,F2,'Method','Approximate','ApproxFloatNNMethod', m, ...) for float descriptors,
+ * m = 1 'subsetpdist2' (N2 <= subset), 2 'kdtree'; binary descriptors and m = 0 take the exhaustive path. */
+int64_t orc_match_features_method(const void* A, int64_t N1, const void* B, int64_t N2, int D, int is_binary, int method,
+                                  double matchThreshold, double maxRatio, int unique, uint32_t* matches,
+                                  double* metric) {
+  if (is_binary || method == 0)
+    return orc_match_features(A, N1, B, N2, D, is_binary, matchThreshold, maxRatio, unique, matches, metric);
+  if (N1 == 0 || N2 == 0) return 0;
+  uint32_t* idx2 = (uint32_t*)malloc((size_t)N1 * sizeof(uint32_t));
+  float* d1 = (float*)malloc((size_t)N1 * sizeof(float));
+  float* d2 = (float*)malloc((size_t)N1 * sizeof(float));
+  float* a = (float*)malloc((size_t)N1 * D * sizeof(float));
+  float* b = (float*)malloc((size_t)N2 * D * sizeof(float));
+  memcpy(a, A, (size_t)N1 * D * sizeof(float));
+  memcpy(b, B, (size_t)N2 * D * sizeof(float));
+  if (orc_needs_normalization(a, N1 * D, b, N2 * D)) { /* :105-110 runs before the method switch */
+    orc_normalize_rows_pairwise(a, N1, D);
+    orc_normalize_rows_pairwise(b, N2, D);
+  }
+  orc_nearest2_euclid(a, N1, b, N2, D, idx2, d1, d2);
+  const int64_t K = orc_filter_unique(idx2, d1, d2, N1, N2, 0, 0, matchThreshold, maxRatio, unique, matches, metric);
+  free(a);
+  free(b);
+  free(idx2);
+  free(d1);
+  free(d2);
+  return K;
+}
+
+/* ------------------------------------------------------------------------------------------
  * A4 / B.2 whole  featureMatchingPairwise.m:43-63 + getMatches :103-120 (useMATLABFeatureMatch=0,
  * Matchingmethod='Exhaustive'): every (i<j), query = image i, train = image j, Unique=true.
  *   desc pooled row-major; CSR output like orc_global_scatter (pair cell (i,j) i<j), rows =

@@ -64,6 +64,10 @@ def lib():
         L.orc_match_features.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                          C.c_double, C.c_double, C.c_int, _u32p, _f64p]
         L.orc_match_features.restype = C.c_int64
+        L.orc_match_features_method.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                                C.c_double, C.c_double, C.c_int, _u32p, _f64p]
+        L.orc_match_features_method.restype = C.c_int64
+        L.orc_nearest2_euclid.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_int, _u32p, _f32p, _f32p]
         L.orc_feature_matching_pairwise.argtypes = [C.c_void_p, C.c_int, _i64p, C.c_int, C.c_int, C.c_double,
                                                     C.c_double, _i64p, _u32p, _f64p]
         L.orc_feature_matching_pairwise.restype = C.c_int64
@@ -212,6 +216,32 @@ def match_features(A, B, match_threshold, max_ratio, unique=True):
     K = lib().orc_match_features(A.ctypes.data, N1, B.ctypes.data, N2, A.shape[1], int(is_binary),
                                  float(match_threshold), float(max_ratio), int(unique), m.reshape(-1), met)
     return m[:K].copy(), met[:K].copy()
+
+
+METHODS = {"exhaustive": 0, "subsetpdist2": 1, "kdtree": 2}
+
+
+def match_features_method(A, B, match_threshold, max_ratio, method, unique=True):
+    """matchFeaturesScratch(A,B,'Method','Approximate','ApproxFloatNNMethod',method,...) -- 'subsetpdist2' (while
+    N2 <= 12000) and 'kdtree' are exact Euclidean searches; method 'exhaustive' = match_features."""
+    is_binary = A.dtype == np.uint8
+    A = _u8(A) if is_binary else _f32(A)
+    B = _u8(B) if is_binary else _f32(B)
+    N1, N2 = A.shape[0], B.shape[0]
+    m = np.zeros((max(N1, 1), 2), np.uint32)
+    met = np.zeros(max(N1, 1), np.float64)
+    K = lib().orc_match_features_method(A.ctypes.data, N1, B.ctypes.data, N2, A.shape[1], int(is_binary),
+                                        METHODS[method], float(match_threshold), float(max_ratio), int(unique),
+                                        m.reshape(-1), met)
+    return m[:K].copy(), met[:K].copy()
+
+
+def nearest2_euclid(A, B):
+    A, B = _f32(A), _f32(B)
+    N1 = A.shape[0]
+    idx2, d1, d2 = np.zeros(N1, np.uint32), np.zeros(N1, np.float32), np.zeros(N1, np.float32)
+    lib().orc_nearest2_euclid(A, N1, B, B.shape[0], A.shape[1], idx2, d1, d2)
+    return idx2, d1, d2
 
 
 def feature_matching_pairwise(desc_list, match_threshold, max_ratio):

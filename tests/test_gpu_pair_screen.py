@@ -103,3 +103,45 @@ def test_screen_on_equals_screen_off(aps, orc):
                 for i in range(j):
                     exp = ref.get((i, j))
                     assert (exp is None and on[i][j].shape[0] == 0) or np.array_equal(on[i][j], exp.astype(np.float64)), (cid, i, j)
+
+
+@pytest.mark.parametrize("nn", ["subsetpdist2", "kdtree"])
+def test_approximate_float_methods_match_the_oracle(aps, orc, nn):
+    """Matchingmethod='Approximate' (the reference's inputs.m default, with 'subsetpdist2'): the two float modes that
+    are Euclidean searches (matchFeaturesScratch.m:142-155) against the oracle's restatement, through
+    featureMatchingPairwise and matchFeaturesScratch; binary descriptors take the exhaustive path; 'pca2nn' raises."""
+    import warnings
+
+    ctx = aps._lib.default_context()
+    inp = {"Matchingmethod": "Approximate", "ApproxFloatNNMethod": nn, "Matchingthreshold": 1.5, "Ratiothreshold": 0.7,
+           "useMATLABFeatureMatch": 0}
+    for cid, n, kp in ((5, 8, 2500), (1, 5, 1500)):
+        desc, _ = aps.synth.make_config(cid, n=n, kp=kp)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")                       # built modes must not warn
+            got, met = aps.featureMatchingPairwise(inp, desc, len(desc), ctx=ctx, return_metric=True)
+        total = 0
+        for j in range(len(desc)):
+            for i in range(j):
+                if desc[i].shape[0] == 0 or desc[j].shape[0] == 0:
+                    assert got[i][j].shape[0] == 0
+                    continue
+                m, d = orc.match_features_method(desc[i], desc[j], 1.5, 0.7, nn)
+                assert got[i][j].shape == (len(m), 2) and np.array_equal(got[i][j], m.astype(np.float64)), (cid, i, j)
+                if len(m):
+                    assert np.array_equal(np.asarray(met[i][j]), d), (cid, i, j)
+                total += len(m)
+        assert total > 500
+    A, B = desc[0], desc[1]
+    m, d = aps.matchFeaturesScratch(A, B, Method="Approximate", ApproxFloatNNMethod=nn, MatchThreshold=1.5, MaxRatio=0.7, ctx=ctx)
+    om, od = orc.match_features_method(A, B, 1.5, 0.7, nn)
+    assert np.array_equal(m, om) and np.array_equal(d, od)
+    # binary: exhaustive whatever the method says (matchFeaturesScratch.m:611)
+    orb, _ = aps.synth.make_config(4, n=3, kp=800)
+    gb = aps.featureMatchingPairwise(dict(inp, Matchingthreshold=40.0), [aps.binaryFeatures(x) for x in orb], 3, ctx=ctx)
+    for j in range(3):
+        for i in range(j):
+            m, _ = orc.match_features(orb[i], orb[j], 40.0, 0.7)
+            assert np.array_equal(gb[i][j], m.astype(np.float64))
+    with pytest.raises(aps.ApsError):
+        aps.featureMatchingPairwise(dict(inp, ApproxFloatNNMethod="pca2nn"), desc, len(desc), ctx=ctx)

@@ -194,3 +194,61 @@ def test_randomised_shapes_differential(orc, seed):
     cand, lin = orc.select_partners(Cm, msel)
     ec, el = mr.select_partners(Cm, msel)
     assert np.array_equal(cand, ec) and np.array_equal(lin + 1, el)
+
+
+def test_euclidean_modes_kdtree_subsetpdist2(orc):
+    """'kdtree' / 'subsetpdist2' (matchFeaturesScratch.m:142-155, :370-440): Euclidean 2-NN, squared afterwards.
+    Independent array-style restatement: pdist2-like distance matrix accumulated column by column in float32."""
+    rng = np.random.default_rng(31)
+    for N1, N2, D in ((40, 55, 16), (7, 300, 64), (120, 2, 5)):
+        A = rng.integers(-8, 9, (N1, D)).astype(np.float32) / 8          # tie-heavy, every sum exact
+        B = rng.integers(-8, 9, (N2, D)).astype(np.float32) / 8
+        B[0] = A[min(3, N1 - 1)]
+        s = np.zeros((N1, N2), np.float32)
+        for c in range(D):
+            e = A[:, c][:, None] - B[:, c][None, :]
+            s = s + e * e
+        r = np.sqrt(s)                                                  # euclidean distances, single
+        order = np.argsort(r, axis=1, kind="stable")                    # 'Smallest', 2: ascending, first index on ties
+        i1 = order[:, 0]
+        d1 = (r[np.arange(N1), i1] ** 2).astype(np.float32)             # dBest = d12eu.^2
+        d2 = (r[np.arange(N1), order[:, 1]] ** 2).astype(np.float32)
+        oi, od1, od2 = orc.nearest2_euclid(A, B)
+        assert np.array_equal(oi, (i1 + 1).astype(np.uint32))
+        assert np.array_equal(od1.view(np.uint32), d1.view(np.uint32)) and np.array_equal(od2.view(np.uint32), d2.view(np.uint32))
+    # through the filters: same lists as feeding the restated distances to the (already cross-checked) filter stage
+    A = rng.standard_normal((60, 32)).astype(np.float32)
+    B = np.vstack([A[:20] + rng.normal(0, 0.02, (20, 32)).astype(np.float32), rng.standard_normal((50, 32)).astype(np.float32)])
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    B /= np.linalg.norm(B, axis=1, keepdims=True)
+    for nn in ("kdtree", "subsetpdist2"):
+        m, d = orc.match_features_method(A, B, 1.5, 0.7, nn)
+        assert len(m) >= 15 and (np.diff(d) >= 0).all() and len(set(m[:, 1].tolist())) == len(m)
+    me, _ = orc.match_features_method(A, B, 1.5, 0.7, "exhaustive")
+    m0, _ = orc.match_features(A, B, 1.5, 0.7)
+    assert np.array_equal(me, m0)
+
+
+def test_host_method_resolution(aps):
+    """Matchingmethod / ApproxFloatNNMethod / useMATLABFeatureMatch of PP/inputs.m:47-49: built modes resolve silently,
+    the closed-source branch warns, 'pca2nn' raises unless acknowledged (no GPU needed: pure host logic)."""
+    import warnings
+
+    from importlib import import_module
+
+    host = import_module(aps.__name__ + ".host")
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert host._resolve_method({"ApproxFloatNNMethod": "subsetpdist2"}, "approximate") == 1
+        assert host._resolve_method({"ApproxFloatNNMethod": "kdtree", "useMATLABFeatureMatch": 0}, "approximate") == 2
+        assert host._resolve_method({}, "exhaustive") == 0
+    with pytest.warns(host.ApsSemanticsWarning):
+        host._resolve_method({"useMATLABFeatureMatch": 1, "ApproxFloatNNMethod": "subsetpdist2"}, "approximate")
+    with pytest.raises(aps.ApsError):
+        host._resolve_method({"ApproxFloatNNMethod": "pca2nn"}, "approximate")
+    with pytest.raises(aps.ApsError):
+        host._resolve_method({}, "approximate")                          # parser default is pca2nn (:75)
+    with pytest.warns(host.ApsSemanticsWarning):
+        assert host._resolve_method({"ApproxFloatNNMethod": "pca2nn", "apsAcceptScratchSemantics": 1}, "approximate") == 0
+    with pytest.raises(ValueError):
+        host._resolve_method({"ApproxFloatNNMethod": "lsh"}, "approximate")
