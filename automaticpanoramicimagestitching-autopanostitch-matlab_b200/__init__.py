@@ -15,6 +15,7 @@ from .host import (  # noqa: F401
     RECORD_PAD,
     binaryFeatures,
     featureMatchingGlobal,
+    featureMatchingGlobalDevice,
     estimateTransformationRANSAC,
     featureMatchingPairwise,
     imageMatching,

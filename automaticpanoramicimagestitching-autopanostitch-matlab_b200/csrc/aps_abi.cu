@@ -877,6 +877,19 @@ extern "C" int aps_gplan_filter(aps_gplan* p, int64_t q0, int64_t q1, double rat
                              (float)ratio, p->records.p);
 }
 
+// Opt-in cross-check on the GLOBAL path (off in the reference: featureMatchingGlobal.m:149-159 keeps A->B and B->A rows
+// alike, BFMatcher is built with crossCheck = false, flann_knn.cpp:204).  Runs on the complete record set (after the
+// ranks exchanged their slices): a query keeps its match only if the matched feature's own accepted match is the query.
+extern "C" int aps_gplan_filter_mutual(aps_gplan* p) {
+  if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
+  aps_ctx* c = p->c;
+  APS_CTX(c);
+  if (p->F == 0) return APS_OK;
+  DevBuf<uint8_t> keep;
+  APS_TRY(keep.alloc((size_t)p->F, c->stream));
+  return aps_k_records_mutual(c->stream, p->records.p, p->img_of_row.p, p->d_off.p, p->F, keep.p);
+}
+
 extern "C" int aps_gplan_download_knn(aps_gplan* p, int64_t q0, int64_t q1, uint32_t* idx, float* dist) {
   if (!p || !idx || !dist) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
   aps_ctx* c = p->c;
@@ -962,6 +975,41 @@ extern "C" int aps_feature_matching_global(aps_ctx* c, const void* const* desc, 
     if (rc == APS_OK) rc = aps_gplan_prepare(p);
     if (rc == APS_OK) rc = aps_gplan_knn(p, 0, p->F);
     if (rc == APS_OK) rc = aps_gplan_filter(p, 0, p->F, ratio);
+    if (rc == APS_OK) rc = aps_gplan_compact(p);
+  }
+  if (rc == APS_OK) rc = aps_gplan_download(p, out);
+  aps_gplan_destroy(p);
+  return rc;
+}
+
+// Same with the pooled descriptors ALREADY ON THE DEVICE (a GPU extractor's output, or a previous stage's buffer):
+// no host staging; the pooled row-major [F x D] matrix is copied device-to-device into the plan.
+extern "C" int aps_feature_matching_global_dev(aps_ctx* c, const void* d_pooled, const int64_t* counts, int n, int D,
+                                               int dtype, int k, double ratio, int mutual, aps_matchlist** out) {
+  APS_CTX(c);
+  if (!out) APS_FAIL(APS_ERR_ARGS, "", "out is NULL");
+  *out = nullptr;
+  aps_gplan* p = nullptr;
+  APS_TRY(aps_gplan_create(c, counts, n, D, dtype, k, &p));
+  int rc = APS_OK;
+  if (p->F > 0) {
+    if (!d_pooled) {
+      aps_gplan_destroy(p);
+      APS_FAIL(APS_ERR_ARGS, "", "device descriptor pointer is NULL");
+    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, d_pooled) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+      cudaGetLastError();
+      aps_gplan_destroy(p);
+      APS_FAIL(APS_ERR_ARGS, "", "aps_feature_matching_global_dev expects a device pointer");
+    }
+    const size_t bytes = (size_t)p->F * D * (dtype == APS_F32 ? 4 : 1);
+    if (cudaMemcpyAsync(aps_gplan_desc_device(p), d_pooled, bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
+      rc = APS_ERR_CUDA;
+    if (rc == APS_OK) rc = aps_gplan_prepare(p);
+    if (rc == APS_OK) rc = aps_gplan_knn(p, 0, p->F);
+    if (rc == APS_OK) rc = aps_gplan_filter(p, 0, p->F, ratio);
+    if (rc == APS_OK && mutual) rc = aps_gplan_filter_mutual(p);
     if (rc == APS_OK) rc = aps_gplan_compact(p);
   }
   if (rc == APS_OK) rc = aps_gplan_download(p, out);

@@ -239,6 +239,8 @@ int aps_k_rerank(cudaStream_t s, const float* Q, const float* sqQ, const float* 
 // K5 aps_filter.cu
 int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, int k, int64_t q0, int64_t q1,
                         const int32_t* img_of_row, const int64_t* img_off, float ratio_thr, int2* records);
+int aps_k_records_mutual(cudaStream_t s, int2* records, const int32_t* img_of_row, const int64_t* img_off, int64_t F,
+                         uint8_t* keep /* [F] scratch */);
 // compaction of per-query records into the CSR cell order (featureMatchingGlobal.m:149-159)
 int aps_k_fill_img_of_row(cudaStream_t s, const int64_t* img_off, int n, int64_t maxcount, int32_t* img_of_row);
 int aps_k_global_compact(cudaStream_t s, const int2* records /* [F]: (target image + 1 | 0, partner) */,

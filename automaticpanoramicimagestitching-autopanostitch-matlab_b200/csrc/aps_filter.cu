@@ -61,6 +61,35 @@ int aps_k_global_filter(cudaStream_t s, const uint32_t* idx, const float* dist, 
   return APS_OK;
 }
 
+// opt-in cross-check of the records: two passes so that every decision reads the ORIGINAL records
+__global__ void k_records_mutual_mark(const int2* __restrict__ rec, const int32_t* __restrict__ img_of_row,
+                                      const int64_t* __restrict__ img_off, int64_t F, uint8_t* __restrict__ keep) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= F) return;
+  const int2 r = rec[q];
+  uint8_t k = 0;
+  if (r.x > 0) {
+    const int64_t g = img_off[r.x - 1] + (int64_t)(uint32_t)r.y - 1;   // global row of the matched feature
+    const int2 b = rec[g];
+    k = (b.x == img_of_row[q] + 1) && ((int64_t)(uint32_t)b.y == q - img_off[img_of_row[q]] + 1);
+  }
+  keep[q] = k;
+}
+__global__ void k_records_mutual_apply(int2* __restrict__ rec, int64_t F, const uint8_t* __restrict__ keep) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < F && !keep[q]) rec[q] = make_int2(0, 0);
+}
+int aps_k_records_mutual(cudaStream_t s, int2* records, const int32_t* img_of_row, const int64_t* img_off, int64_t F,
+                         uint8_t* keep) {
+  if (F == 0) return APS_OK;
+  const unsigned grid = (unsigned)aps_ceil_div(F, 256);
+  k_records_mutual_mark<<<grid, 256, 0, s>>>(records, img_of_row, img_off, F, keep);
+  APS_LAUNCHED();
+  k_records_mutual_apply<<<grid, 256, 0, s>>>(records, F, keep);
+  APS_LAUNCHED();
+  return APS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5b  compaction.  Cell (a,b), a<b, holds first the accepted queries of image a (ascending local
 // index) then those of image b -- i.e. ascending GLOBAL query order.  One warp walks one image's

@@ -155,11 +155,24 @@ def featureMatchingGlobal(input, allDescriptors, numImg, ctx=None):
     k = int(_field(input, "k", required=True))
     ratio = float(_field(input, "Ratiothreshold", required=True))
     use_bf = bool(_field(input, "BFMatch", 0))
+    mutual = bool(int(_field(input, "apsMutual", 0)))   # opt-in cross-check, NOT reference behaviour (include/apsmatch.h)
     n, first, mats, counts, D, is_binary = _describe(allDescriptors, numImg)
     if first is None:
         return [[np.zeros((0, 0)) for _ in range(n)] for _ in range(n)]  # :49-52
     ptrs, cnt, layout, keep = _desc_args(mats, counts)
     h = C.c_void_p()
+    if mutual:
+        plan = GlobalPlan(ctx, counts, D, is_binary, k)
+        try:
+            plan.upload(mats)
+            plan.prepare()
+            plan.knn()
+            plan.filter(ratio)
+            plan.filter_mutual()
+            plan.compact()
+            return plan.download()[0]
+        finally:
+            plan.close()
     check(lib().aps_feature_matching_global(ctx.handle, ptrs, cnt, n, int(D), APS_U8 if is_binary else APS_F32, layout,
                                             k, ratio, int(use_bf), C.byref(h)))
     try:
@@ -200,6 +213,25 @@ def _resolve_method(input, method):
         warnings.warn("ApproxFloatNNMethod 'pca2nn' is served by the exhaustive search", ApsSemanticsWarning, stacklevel=3)
         return APS_METHOD["exhaustive"]
     raise ValueError("Select a approximate method")                      # :156-157
+
+
+def featureMatchingGlobalDevice(input, d_pooled, counts, D, is_binary=False, ctx=None):
+    """featureMatchingGlobal for descriptors that already live on the device (aps_feature_matching_global_dev):
+    d_pooled = device pointer (int) of the pooled ROW-major [sum(counts) x D] matrix, float32 or uint8 -- e.g. a torch
+    tensor's data_ptr().  Returns the same n x n nested list."""
+    ctx = ctx or default_context()
+    n = len(counts)
+    cnt = (C.c_int64 * max(n, 1))(*[int(c) for c in counts])
+    h = C.c_void_p()
+    check(lib().aps_feature_matching_global_dev(ctx.handle, C.c_void_p(int(d_pooled)), cnt, n, int(D),
+                                                APS_U8 if is_binary else APS_F32, int(_field(input, "k", required=True)),
+                                                float(_field(input, "Ratiothreshold", required=True)),
+                                                int(bool(int(_field(input, "apsMutual", 0)))), C.byref(h)))
+    try:
+        matches, _, _, _ = _cells_from_matchlist(h, n)
+    finally:
+        lib().aps_matchlist_free(h)
+    return matches
 
 
 def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metric=False, shard=None, csr=False):
@@ -720,6 +752,10 @@ class GlobalPlan:
     def filter(self, ratio, q0=0, q1=None):
         """K5a: self / same-image removal and Lowe ratio test of rows [q0, q1) (:123-147) -> records."""
         check(lib().aps_gplan_filter(self._h, int(q0), int(self.F if q1 is None else q1), float(ratio)))
+
+    def filter_mutual(self):
+        """Opt-in cross-check of the complete record set (not reference behaviour, see include/apsmatch.h)."""
+        check(lib().aps_gplan_filter_mutual(self._h))
 
     def compact(self):
         """K5b: scatter of all F records into the n x n cell in the reference's loop order (:149-159), CSR form."""

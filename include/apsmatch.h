@@ -151,6 +151,13 @@ int aps_match_features_bits(aps_ctx* ctx, const uint8_t* F1, int64_t N1, const u
 int aps_feature_matching_global(aps_ctx* ctx, const void* const* desc, const int64_t* counts, int n, int D,
                                 int dtype, int layout, int k, double ratio, int use_bf, aps_matchlist** out);
 
+/* Same stage for descriptors that already live on the device (the step before the path, PP/featureMatching/
+ * getFeaturePoints.m:32-74 -> allDescriptors, when the extractor runs on the GPU): d_pooled = pooled ROW-major [F x D]
+ * device matrix (image i = rows sum(counts[0..i)) ...), float32 or uint8.  mutual != 0 adds the opt-in cross-check
+ * (aps_gplan_filter_mutual).  The match list comes back on the host like aps_feature_matching_global's. */
+int aps_feature_matching_global_dev(aps_ctx* ctx, const void* d_pooled, const int64_t* counts, int n, int D, int dtype,
+                                    int k, double ratio, int mutual, aps_matchlist** out);
+
 /* ---- matches = featureMatchingPairwise(input, allDescriptors, numImg) ------------------------
  * PP/featureMatching/featureMatchingPairwise.m:1-63 with getMatches :103-120 on the
  * matchFeaturesScratch 'Exhaustive' branch (input.useMATLABFeatureMatch = 0), Unique = true. */
@@ -244,6 +251,11 @@ int aps_gplan_filter(aps_gplan* p, int64_t q0, int64_t q1, double ratio); /* K5a
  * equal-sized rank slices (multiples of 128 rows) run past F. */
 #define APS_RECORD_PAD 16384
 void* aps_gplan_records_device(aps_gplan* p);
+/* Opt-in cross-check (NOT reference behaviour: featureMatchingGlobal.m:149-159 keeps A->B and B->A rows alike and
+ * PP/mex/flann_knn.cpp:204 builds BFMatcher with crossCheck = false; BASELINE.json's "keeps mutual matches"): after
+ * filter() on every rank's rows and the record exchange, a query keeps its match only if the matched feature's own
+ * accepted match is that query.  Call between filter()/exchange and compact(). */
+int aps_gplan_filter_mutual(aps_gplan* p);
 void* aps_gplan_knn_idx_device(aps_gplan* p);  /* uint32 [F][k] row-major, 1-based */
 void* aps_gplan_knn_dist_device(aps_gplan* p); /* float  [F][k] row-major */
 /* D2H of the kNN table rows [q0,q1): idx/dist host buffers of (q1-q0)*k entries, row-major (synchronises) */

@@ -420,3 +420,67 @@ def test_pairwise_segment_epilogue_variant(aps, orc, cid, n, kp):
         assert stats["fallback_rows"] >= 1, stats
     if kp >= 500:  # (train images of one or two tiles have short lists, whose conservative bound sends ~10 % to the fallback)
         assert stats["fallback_rows"] < 0.05 * stats["rows"] + 16, stats
+
+
+def _oracle_mutual_cells(orc, desc, k, ratio):
+    """Opt-in cross-check restated on the oracle's records: keep q -> p only if p's accepted match is q."""
+    from oracle import oracle as O
+
+    ref = orc.feature_matching_global(desc, k, ratio, return_knn=True)
+    counts = np.array([d.shape[0] for d in desc], np.int64)
+    F, n = int(counts.sum()), len(desc)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    img = np.repeat(np.arange(n), counts)
+    tgt, par, _ = orc.global_filter(ref["knn_idx"], ref["knn_dist"], counts, ratio)
+    q = np.arange(F)
+    has = tgt > 0
+    g = np.where(has, off[np.maximum(tgt, 1) - 1] + par.astype(np.int64) - 1, 0)
+    keep = has & (tgt[g] == img + 1) & (par[g].astype(np.int64) == q - off[img] + 1)
+    tgt2 = np.where(keep, tgt, 0).astype(np.int32)
+    par2 = np.where(keep, par, 0).astype(np.uint32)
+    pp = np.zeros(n * n + 1, np.int64)
+    rows = np.zeros((max(F, 1), 2), np.uint32)
+    M = O.lib().orc_global_scatter(tgt2, par2, F, counts, n, pp, rows.reshape(-1))
+    return pp, rows[:M], int(has.sum())
+
+
+def test_global_opt_in_mutual_filter(aps, orc):
+    """BASELINE.json's "keeps mutual matches": an OPT-IN flag (input.apsMutual) -- the reference's global path keeps
+    A->B and B->A rows alike (featureMatchingGlobal.m:149-159).  Checked against the restated cross-check of the
+    oracle's records; off by default (every other test)."""
+    ctx = aps._lib.default_context()
+    for cid, n, kp in ((1, 5, 1500), (4, 4, 1200)):
+        desc, c = aps.synth.make_config(cid, n=n, kp=kp)
+        cells = [aps.binaryFeatures(d) for d in desc] if c["kind"] == "orb" else desc
+        got = aps.featureMatchingGlobal({"k": c["k"], "Ratiothreshold": 0.8, "BFMatch": 1, "apsMutual": 1}, cells, len(desc), ctx=ctx)
+        pp, rows, n_before = _oracle_mutual_cells(orc, desc, c["k"], 0.8)
+        total = 0
+        for j in range(len(desc)):
+            for i in range(j):
+                cidx = i + j * len(desc)
+                exp = rows[pp[cidx]:pp[cidx + 1]]
+                g = got[i][j]
+                assert (g.shape[0] == 0 and len(exp) == 0) or np.array_equal(g, exp.astype(np.float64)), (cid, i, j)
+                total += len(exp)
+        assert 0 < total < n_before and total % 2 == 0          # every surviving match appears from both sides
+
+
+def test_global_device_resident_descriptors(aps, orc):
+    """aps_feature_matching_global_dev: the pooled descriptor matrix already on the device (a GPU extractor's output)."""
+    import torch
+
+    ctx = aps._lib.default_context()
+    for cid, n, kp in ((1, 5, 1500), (4, 3, 900)):
+        desc, c = aps.synth.make_config(cid, n=n, kp=kp)
+        is_bin = c["kind"] == "orb"
+        pooled = torch.from_numpy(np.ascontiguousarray(np.concatenate(desc))).cuda()
+        inp = {"k": c["k"], "Ratiothreshold": c["ratio"], "BFMatch": 1}
+        got = aps.featureMatchingGlobalDevice(inp, pooled.data_ptr(), [d.shape[0] for d in desc], desc[0].shape[1], is_bin, ctx=ctx)
+        ref = orc.feature_matching_global(desc, c["k"], c["ratio"])["cells"]
+        for j in range(len(desc)):
+            for i in range(j):
+                exp = ref.get((i, j))
+                assert (exp is None and got[i][j].size == 0) or np.array_equal(got[i][j], exp.astype(np.float64)), (cid, i, j)
+    with pytest.raises(aps.ApsError):       # a host pointer is refused, not dereferenced
+        host_arr = np.zeros((64, 128), np.float32)
+        aps.featureMatchingGlobalDevice({"k": 4, "Ratiothreshold": 0.8}, host_arr.ctypes.data, [64], 128, False, ctx=ctx)
