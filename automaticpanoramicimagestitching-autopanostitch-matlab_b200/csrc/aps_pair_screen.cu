@@ -23,8 +23,6 @@
 // Roofline: tensor pipe (2*D FLOP per pair); operands stream from L2 (consecutive units share the train image).
 #include <cuda_fp16.h>
 
-#include <cstdlib>
-
 #include "aps_tc_ptx.cuh"
 
 namespace {
@@ -55,7 +53,6 @@ struct SParams {
   uint32_t* dump;       // tests: raw accumulator registers [entries][dump_tiles][64], else nullptr
   int dump_tiles;
   uint32_t idesc;       // tcgen05 instruction descriptor (kind::f16: F16 operands, F16 accumulators)
-  int variant;          // experiments (APS_SCREEN_VARIANT): 1 = epilogue skips the TMEM loads, 2 = polling waits
 };
 
 // 64 TMEM columns of 16-bit accumulators -> 32 registers of two packed fp16 (columns 2j, 2j+1 -> register j)
@@ -84,19 +81,6 @@ static __device__ __forceinline__ void tmem_wait_ld2(uint32_t (&a)[32], uint32_t
                     "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
                :
                : "memory");
-}
-static __device__ __forceinline__ void mbar_poll(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
 }
 static __device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b) {
   uint32_t d;
@@ -175,8 +159,8 @@ k_pair_screen(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int tl = x.t0 / TN, th = (x.t1 + TN - 1) / TN;
         for (int t = tl; t < th; ++t, ++tcount) {
           const uint32_t slot = (tcount % ACC_PHASES) * RB + r, acph = (tcount / ACC_PHASES) & 1;
-          if (P.variant & 2) { mbar_poll(&bars->acc_empty[slot], acph ^ 1); mbar_poll(&bars->b_full[bs], bph); }
-          else { mbar_wait(&bars->acc_empty[slot], acph ^ 1); mbar_wait(&bars->b_full[bs], bph); }
+          mbar_wait(&bars->acc_empty[slot], acph ^ 1);
+          mbar_wait(&bars->b_full[bs], bph);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(smem_b + bs * b_bytes);
           const uint32_t d_tmem = tmem_base + slot * ACC_COLS;
@@ -205,18 +189,13 @@ k_pair_screen(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint32_t m[4] = {NEG2, NEG2, NEG2, NEG2};   // class maxima: m[i].lo = columns == 2i (mod 8), m[i].hi = 2i+1 (mod 8)
       for (int t = tl; t < th; ++t, ++tcount) {
         const uint32_t slot = (tcount % ACC_PHASES) * RB + grp, acph = (tcount / ACC_PHASES) & 1;
-        if (P.variant & 2) mbar_poll(&bars->acc_full[slot], acph); else mbar_wait(&bars->acc_full[slot], acph);
+        mbar_wait(&bars->acc_full[slot], acph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * ACC_COLS;
         uint32_t va[32], vb[32];
-        if (P.variant & 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { va[j] = NEG2; vb[j] = NEG2; }
-        } else {
-          tmem_ld64p(taddr, va);
-          tmem_ld64p(taddr + 64, vb);
-          tmem_wait_ld2(va, vb);
-        }
+        tmem_ld64p(taddr, va);
+        tmem_ld64p(taddr + 64, vb);
+        tmem_wait_ld2(va, vb);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);   // registers hold the tile: the slot can be refilled
@@ -399,9 +378,6 @@ int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh, int64_t F, i
   P.dump = dump;
   P.dump_tiles = dump_tiles;
   P.idesc = make_idesc_f16_f16acc(TM, TN);
-  if (const char* e = getenv("APS_SCREEN_IDESC")) P.idesc = (uint32_t)strtoul(e, nullptr, 16);   // experiments only
-  P.variant = 0;
-  if (const char* e = getenv("APS_SCREEN_VARIANT")) P.variant = atoi(e);
   const size_t smem = 1024 + (size_t)P.a_bufs * RB * TM * Dp * 2 + (size_t)P.b_stages * TN * Dp * 2 + sizeof(Bars);
   APS_CUDA(cudaFuncSetAttribute(k_pair_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);

@@ -62,10 +62,14 @@ int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass 1.  WARP-centric: each warp stages 32 rows in its own shared-memory tile with coalesced loads, then lane r
-// walks row r: the per-row sums are SEQUENTIAL float32 (one rounding per operation, no FMA) so that the normalised
-// values carry the same bits as the oracle's / the reference's single-precision arithmetic.  No block-wide barrier;
-// row stride D+1 floats makes the per-lane walks bank-conflict free.  HBM streaming: reads 4D, writes 4D + 8 per row.
+// pass 1.  WARP-centric: each warp stages 32 rows in its own shared-memory tile with coalesced (float4) loads; the
+// divisions x/norm are done by all lanes on coalesced elements, and lane r walks row r for the sums of squares in
+// column order: the per-row sums stay SEQUENTIAL float32 (one rounding per operation, no FMA) so that the
+// normalised values carry the same bits as the oracle's / the reference's single-precision arithmetic.  No block-wide
+// barrier; row stride D+1 floats makes the per-lane walks bank-conflict free.  Measured (ncu, C2: 163840 x 128): 118 us
+// for 84 MB read + 84 MB written = 1.4 TB/s, 0.22 of the HBM peak -- INSTRUCTION bound, not bandwidth bound: IPC 1.46,
+// ~80 warp instructions per element-row, most of them the correctly rounded IEEE divisions (__fdiv_rn) and the
+// exactness test; x * (1/n) would be 4x cheaper but does not give the oracle's bits (profiles/r2_ncu_aux_kernels.txt).  HBM streaming: reads 4D, writes 4D + 8 per row.
 // img_off != nullptr: blockIdx.y = image, rows [img_off[y], img_off[y+1]) with its own flag words flags + 8*y (the
 // per-image magnitude test of the pairwise path in ONE launch)
 constexpr int PN_WARPS = 4;   // warps per block; shared memory = PN_WARPS * 32 * (D+1) * 4 bytes
@@ -87,46 +91,94 @@ __global__ void __launch_bounds__(32 * PN_WARPS) k_prepare_norm(const float* __r
   int exact = 1;
   float maxabs = 0.f, maxdev = 0.f, maxsq = 0.f;
   const bool write_xn = (xn != raw) || norm_mode != APS_NORM_NONE;
+  const bool vec4 = (D % 4 == 0) && ((((uintptr_t)raw) | ((uintptr_t)xn)) % 16 == 0);
   for (int64_t r0 = row_lo + ((int64_t)blockIdx.x * PN_WARPS + warp) * 32; r0 < F; r0 += (int64_t)gridDim.x * PN_WARPS * 32) {
     const int nr = (int)min((int64_t)32, F - r0);
-    const int64_t n_el = (int64_t)nr * D;
+    const int n_el = nr * D;
     const float* src = raw + r0 * D;
-    // coalesced load of nr consecutive rows ((row, column) advance by a fixed step: no division in the loop)
-    const int step_r = 32 / D, step_c = 32 - step_r * D;
-    for (int i = lane, r = lane / D, c = lane - (lane / D) * D; i < n_el; i += 32) {
-      const float v = src[i];
-      tile[r * ld + c] = v;
-      exact &= fp16 ? (__half2float(__float2half_rn(v)) == v) : (__bfloat162float(__float2bfloat16_rn(v)) == v);
-      maxabs = fmaxf(maxabs, fabsf(v));
-      r += step_r; c += step_c; if (c >= D) { c -= D; ++r; }
-    }
-    __syncwarp();
-    if (lane < nr) {
-      float* x = tile + lane * ld;
-      float sum = 0.f;
-      for (int c = 0; c < D; ++c) sum = __fadd_rn(sum, __fmul_rn(x[c], x[c]));
-      float n = 1.0f;
-      if (norm_mode == APS_NORM_GLOBAL) n = __fsqrt_rn(__fadd_rn(sum, APS_EPS32));      // featureMatchingGlobal.m:83-84
-      if (norm_mode == APS_NORM_PAIRWISE) n = __fadd_rn(__fsqrt_rn(sum), APS_EPS32);    // matchFeaturesScratch.m:232
-      if (norm_mode != APS_NORM_NONE) {
-        sum = 0.f;
-        for (int c = 0; c < D; ++c) {
-          const float v = __fdiv_rn(x[c], n);
-          x[c] = v;
-          sum = __fadd_rn(sum, __fmul_rn(v, v));
+    // phase A (all lanes, coalesced): load the rows, keep value and square
+    if (vec4) {
+      const int d4 = D / 4, n4 = n_el / 4;
+      for (int i0 = 0; i0 < n4; i0 += 32 * 8) {   // 8 independent 16-byte loads per lane in flight
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          v[u] = i < n4 ? *reinterpret_cast<const float4*>(src + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          if (i < n4) {
+            const int r = i / d4, c = (i - r * d4) * 4;
+            const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              tile[r * ld + c + j] = e[j];
+              exact &= fp16 ? (__half2float(__float2half_rn(e[j])) == e[j]) : (__bfloat162float(__float2bfloat16_rn(e[j])) == e[j]);
+              maxabs = fmaxf(maxabs, fabsf(e[j]));
+            }
+          }
         }
       }
+    } else {
+      const int step_r = 32 / D, step_c = 32 - step_r * D;
+      for (int i = lane, r = lane / D, c = lane - (lane / D) * D; i < n_el; i += 32) {
+        const float v = src[i];
+        tile[r * ld + c] = v;
+        exact &= fp16 ? (__half2float(__float2half_rn(v)) == v) : (__bfloat162float(__float2bfloat16_rn(v)) == v);
+        maxabs = fmaxf(maxabs, fabsf(v));
+        r += step_r; c += step_c; if (c >= D) { c -= D; ++r; }
+      }
+    }
+    __syncwarp();
+    // phase B (lane = row): the SEQUENTIAL sum of the squares, then the row's norm
+    float n = 1.0f, sum = 0.f;
+    if (lane < nr) {
+      const float* x = tile + lane * ld;
+#pragma unroll 8
+      for (int c = 0; c < D; ++c) sum = __fadd_rn(sum, __fmul_rn(x[c], x[c]));
+      if (norm_mode == APS_NORM_GLOBAL) n = __fsqrt_rn(__fadd_rn(sum, APS_EPS32));      // featureMatchingGlobal.m:83-84
+      if (norm_mode == APS_NORM_PAIRWISE) n = __fadd_rn(__fsqrt_rn(sum), APS_EPS32);    // matchFeaturesScratch.m:232
+    }
+    if (norm_mode != APS_NORM_NONE) {
+      // phase C (all lanes): divide by the row's norm, store the normalised value and its square
+      for (int r = 0; r < nr; ++r) {
+        const float nrm = __shfl_sync(0xffffffffu, n, r);
+        for (int c = lane; c < D; c += 32) {
+          tile[r * ld + c] = __fdiv_rn(tile[r * ld + c], nrm);
+        }
+      }
+      __syncwarp();
+      // phase D (lane = row): sequential sum of the normalised squares
+      if (lane < nr) {
+        const float* x = tile + lane * ld;
+        sum = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < D; ++c) sum = __fadd_rn(sum, __fmul_rn(x[c], x[c]));
+      }
+    }
+    if (lane < nr) {
       sq[r0 + lane] = sum;
       invn[r0 + lane] = __fdiv_rn(1.0f, n);
       maxdev = fmaxf(maxdev, fabsf(sum - 1.0f));
       maxsq = fmaxf(maxsq, sum);
     }
-    __syncwarp();
     if (write_xn) {
       float* dst = xn + r0 * D;
-      for (int i = lane, r = lane / D, c = lane - (lane / D) * D; i < n_el; i += 32) {
-        dst[i] = tile[r * ld + c];
-        r += step_r; c += step_c; if (c >= D) { c -= D; ++r; }
+      if (vec4) {
+        const int d4 = D / 4, n4 = n_el / 4;
+        for (int i = lane; i < n4; i += 32) {
+          const int r = i / d4, c = (i - r * d4) * 4;
+          const float* t = tile + r * ld + c;
+          *reinterpret_cast<float4*>(dst + 4 * (size_t)i) = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      } else {
+        const int step_r = 32 / D, step_c = 32 - step_r * D;
+        for (int i = lane, r = lane / D, c = lane - (lane / D) * D; i < n_el; i += 32) {
+          dst[i] = tile[r * ld + c];
+          r += step_r; c += step_c; if (c >= D) { c -= D; ++r; }
+        }
       }
     }
     __syncwarp();
@@ -139,10 +191,12 @@ __global__ void __launch_bounds__(32 * PN_WARPS) k_prepare_norm(const float* __r
     maxsq = fmaxf(maxsq, __shfl_xor_sync(0xffffffffu, maxsq, o));
   }
   if (lane == 0) {
-    if (!exact) atomicAnd(&flags[0], 0);
-    atomicMax(&flags[1], __float_as_int(maxdev));
-    atomicMax(&flags[2], __float_as_int(maxsq));
-    atomicMax(&flags[3], __float_as_int(maxabs));
+    // the maxima are monotone: a plain read first lets almost every warp skip its atomic on the four shared words
+    volatile int32_t* f = flags;
+    if (!exact && f[0] != 0) atomicAnd(&flags[0], 0);
+    if (__float_as_int(maxdev) > f[1]) atomicMax(&flags[1], __float_as_int(maxdev));
+    if (__float_as_int(maxsq) > f[2]) atomicMax(&flags[2], __float_as_int(maxsq));
+    if (__float_as_int(maxabs) > f[3]) atomicMax(&flags[3], __float_as_int(maxabs));
   }
 }
 
