@@ -83,8 +83,12 @@ int launch_nw(cudaStream_t s, const uint8_t* Q, int64_t q0, int64_t nq, const ui
     k_knn_hamming<NW, 2><<<grid, HQ, 0, s>>>(q4, q0, nq, t4, t0, t1, k, out_row0, idx, dist);
   else if (k <= 4)
     k_knn_hamming<NW, 4><<<grid, HQ, 0, s>>>(q4, q0, nq, t4, t0, t1, k, out_row0, idx, dist);
-  else
+  else if (k <= 8)
     k_knn_hamming<NW, 8><<<grid, HQ, 0, s>>>(q4, q0, nq, t4, t0, t1, k, out_row0, idx, dist);
+  else if (k <= 16)
+    k_knn_hamming<NW, 16><<<grid, HQ, 0, s>>>(q4, q0, nq, t4, t0, t1, k, out_row0, idx, dist);
+  else
+    k_knn_hamming<NW, 32><<<grid, HQ, 0, s>>>(q4, q0, nq, t4, t0, t1, k, out_row0, idx, dist);
   APS_LAUNCHED();
   return APS_OK;
 }

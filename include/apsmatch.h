@@ -48,7 +48,9 @@ enum aps_status {
 enum aps_layout { APS_COL_MAJOR = 0, APS_ROW_MAJOR = 1 };
 enum aps_dtype { APS_F32 = 0, APS_U8 = 1 };
 
-#define APS_MAX_K 8 /* neighbours per query supported by the kNN entry points (reference uses 4 and 2) */
+#define APS_MAX_K 32 /* neighbours per query supported by the kNN entry points; the reference accepts any k > 0
+                       (PP/mex/flann_knn.cpp:154-157) and its pipeline uses input.k = 4 and 2.  k <= 5 on float descriptors
+                       runs the tcgen05 search, larger k the exact CUDA-core engine; above 32: flann_knn:k */
 
 typedef struct aps_ctx aps_ctx;             /* one per (process, GPU): device buffers, stream          */
 typedef struct aps_matchlist aps_matchlist; /* CSR form of the reference's n x n `matches` cell        */

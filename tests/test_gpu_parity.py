@@ -262,7 +262,7 @@ def test_flann_knn_binary_k_sweep_and_widths(aps, orc):
     rng = np.random.default_rng(3)
     for nb in (16, 32, 48, 64):
         T = rng.integers(0, 256, (2000, nb), dtype=np.uint8)
-        for k in (1, 2, 4, 7):
+        for k in (1, 2, 4, 7, 12, 32):
             idx, dist = aps.flann_knn_win(T, T[:300].copy(), k, "bf")
             oi, od = orc.knn_hamming(T, T[:300], k)
             assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nb, k)
@@ -484,3 +484,27 @@ def test_global_device_resident_descriptors(aps, orc):
     with pytest.raises(aps.ApsError):       # a host pointer is refused, not dereferenced
         host_arr = np.zeros((64, 128), np.float32)
         aps.featureMatchingGlobalDevice({"k": 4, "Ratiothreshold": 0.8}, host_arr.ctypes.data, [64], 128, False, ctx=ctx)
+
+
+@pytest.mark.parametrize("k", [9, 16, 32])
+def test_flann_knn_large_k(aps, orc, k):
+    """k up to APS_MAX_K = 32 (the reference accepts any k, flann_knn.cpp:154-157): exact engine; one more is flann_knn:k;
+    a global matching with input.k = 12 against the oracle."""
+    rng = np.random.default_rng(100 + k)
+    X = rng.standard_normal((3000, 64)).astype(np.float32)
+    X[20:30] = X[20]
+    idx, dist = aps.flann_knn_win(X, X[:500].copy(), k)
+    oi, od = orc.knn_l2(X, X[:500], k)
+    assert np.array_equal(idx, oi) and np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+    if k == 32:
+        with pytest.raises(aps.ApsError) as e:
+            aps.flann_knn_win(X, X[:10].copy(), 33)
+        assert e.value.identifier == "flann_knn:k"
+    if k == 9:
+        desc, c = aps.synth.make_config(1, n=4, kp=900)
+        got = aps.featureMatchingGlobal({"k": 12, "Ratiothreshold": 0.7}, desc, len(desc))
+        ref = orc.feature_matching_global(desc, 12, 0.7)["cells"]
+        for j in range(len(desc)):
+            for i in range(j):
+                exp = ref.get((i, j))
+                assert (exp is None and got[i][j].size == 0) or np.array_equal(got[i][j], exp.astype(np.float64)), (i, j)
