@@ -141,7 +141,8 @@ def lib():
         "aps_pplan_upload": (i32, [vp, pp, i32]),
         "aps_pplan_prepare": (i32, [vp]),
         "aps_pplan_match": (i32, [vp, dbl, dbl, i32, i32, pp]),
-        "aps_pplan_set_method": (i32, [vp, i32, i64]),
+        "aps_pplan_set_method": (i32, [vp, i32, i64, C.c_uint64]),
+        "aps_pplan_subset_table": (i32, [vp, i32, vp]),
         "aps_debug_tc_slots": (i32, [vp, i64, i64]),
         "aps_debug_pair_screen": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, i32]),
         "aps_debug_tc_scores": (i32, [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),

@@ -1032,7 +1032,41 @@ struct PairwiseSets {
   DevBuf<float> ones;    // [F + 256] column scales of the fp16 operand rows (they hold the values themselves: scale 1)
   DevBuf<float2> bounds_raw, bounds_norm;
   DevBuf<int64_t> d_img_off;
+  // TRAIN VIEW.  Normally the set's own rows.  'subsetpdist2' with images above the subset size: extended copies whose
+  // rows [Freal, Freal + nbig * vcnt) hold, per big image, the rows candB = randperm-like subset (a "virtual image").
+  int64_t Freal = 0, vcnt = 0;
+  std::vector<int64_t> voff;   // per image: first row of its virtual image in the train view, -1 = use the real rows
+  DevBuf<int32_t> vsrc, vmap, d_big;
+  DevBuf<float> tv_xn[2], tv_sq[2], tv_colbias[2], tv_ones;   // [0] un-normalised view, [1] normalised view
+  DevBuf<uint16_t> tv_xh[2];
+  DevBuf<int64_t> d_tstart, d_tcount;
+  bool subsets() const { return !voff.empty(); }
+  int64_t toff(int j) const { return (subsets() && voff[j] >= 0) ? voff[j] : off[j]; }
+  int64_t tcnt(int j, const int64_t* counts) const { return (subsets() && voff[j] >= 0) ? vcnt : counts[j]; }
 };
+
+// what the pairwise kernels read on the train side
+struct TrainView {
+  const float* xn;
+  const float* sq;
+  const void* xh;
+  const float* colbias;
+  const float* ones;
+  int64_t N;
+};
+static TrainView train_view(const PairwiseSets& ps, bool norm) {
+  const FloatSet& S = norm ? ps.normset : ps.rawset;
+  TrainView v;
+  const int w = norm ? 1 : 0;
+  if (ps.subsets() && ps.tv_xn[w].p) {
+    v.xn = ps.tv_xn[w].p; v.sq = ps.tv_sq[w].p; v.xh = ps.tv_xh[w].p; v.colbias = ps.tv_colbias[w].p; v.ones = ps.tv_ones.p;
+    v.N = ps.Freal + (int64_t)ps.vcnt * (int64_t)(ps.vsrc.n / (ps.vcnt > 0 ? ps.vcnt : 1));
+  } else {
+    v.xn = S.xn.p ? S.xn.p : S.raw.p; v.sq = S.sq.p; v.xh = norm ? (const void*)ps.xh_norm.p : (const void*)ps.xh_raw.p;
+    v.colbias = S.colbias.p; v.ones = ps.ones.p; v.N = S.N;
+  }
+  return v;
+}
 
 // allocation of the pooled raw matrix + bookkeeping
 static int pairwise_alloc(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, int n, int D, int dtype) {
@@ -1130,7 +1164,6 @@ static int pairwise_finish(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, 
     APS_TRY(ps.ones.alloc((size_t)F + 256, c->stream));
     APS_TRY(aps_k_fill_f32(c->stream, ps.ones.p, F + 256, 1.0f));
     APS_TRY(aps_k_prepare_operands_f16(c->stream, ps.rawset.raw.p, F, D, Dp, ps.xh_raw.p));
-    APS_TRY(aps_k_image_sq_bounds(c->stream, ps.rawset.sq.p, ps.d_img_off.p, n, ps.bounds_raw.p));
   }
   if (any_big) {
     APS_TRY(floatset_alloc(c, ps.normset, F, D));
@@ -1143,7 +1176,81 @@ static int pairwise_finish(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, 
       APS_TRY(ps.xh_norm.alloc((size_t)F * Dp, c->stream));
       APS_TRY(ps.bounds_norm.alloc((size_t)n, c->stream));
       APS_TRY(aps_k_prepare_operands_f16(c->stream, ps.normset.xn.p, F, D, Dp, ps.xh_norm.p));
-      APS_TRY(aps_k_image_sq_bounds(c->stream, ps.normset.sq.p, ps.d_img_off.p, n, ps.bounds_norm.p));
+    }
+  }
+  return APS_OK;
+}
+
+// Train view of the staged plan (after pairwise_finish): per-image norm bounds of the screen, and -- for 'subsetpdist2'
+// with images above `subset` rows -- the virtual subset images (matchFeaturesScratch.m:388-393: candB = randperm(N2,
+// subset), B2 = B(candB,:); here ONE subset per train image, drawn by a keyed bijection, instead of one per call).
+static int pairwise_build_train_view(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, int n, int D, bool tensor,
+                                     int64_t subset, uint64_t seed) {
+  cudaStream_t s = c->stream;
+  const int64_t F = ps.off[n];
+  ps.Freal = F;
+  ps.voff.clear();
+  ps.vcnt = 0;
+  if (F == 0) return APS_OK;
+  std::vector<int32_t> big;
+  if (subset > 0)
+    for (int j = 0; j < n; ++j)
+      if (counts[j] > subset) big.push_back(j);
+  const int Dp = (D + 63) / 64 * 64;
+  if (!big.empty()) {
+    const int nbig = (int)big.size();
+    const int64_t V = (int64_t)nbig * subset;
+    if (F + V >= ((int64_t)1 << 31) - 512) APS_FAIL(APS_ERR_ARGS, "", "too many descriptors for the subset views");
+    ps.voff.assign(n, -1);
+    ps.vcnt = subset;
+    for (int b = 0; b < nbig; ++b) ps.voff[big[b]] = F + (int64_t)b * subset;
+    APS_TRY(ps.d_big.alloc((size_t)nbig, s));
+    APS_TRY(ps.vsrc.alloc((size_t)V, s));
+    APS_TRY(ps.vmap.alloc((size_t)V, s));
+    APS_CUDA(cudaMemcpyAsync(ps.d_big.p, big.data(), (size_t)nbig * 4, cudaMemcpyHostToDevice, s));
+    APS_CUDA(cudaStreamSynchronize(s));   // `big` is pageable host memory
+    APS_TRY(aps_k_subset_rows(s, ps.d_img_off.p, ps.d_big.p, nbig, subset, seed, ps.vsrc.p, ps.vmap.p));
+    APS_TRY(ps.tv_ones.alloc((size_t)(F + V) + 256, s));
+    APS_TRY(aps_k_fill_f32(s, ps.tv_ones.p, F + V + 256, 1.0f));
+    for (int w = 0; w < 2; ++w) {
+      const FloatSet& S = w ? ps.normset : ps.rawset;
+      if (S.N == 0) continue;
+      const float* xn = S.xn.p ? S.xn.p : S.raw.p;
+      const uint16_t* xh = w ? ps.xh_norm.p : ps.xh_raw.p;
+      APS_TRY(ps.tv_xn[w].alloc((size_t)(F + V) * D, s));
+      APS_TRY(ps.tv_sq[w].alloc((size_t)(F + V), s));
+      APS_CUDA(cudaMemcpyAsync(ps.tv_xn[w].p, xn, (size_t)F * D * 4, cudaMemcpyDeviceToDevice, s));
+      APS_CUDA(cudaMemcpyAsync(ps.tv_sq[w].p, S.sq.p, (size_t)F * 4, cudaMemcpyDeviceToDevice, s));
+      APS_TRY(aps_k_gather_f32_rows(s, xn, ps.vsrc.p, V, D, ps.tv_xn[w].p + (size_t)F * D));
+      APS_TRY(aps_k_gather_f32_rows(s, S.sq.p, ps.vsrc.p, V, 1, ps.tv_sq[w].p + F));
+      if (tensor && xh) {
+        APS_TRY(ps.tv_xh[w].alloc((size_t)(F + V) * Dp, s));
+        APS_TRY(ps.tv_colbias[w].alloc((size_t)(F + V) + 256, s));
+        APS_CUDA(cudaMemcpyAsync(ps.tv_xh[w].p, xh, (size_t)F * Dp * 2, cudaMemcpyDeviceToDevice, s));
+        APS_TRY(aps_k_gather_u16_rows(s, xh, ps.vsrc.p, V, Dp, ps.tv_xh[w].p + (size_t)F * Dp));
+        APS_CUDA(cudaMemsetAsync(ps.tv_colbias[w].p, 0, ((size_t)(F + V) + 256) * 4, s));
+        if (S.colbias.p) {
+          APS_CUDA(cudaMemcpyAsync(ps.tv_colbias[w].p, S.colbias.p, (size_t)F * 4, cudaMemcpyDeviceToDevice, s));
+          APS_TRY(aps_k_gather_f32_rows(s, S.colbias.p, ps.vsrc.p, V, 1, ps.tv_colbias[w].p + F));
+        }
+      }
+    }
+  }
+  if (tensor) {   // per TRAIN image (real rows or its subset): (min, max) of the squared norms, for the screen's bounds
+    std::vector<int64_t> st((size_t)n * 2);
+    for (int j = 0; j < n; ++j) {
+      st[j] = ps.toff(j);
+      st[(size_t)n + j] = ps.tcnt(j, counts);
+    }
+    APS_TRY(ps.d_tstart.alloc((size_t)n * 2, s));
+    APS_CUDA(cudaMemcpyAsync(ps.d_tstart.p, st.data(), st.size() * 8, cudaMemcpyHostToDevice, s));
+    APS_CUDA(cudaStreamSynchronize(s));
+    for (int w = 0; w < 2; ++w) {
+      const FloatSet& S = w ? ps.normset : ps.rawset;
+      DevBuf<float2>& bo = w ? ps.bounds_norm : ps.bounds_raw;
+      if (S.N == 0 || !bo.p) continue;
+      const TrainView tv = train_view(ps, w == 1);
+      APS_TRY(aps_k_image_sq_bounds(s, tv.sq, ps.d_tstart.p, ps.d_tstart.p + n, n, bo.p));
     }
   }
   return APS_OK;
@@ -1153,7 +1260,9 @@ static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* des
                             int D, int dtype, int layout, bool tensor) {
   APS_TRY(pairwise_alloc(c, ps, counts, n, D, dtype));
   APS_TRY(pairwise_upload(c, ps, desc, counts, n, D, dtype, layout));
-  return pairwise_finish(c, ps, counts, n, D, dtype, tensor);
+  APS_TRY(pairwise_finish(c, ps, counts, n, D, dtype, tensor));
+  if (dtype == APS_F32) APS_TRY(pairwise_build_train_view(c, ps, counts, n, D, tensor, 0, 0));
+  return APS_OK;
 }
 
 // one pair on the device: results into caller regions; count stays on the device
@@ -1321,10 +1430,10 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   std::vector<int32_t> qoff(np), toff(np), tcnt(np);
   for (int p = 0; p < np; ++p) {
     eoff[p + 1] = eoff[p] + counts[pairs[p].i];
-    boff[p + 1] = boff[p] + counts[pairs[p].j];
+    boff[p + 1] = boff[p] + ps.tcnt(pairs[p].j, counts);
     qoff[p] = (int32_t)ps.off[pairs[p].i];
-    toff[p] = (int32_t)ps.off[pairs[p].j];
-    tcnt[p] = (int32_t)counts[pairs[p].j];
+    toff[p] = (int32_t)ps.toff(pairs[p].j);       // the train image's rows, or its subset view ('subsetpdist2')
+    tcnt[p] = (int32_t)ps.tcnt(pairs[p].j, counts);
   }
   const int64_t E = eoff[np], B = boff[np];
   DevBuf<int64_t> d_eoff, d_boff;
@@ -1357,6 +1466,10 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   aps_pair_tables pt;
   memset(&pt, 0, sizeof pt);
   pt.eoff = d_eoff.p; pt.qoff = d_qoff.p; pt.toff = d_toff.p; pt.tcnt = d_tcnt.p; pt.boff = d_boff.p; pt.npairs = np;
+  if (dtype == APS_F32 && ps.subsets()) {
+    pt.vmap = ps.vmap.p;
+    pt.vfirst = ps.Freal;
+  }
 
   if (dtype == APS_U8) {
     APS_TRY(aps_k_pairs_hamming2(s, ps.u8pad.p, ps.nb16, eoff, qoff, toff, tcnt, i2.p, dd.p));
@@ -1366,6 +1479,7 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   } else {
     FloatSet& S = norm ? ps.normset : ps.rawset;
     const FloatSide side = S.side();
+    const TrainView tv = train_view(ps, norm);
     const int bias_mode = norm ? 0 : 1;
     c->stats[0] += E;
     if (tensor) {
@@ -1409,12 +1523,12 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       // term in the proof's eps than bf16, so far fewer rows end in the exact fallback
       const void* xh = norm ? (const void*)ps.xh_norm.p : (const void*)ps.xh_raw.p;
       tp.Qb = xh ? (const __nv_bfloat16*)xh : side.xb;
-      tp.Tb = xh ? (const __nv_bfloat16*)xh : side.xb_t;
+      tp.Tb = xh ? (const __nv_bfloat16*)tv.xh : side.xb_t;
       tp.operand_fp16 = xh ? 1 : 0;
-      tp.colscale = xh ? ps.ones.p : side.colscale_t;
-      tp.colbias = side.colbias_t;
+      tp.colscale = xh ? tv.ones : side.colscale_t;
+      tp.colbias = xh ? tv.colbias : side.colbias_t;
       tp.tile_bounds = side.tile_bounds; tp.bias = bias_mode;
-      tp.Fq_total = side.N; tp.Ft_total = side.N; tp.Dp = (D + 63) / 64 * 64;
+      tp.Fq_total = side.N; tp.Ft_total = xh ? tv.N : side.N; tp.Dp = (D + 63) / 64 * 64;
       tp.q0 = 0; tp.q1 = 0; tp.t0 = 0; tp.t1 = 0; tp.nslot = 1; tp.kcand = KCP;
       tp.cand_idx = cidx.p; tp.cand_score = cscore.p; tp.dump = nullptr;
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1435,14 +1549,14 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       ptr_.prune_mt = match_threshold;
       ptr_.tile_mode = KCP == 3 ? aps_k_knn_tc_tile_mode_segment() : 0;
       ptr_.operand_fp16 = tp.operand_fp16;
-      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, side.xn, side.sq, D, dist_metric, 0, E, 0, nlist, KCP, cidx.p,
+      APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, tv.xn, tv.sq, D, dist_metric, 0, E, 0, nlist, KCP, cidx.p,
                            cscore.p, S.flags.p, bias_mode, S.flags.p, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &ptr_));
-      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, dist_metric, pt, fb.p, fb.p + E, E, i2.p, dd.p));
+      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, tv.xn, tv.sq, D, dist_metric, pt, fb.p, fb.p + E, E, i2.p, dd.p));
       APS_CUDA(cudaMemcpyAsync(c->h_flags + 33, fb.p + E, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     } else {
       c->stats[2] = 1;
       APS_CUDA(cudaStreamSynchronize(s));
-      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, D, dist_metric, pt, nullptr, nullptr, E, i2.p, dd.p));
+      APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, tv.xn, tv.sq, D, dist_metric, pt, nullptr, nullptr, E, i2.p, dd.p));
     }
     APS_TRY(aps_k_pairs_k2_to_nn(s, pt, E, 0, 0, i2.p, dd.p, idx2.p, d1.p, d2.p));
     APS_TRY(aps_k_pairs_filter_unique(s, pt, E, B, idx2.p, d1.p, d2.p, 0, 0, match_threshold, max_ratio, best.p, keys.p,
@@ -1504,8 +1618,8 @@ static int pairwise_screen_stage(aps_ctx* c, PairwiseSets& ps, std::vector<PairR
   for (int p = 0; p < np; ++p) {
     qoff[p] = (int32_t)ps.off[pairs[p].i];
     qcnt[p] = (int32_t)counts[pairs[p].i];
-    toff[p] = (int32_t)ps.off[pairs[p].j];
-    tcnt[p] = (int32_t)counts[pairs[p].j];
+    toff[p] = (int32_t)ps.toff(pairs[p].j);
+    tcnt[p] = (int32_t)ps.tcnt(pairs[p].j, counts);
     timg[p] = pairs[p].j;
     eoff[p + 1] = eoff[p] + counts[pairs[p].i];
     uoff[p + 1] = uoff[p] + (counts[pairs[p].i] + 255) / 256;
@@ -1531,7 +1645,8 @@ static int pairwise_screen_stage(aps_ctx* c, PairwiseSets& ps, std::vector<PairR
     APS_CUDA(cudaEventCreate(&ev1));
     APS_CUDA(cudaEventRecord(ev0, s));
   }
-  APS_TRY(aps_k_pair_screen(s, c->sm_count, xh, S.N, Dp, t, d_units.p, U, scr.p));
+  const TrainView tv = train_view(ps, norm);
+  APS_TRY(aps_k_pair_screen(s, c->sm_count, xh, S.N, tv.xh, tv.N, Dp, t, d_units.p, U, scr.p));
   if (c->timing) {
     APS_CUDA(cudaEventRecord(ev1, s));
     c->tc_events.push_back(ev0);
@@ -1562,6 +1677,7 @@ struct aps_pplan {
   bool tensor = false, prepared = false;
   int method = APS_METHOD_EXHAUSTIVE;  // aps_pplan_set_method
   int64_t subset = 12000;
+  uint64_t seed = 0;
   PairwiseSets ps;
 };
 
@@ -1622,17 +1738,33 @@ extern "C" int aps_pplan_prepare(aps_pplan* p) {
   if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
   APS_CTX(p->c);
   APS_TRY(pairwise_finish(p->c, p->ps, p->counts.data(), p->n, p->D, p->dtype, p->tensor));
+  if (p->dtype == APS_F32)
+    APS_TRY(pairwise_build_train_view(p->c, p->ps, p->counts.data(), p->n, p->D, p->tensor,
+                                      p->method == APS_METHOD_APPROX_SUBSETPDIST2 ? p->subset : 0, p->seed));
   p->prepared = true;
   return APS_OK;
 }
 
-extern "C" int aps_pplan_set_method(aps_pplan* p, int method, int64_t subset) {
+extern "C" int aps_pplan_subset_table(aps_pplan* p, int image, int32_t* out) {
+  if (!p || !out || image < 0 || image >= p->n) APS_FAIL(APS_ERR_ARGS, "", "bad arguments");
+  APS_CTX(p->c);
+  if (!p->prepared || !p->ps.subsets() || p->ps.voff[image] < 0)
+    APS_FAIL(APS_ERR_ARGS, "", "image %d has no subset view (prepare() with 'subsetpdist2' and more rows than the subset)", image);
+  const int64_t o = p->ps.voff[image] - p->ps.Freal;
+  APS_CUDA(cudaMemcpyAsync(out, p->ps.vmap.p + o, (size_t)p->ps.vcnt * 4, cudaMemcpyDeviceToHost, p->c->stream));
+  APS_CUDA(cudaStreamSynchronize(p->c->stream));
+  return APS_OK;
+}
+
+extern "C" int aps_pplan_set_method(aps_pplan* p, int method, int64_t subset, uint64_t seed) {
   if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
   if (method < APS_METHOD_EXHAUSTIVE || method > APS_METHOD_APPROX_KDTREE)
     APS_FAIL(APS_ERR_METHOD, "", "Select a approximate method");   // matchFeaturesScratch.m:156-157
   if (subset < 1) APS_FAIL(APS_ERR_ARGS, "", "subset must be positive");
   p->method = method;
   p->subset = subset;
+  p->seed = seed;
+  p->prepared = false;   // the train view depends on the method
   return APS_OK;
 }
 
@@ -1645,11 +1777,7 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
   // float descriptors: 1 = (a2 + b2) - 2 G of nearest2SSDExhaustive; 2 = Euclidean search squared afterwards ('kdtree'
   // = exact KD-tree search, :142-148; 'subsetpdist2', :149-155, whose candidate subset is ALL of B while N2 <= subset)
   const int metric = (p->dtype == APS_F32 && p->method != APS_METHOD_EXHAUSTIVE) ? 2 : 1;
-  if (p->dtype == APS_F32 && p->method == APS_METHOD_APPROX_SUBSETPDIST2 && p->maxc > p->subset)
-    APS_FAIL(APS_ERR_ARGS, "apsmatch:subset",
-             "'subsetpdist2' with more than %lld descriptors in an image draws a random subset (randperm, "
-             "matchFeaturesScratch.m:391-392), which is not built: use 'kdtree' (exact) or 'Exhaustive'",
-             (long long)p->subset);
+
   if (pair_stride < 1 || pair_first < 0 || pair_first >= pair_stride) APS_FAIL(APS_ERR_ARGS, "", "bad pair share");
   const int n = p->n, D = p->D, dtype = p->dtype;
   const int64_t* counts = p->counts.data();
@@ -1882,7 +2010,7 @@ extern "C" int aps_debug_pair_screen(aps_ctx* c, const float* A, int64_t N1, con
   aps_pair_screen_tables t;
   t.qoff = tab.p; t.qcnt = tab.p + 1; t.toff = tab.p + 2; t.tcnt = tab.p + 3; t.timg = tab.p + 4;
   t.eoff = off2.p; t.uoff = off2.p + 2; t.npairs = 1;
-  APS_TRY(aps_k_pair_screen(s, c->sm_count, xh.p, F, Dp, t, units.p, U, scr.p, ddump.p, ddump.p ? dump_tiles : 0));
+  APS_TRY(aps_k_pair_screen(s, c->sm_count, xh.p, F, xh.p, F, Dp, t, units.p, U, scr.p, ddump.p, ddump.p ? dump_tiles : 0));
   std::vector<uint32_t> h((size_t)N1);
   APS_CUDA(cudaMemcpyAsync(h.data(), scr.p, (size_t)N1 * 4, cudaMemcpyDeviceToHost, s));
   if (ddump.p) APS_CUDA(cudaMemcpyAsync(dump, ddump.p, (size_t)N1 * dump_tiles * 64 * 4, cudaMemcpyDeviceToHost, s));

@@ -198,6 +198,10 @@ struct aps_pair_tables {
   // != 0: the tensor pass ran on fp16 operands (10-bit mantissa): the operand-rounding term of eps is 2.0e-3 instead of
   // 7.9e-3.  1 = never exact (pairwise: normalised rows are rounded), 2 = flags[0] tells (global path, set by K1)
   int operand_fp16;
+  // 'subsetpdist2' with images above the subset size: the train rows of such an image are a random subset stored as a
+  // "virtual image" at rows >= vfirst of the train view; vmap[row - vfirst] = 0-based local index in the original image
+  const int32_t* vmap;
+  int64_t vfirst;
 };
 
 // aps_pair_screen.cu : pairwise stage 1 -- fp16 tensor-core screen of every (query row, train image); see the file header
@@ -217,9 +221,18 @@ struct aps_pair_screen_tables {   // per image pair p of the launch (device arra
 __host__ __device__ inline float aps_pair_screen_dot_eps(int Dp) { return (float)(Dp / 16) * 9.765625e-4f + 1.5e-3f; }
 int aps_k_fill_f32(cudaStream_t s, float* dst, int64_t n, float v);
 int aps_k_prepare_operands_f16(cudaStream_t s, const float* src, int64_t F, int D, int Dp, void* xh);
-int aps_k_image_sq_bounds(cudaStream_t s, const float* sq, const int64_t* d_img_off, int n, float2* out);
-int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh, int64_t F, int Dp, const aps_pair_screen_tables& t,
-                      aps_tc_unit* d_units, int64_t n_units, uint32_t* out, uint32_t* dump = nullptr, int dump_tiles = 0);
+// per train image i: (min, max) of sq over rows [start[i], start[i] + count[i])
+int aps_k_image_sq_bounds(cudaStream_t s, const float* sq, const int64_t* d_start, const int64_t* d_count, int n, float2* out);
+// xh_q / xh_t: fp16 operand rows of the query side [Fq x Dp] and of the train view [Ft x Dp] (the same matrix unless
+// the train view carries subset images)
+int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh_q, int64_t Fq, const void* xh_t, int64_t Ft, int Dp,
+                      const aps_pair_screen_tables& t, aps_tc_unit* d_units, int64_t n_units, uint32_t* out,
+                      uint32_t* dump = nullptr, int dump_tiles = 0);
+// virtual (subset) images: vsrc[v] = global source row of virtual row v, chosen by a keyed bijection of [0, N_j)
+int aps_k_subset_rows(cudaStream_t s, const int64_t* d_img_off, const int32_t* d_big_img, int nbig, int64_t subset,
+                      uint64_t seed, int32_t* vsrc, int32_t* vmap);
+int aps_k_gather_f32_rows(cudaStream_t s, const float* src, const int32_t* rows, int64_t nrows, int D, float* dst);
+int aps_k_gather_u16_rows(cudaStream_t s, const uint16_t* src, const int32_t* rows, int64_t nrows, int Dp, uint16_t* dst);
 int aps_k_pair_screen_decide(cudaStream_t s, const uint32_t* scr, const float* sq, const aps_pair_screen_tables& t,
                              const float2* img_bounds, const int32_t* flags, int Dp, double r2, double mt,
                              int32_t* survivors);
@@ -261,8 +274,10 @@ int aps_k_pair_filter_unique(cudaStream_t s, const uint32_t* idx2, const float* 
 int aps_k_select_partners(cudaStream_t s, const int64_t* counts_cm, int n, int m, uint8_t* cand_cm);
 
 // aps_pairwise.cu : batched pairwise stages (see the file header)
-int aps_k_pair_exact2(cudaStream_t s, const float* X, const float* sq, int D, int metric, const aps_pair_tables& pt,
-                      const int32_t* rows, const int32_t* nrows_dev, int64_t n_entries, uint32_t* idx, float* dist);
+// X / sq: query rows ; XT / sqT: train view (the same arrays unless the train view carries subset images)
+int aps_k_pair_exact2(cudaStream_t s, const float* X, const float* sq, const float* XT, const float* sqT, int D, int metric,
+                      const aps_pair_tables& pt, const int32_t* rows, const int32_t* nrows_dev, int64_t n_entries,
+                      uint32_t* idx, float* dist);
 int aps_k_pairs_hamming2(cudaStream_t s, const uint8_t* Xpad, int nb16, const std::vector<int64_t>& eoff,
                          const std::vector<int32_t>& qoff, const std::vector<int32_t>& toff,
                          const std::vector<int32_t>& tcnt, uint32_t* idx, float* dist);

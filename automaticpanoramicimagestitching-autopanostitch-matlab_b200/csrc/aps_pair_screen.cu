@@ -267,10 +267,11 @@ __global__ void k_fill_f32(float* __restrict__ dst, int64_t n, float v) {
 }
 
 // per image: (min, max) of the squared row norms
-__global__ void k_image_sq_bounds(const float* __restrict__ sq, const int64_t* __restrict__ img_off, float2* __restrict__ out) {
+__global__ void k_image_sq_bounds(const float* __restrict__ sq, const int64_t* __restrict__ start,
+                                  const int64_t* __restrict__ count, float2* __restrict__ out) {
   const int i = blockIdx.x;
   float mn = 3.0e38f, mx = 0.f;
-  for (int64_t r = img_off[i] + threadIdx.x; r < img_off[i + 1]; r += blockDim.x) {
+  for (int64_t r = start[i] + threadIdx.x; r < start[i] + count[i]; r += blockDim.x) {
     mn = fminf(mn, sq[r]);
     mx = fmaxf(mx, sq[r]);
   }
@@ -332,7 +333,75 @@ __global__ void k_pair_screen_decide(const uint32_t* __restrict__ scr, const flo
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&survivors[p], mine);
 }
 
+// ---- 'subsetpdist2' above the subset size: candB = randperm(N2, subset) (matchFeaturesScratch.m:391-392) -----------------
+// Stand-in for MATLAB's generator: a keyed bijection of [0, N) (odd multiplications, xor-shifts and additions modulo a power
+// of two, cycle-walked into range); candB[r] = perm(r), r = 0 .. subset-1: `subset` distinct rows in a pseudo-random order.
+__device__ __forceinline__ uint32_t perm_in_range(uint32_t x, uint32_t N, uint64_t key) {
+  int bits = 1;
+  while ((1u << bits) < N && bits < 31) ++bits;
+  const uint32_t mask = (bits >= 32) ? 0xffffffffu : ((1u << bits) - 1u);
+  const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  const int sh = bits > 1 ? bits / 2 : 1;
+  do {
+    x = (x * 0x9E3779B1u) & mask;  x ^= x >> sh;  x = (x + k0) & mask;
+    x = (x * 0x85EBCA6Bu) & mask;  x ^= x >> sh;  x = (x + k1) & mask;
+    x = (x * 0xC2B2AE35u) & mask;  x ^= x >> sh;  x = (x + (k0 ^ (k1 * 0x27D4EB2Fu))) & mask;
+    x = (x * 0x165667B1u) & mask;  x ^= x >> sh;
+  } while (x >= N);
+  return x;
+}
+__global__ void k_subset_rows(const int64_t* __restrict__ img_off, const int32_t* __restrict__ big_img, int64_t subset,
+                              uint64_t seed, int32_t* __restrict__ vsrc, int32_t* __restrict__ vmap) {
+  const int b = blockIdx.y, j = big_img[b];
+  const uint32_t N = (uint32_t)(img_off[j + 1] - img_off[j]);
+  const uint64_t key = seed * 0x9E3779B97F4A7C15ull + (uint64_t)(j + 1) * 0xD1B54A32D192ED03ull;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < subset; r += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t loc = perm_in_range((uint32_t)r, N, key);
+    vmap[b * subset + r] = (int32_t)loc;
+    vsrc[b * subset + r] = (int32_t)(img_off[j] + loc);
+  }
+}
+__global__ void k_gather_f32_rows(const float* __restrict__ src, const int32_t* __restrict__ rows, int64_t nrows, int D,
+                                  float* __restrict__ dst) {
+  const int64_t total = nrows * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D;
+    dst[i] = src[(int64_t)rows[r] * D + (i - r * D)];
+  }
+}
+__global__ void k_gather_u16_rows(const uint4* __restrict__ src, const int32_t* __restrict__ rows, int64_t nrows, int chunks,
+                                  uint4* __restrict__ dst) {
+  const int64_t total = nrows * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / chunks;
+    dst[i] = src[(int64_t)rows[r] * chunks + (i - r * chunks)];
+  }
+}
+
 }  // namespace
+
+int aps_k_subset_rows(cudaStream_t s, const int64_t* d_img_off, const int32_t* d_big_img, int nbig, int64_t subset,
+                      uint64_t seed, int32_t* vsrc, int32_t* vmap) {
+  if (nbig == 0 || subset == 0) return APS_OK;
+  dim3 grid((unsigned)aps_min64(aps_ceil_div(subset, 256), 64), (unsigned)nbig);
+  k_subset_rows<<<grid, 256, 0, s>>>(d_img_off, d_big_img, subset, seed, vsrc, vmap);
+  APS_LAUNCHED();
+  return APS_OK;
+}
+int aps_k_gather_f32_rows(cudaStream_t s, const float* src, const int32_t* rows, int64_t nrows, int D, float* dst) {
+  if (nrows == 0) return APS_OK;
+  k_gather_f32_rows<<<(unsigned)aps_min64(aps_ceil_div(nrows * D, 256), 148 * 16), 256, 0, s>>>(src, rows, nrows, D, dst);
+  APS_LAUNCHED();
+  return APS_OK;
+}
+int aps_k_gather_u16_rows(cudaStream_t s, const uint16_t* src, const int32_t* rows, int64_t nrows, int Dp, uint16_t* dst) {
+  if (nrows == 0) return APS_OK;
+  const int chunks = Dp * 2 / 16;
+  k_gather_u16_rows<<<(unsigned)aps_min64(aps_ceil_div(nrows * chunks, 256), 148 * 16), 256, 0, s>>>(
+      (const uint4*)src, rows, nrows, chunks, (uint4*)dst);
+  APS_LAUNCHED();
+  return APS_OK;
+}
 
 int aps_k_prepare_operands_f16(cudaStream_t s, const float* src, int64_t F, int D, int Dp, void* xh) {
   if (F == 0) return APS_OK;
@@ -349,15 +418,16 @@ int aps_k_fill_f32(cudaStream_t s, float* dst, int64_t n, float v) {
   return APS_OK;
 }
 
-int aps_k_image_sq_bounds(cudaStream_t s, const float* sq, const int64_t* d_img_off, int n, float2* out) {
+int aps_k_image_sq_bounds(cudaStream_t s, const float* sq, const int64_t* d_start, const int64_t* d_count, int n, float2* out) {
   if (n == 0) return APS_OK;
-  k_image_sq_bounds<<<n, 256, 0, s>>>(sq, d_img_off, out);
+  k_image_sq_bounds<<<n, 256, 0, s>>>(sq, d_start, d_count, out);
   APS_LAUNCHED();
   return APS_OK;
 }
 
-int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh, int64_t F, int Dp, const aps_pair_screen_tables& t,
-                      aps_tc_unit* d_units, int64_t n_units, uint32_t* out, uint32_t* dump, int dump_tiles) {
+int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh_q, int64_t Fq, const void* xh_t, int64_t Ft, int Dp,
+                      const aps_pair_screen_tables& t, aps_tc_unit* d_units, int64_t n_units, uint32_t* out,
+                      uint32_t* dump, int dump_tiles) {
   if (Dp != 64 && Dp != 128) {
     aps_set_error(APS_ERR_DIM, "", "pair screen supports padded descriptor lengths 64 and 128 (got %d)", Dp);
     return APS_ERR_DIM;
@@ -366,8 +436,8 @@ int aps_k_pair_screen(cudaStream_t s, int sm_count, const void* xh, int64_t F, i
   k_make_units<<<t.npairs, 32, 0, s>>>(t.qoff, t.qcnt, t.toff, t.tcnt, t.eoff, t.uoff, t.npairs, d_units);
   APS_LAUNCHED();
   CUtensorMap map_q, map_t;
-  APS_TRY(make_map(&map_q, xh, F, Dp, TM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
-  APS_TRY(make_map(&map_t, xh, F, Dp, TN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+  APS_TRY(make_map(&map_q, xh_q, Fq, Dp, TM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+  APS_TRY(make_map(&map_t, xh_t, Ft, Dp, TN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
   SParams P;
   P.units = d_units;
   P.n_units = n_units;

@@ -30,7 +30,8 @@ __device__ __forceinline__ int pair_of_entry(const aps_pair_tables& pt, int64_t 
 
 // ---- exact 2-NN of single entries: one warp per entry (fallback list, or every entry) ----------------------
 template <int METRIC>
-__global__ void __launch_bounds__(256) k_pair_exact2(const float* __restrict__ X, const float* __restrict__ sq, int D,
+__global__ void __launch_bounds__(256) k_pair_exact2(const float* __restrict__ X, const float* __restrict__ sq,
+                                                     const float* __restrict__ XT, const float* __restrict__ sqT, int D,
                                                      aps_pair_tables pt, const int32_t* __restrict__ rows,
                                                      const int32_t* __restrict__ nrows_dev, int64_t n_entries,
                                                      uint32_t* __restrict__ idx, float* __restrict__ dist) {
@@ -48,9 +49,9 @@ __global__ void __launch_bounds__(256) k_pair_exact2(const float* __restrict__ X
     float d0 = CUDART_INF_F, d1 = CUDART_INF_F;  // this lane's two best (ascending j => ties keep the lower index)
     int j0 = -1, j1 = -1;
     for (int j = lane; j < tn; j += 32) {
-      const float* b = X + (t0 + j) * D;
+      const float* b = XT + (t0 + j) * D;
       const float d = METRIC == 0 ? l2sq_flann(a, b, D)
-                      : (METRIC == 2 ? __fsqrt_rn(l2sq_seq(a, b, D)) : ssd_seq(a, b, D, a2, sq[t0 + j]));
+                      : (METRIC == 2 ? __fsqrt_rn(l2sq_seq(a, b, D)) : ssd_seq(a, b, D, a2, sqT[t0 + j]));
       if (d < d0) { d1 = d0; j1 = j0; d0 = d; j0 = j; }
       else if (d < d1) { d1 = d; j1 = j; }
     }
@@ -209,8 +210,11 @@ __global__ void __launch_bounds__(256) k_pairs_rank_emit(aps_pair_tables pt, con
     }
     if (w < W) {
       const uint32_t q = (uint32_t)(mine & 0xffffffffull);
+      uint32_t t = idx2[base + q];
+      if (pt.vmap && (int64_t)pt.toff[p] >= pt.vfirst)   // subset image: position in candB -> row of B (:406, idx2 = candB(I))
+        t = (uint32_t)pt.vmap[(int64_t)pt.toff[p] - pt.vfirst + (int64_t)t - 1] + 1u;
       matches[2 * (base + r)] = q + 1;
-      matches[2 * (base + r) + 1] = idx2[base + q];
+      matches[2 * (base + r) + 1] = t;
       metric[base + r] = (double)f32_from_order_bits((uint32_t)(mine >> 32));
     }
   }
@@ -219,16 +223,17 @@ __global__ void __launch_bounds__(256) k_pairs_rank_emit(aps_pair_tables pt, con
 }  // namespace
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
-int aps_k_pair_exact2(cudaStream_t s, const float* X, const float* sq, int D, int metric, const aps_pair_tables& pt,
-                      const int32_t* rows, const int32_t* nrows_dev, int64_t n_entries, uint32_t* idx, float* dist) {
+int aps_k_pair_exact2(cudaStream_t s, const float* X, const float* sq, const float* XT, const float* sqT, int D, int metric,
+                      const aps_pair_tables& pt, const int32_t* rows, const int32_t* nrows_dev, int64_t n_entries,
+                      uint32_t* idx, float* dist) {
   if (n_entries == 0) return APS_OK;
   const unsigned grid = (unsigned)aps_min64(aps_ceil_div(n_entries, 8), 148 * 8);
   if (metric == 0)
-    k_pair_exact2<0><<<grid, 256, 0, s>>>(X, sq, D, pt, rows, nrows_dev, n_entries, idx, dist);
+    k_pair_exact2<0><<<grid, 256, 0, s>>>(X, sq, XT, sqT, D, pt, rows, nrows_dev, n_entries, idx, dist);
   else if (metric == 2)
-    k_pair_exact2<2><<<grid, 256, 0, s>>>(X, sq, D, pt, rows, nrows_dev, n_entries, idx, dist);
+    k_pair_exact2<2><<<grid, 256, 0, s>>>(X, sq, XT, sqT, D, pt, rows, nrows_dev, n_entries, idx, dist);
   else
-    k_pair_exact2<1><<<grid, 256, 0, s>>>(X, sq, D, pt, rows, nrows_dev, n_entries, idx, dist);
+    k_pair_exact2<1><<<grid, 256, 0, s>>>(X, sq, XT, sqT, D, pt, rows, nrows_dev, n_entries, idx, dist);
   APS_LAUNCHED();
   return APS_OK;
 }

@@ -269,7 +269,8 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
         ph = C.c_void_p()
         check(lib().aps_pplan_create(ctx.handle, cnt, n, int(D), APS_F32, C.byref(ph)))
         try:
-            check(lib().aps_pplan_set_method(ph, aps_method, 12000))      # subset = 12000, matchFeaturesScratch.m:151
+            check(lib().aps_pplan_set_method(ph, aps_method, int(_field(input, "apsSubset", 12000)),   # 12000: :151
+                                             int(_field(input, "apsSeed", 0))))
             check(lib().aps_pplan_upload(ph, ptrs, layout))
             check(lib().aps_pplan_prepare(ph))
             check(lib().aps_pplan_match(ph, thr, ratio, int(first), int(stride), C.byref(h)))
@@ -671,9 +672,17 @@ class PairwisePlan:
     def desc_device(self):
         return lib().aps_pplan_desc_device(self._h)
 
-    def set_method(self, method, subset=12000):
-        """'exhaustive' | 'subsetpdist2' | 'kdtree' (aps_method, include/apsmatch.h; matchFeaturesScratch.m:116-163)."""
-        check(lib().aps_pplan_set_method(self._h, APS_METHOD[str(method).lower()], int(subset)))
+    def set_method(self, method, subset=12000, seed=0):
+        """'exhaustive' | 'subsetpdist2' | 'kdtree' (aps_method, include/apsmatch.h; matchFeaturesScratch.m:116-163).
+        Call before prepare()."""
+        self.subset = int(subset)
+        check(lib().aps_pplan_set_method(self._h, APS_METHOD[str(method).lower()], int(subset), int(seed)))
+
+    def subset_table(self, image):
+        """candB of a train image above the subset size: `subset` distinct 0-based rows (after prepare())."""
+        out = np.zeros(self.subset, np.int32)
+        check(lib().aps_pplan_subset_table(self._h, int(image), _ptr(out)))
+        return out
 
     def prepare(self):
         """K1 of the pairwise path: magnitude test per image (matchFeaturesScratch.m:105-110), norms, tensor operands."""

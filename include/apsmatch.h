@@ -284,12 +284,16 @@ int aps_pplan_prepare(aps_pplan* p);
  *   APS_METHOD_EXHAUSTIVE            nearest2SSDExhaustive, D2 = a2 + b2' - 2 A B'                          (:322-366)
  *   APS_METHOD_APPROX_SUBSETPDIST2   pdist2(B(candB,:), A, 'euclidean', 'Smallest', 2), squared afterwards   (:149-155,
  *                                    :370-409); candB = ALL rows of B while N2 <= subset (12000, the reference's constant;
- *                                    PP/inputs.m:48 makes this the default) -- larger images need randperm: APS_ERR_ARGS
+ *                                    PP/inputs.m:48 makes this the default).  Larger images: candB = `subset` distinct rows in
+ *                                    a pseudo-random order drawn on the device from `seed` by a keyed bijection of [0, N2)
+ *                                    -- a stand-in for randperm (MATLAB's stream cannot be reproduced), ONE subset per train
+ *                                    image instead of one per call; aps_pplan_subset_table returns it (0-based rows of B)
  *   APS_METHOD_APPROX_KDTREE         knnsearch(createns(B,'kdtree'), A, 'K', 2): an EXACT Euclidean search, squared (:142-148)
  * Both approximate modes are served by the exact search with the Euclidean metric: distance = fl(sqrt(s))^2 with
  * s = sum((a-b).^2) in sequential float32, ranking by fl(sqrt(s)), ties -> lower index.  'pca2nn' is not built. */
 enum aps_method { APS_METHOD_EXHAUSTIVE = 0, APS_METHOD_APPROX_SUBSETPDIST2 = 1, APS_METHOD_APPROX_KDTREE = 2 };
-int aps_pplan_set_method(aps_pplan* p, int method, int64_t subset);
+int aps_pplan_set_method(aps_pplan* p, int method, int64_t subset, uint64_t seed);   /* before prepare() */
+int aps_pplan_subset_table(aps_pplan* p, int image, int32_t* out /* [subset] */);   /* after prepare() */
 int aps_pplan_match(aps_pplan* p, double match_threshold, double max_ratio, int pair_first, int pair_stride,
                     aps_matchlist** out);
 

@@ -64,7 +64,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     } else {   // 'subsetpdist2' / 'kdtree' (matchFeaturesScratch.m:142-155): staged plan with the Euclidean metric
       aps_pplan* plan = nullptr;
       rc = aps_pplan_create(aps_mex_ctx(), counts.data(), n, D, dtype, &plan);
-      if (rc == APS_OK) rc = aps_pplan_set_method(plan, method, 12000);
+      if (rc == APS_OK) rc = aps_pplan_set_method(plan, method, 12000, 0);
       if (rc == APS_OK) rc = aps_pplan_upload(plan, ptrs.data(), APS_COL_MAJOR);
       if (rc == APS_OK) rc = aps_pplan_prepare(plan);
       if (rc == APS_OK) rc = aps_pplan_match(plan, mxGetScalar(prhs[3]), mxGetScalar(prhs[4]), 0, 1, &ml);

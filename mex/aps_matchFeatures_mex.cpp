@@ -62,7 +62,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     aps_pplan* plan = nullptr;
     aps_matchlist* ml = nullptr;
     rc = aps_pplan_create(aps_mex_ctx(), counts, 2, D, APS_F32, &plan);
-    if (rc == APS_OK) rc = aps_pplan_set_method(plan, method, 12000);
+    if (rc == APS_OK) rc = aps_pplan_set_method(plan, method, 12000, 0);
     if (rc == APS_OK) rc = aps_pplan_upload(plan, desc, APS_COL_MAJOR);
     if (rc == APS_OK) rc = aps_pplan_prepare(plan);
     if (rc == APS_OK) rc = aps_pplan_match(plan, thr, ratio, 0, 1, &ml);

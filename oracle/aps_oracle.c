@@ -677,6 +677,39 @@ int64_t orc_match_features_method(const void* A, int64_t N1, const void* B, int6
   return K;
 }
 
+/* 'subsetpdist2' with N2 > subset (matchFeaturesScratch.m:388-408): candB [subset] = 0-based rows of B in the order
+ * randperm returned them (here: the table the GPU drew, aps_pplan_subset_table -- MATLAB's stream cannot be reproduced);
+ * B2 = B(candB,:), Euclidean 2-NN over B2 (ties -> first row of B2), idx2 = candB(I). */
+int64_t orc_match_features_subset(const float* A, int64_t N1, const float* B, int64_t N2, int D, const int32_t* candB,
+                                  int64_t subset, double matchThreshold, double maxRatio, int unique, uint32_t* matches,
+                                  double* metric) {
+  if (N1 == 0 || N2 == 0 || subset == 0) return 0;
+  uint32_t* idx2 = (uint32_t*)malloc((size_t)N1 * sizeof(uint32_t));
+  float* d1 = (float*)malloc((size_t)N1 * sizeof(float));
+  float* d2 = (float*)malloc((size_t)N1 * sizeof(float));
+  float* a = (float*)malloc((size_t)N1 * D * sizeof(float));
+  float* b = (float*)malloc((size_t)N2 * D * sizeof(float));
+  float* b2 = (float*)malloc((size_t)subset * D * sizeof(float));
+  memcpy(a, A, (size_t)N1 * D * sizeof(float));
+  memcpy(b, B, (size_t)N2 * D * sizeof(float));
+  if (orc_needs_normalization(a, N1 * D, b, N2 * D)) { /* :105-110: on the FULL inputs, before the method switch */
+    orc_normalize_rows_pairwise(a, N1, D);
+    orc_normalize_rows_pairwise(b, N2, D);
+  }
+  for (int64_t r = 0; r < subset; ++r) memcpy(b2 + r * D, b + (size_t)candB[r] * D, (size_t)D * sizeof(float));
+  orc_nearest2_euclid(a, N1, b2, subset, D, idx2, d1, d2);
+  /* uniqueness is decided per candidate row; positions in B2 and rows of B are in bijection, so filter first, map after */
+  const int64_t K = orc_filter_unique(idx2, d1, d2, N1, subset, 0, 0, matchThreshold, maxRatio, unique, matches, metric);
+  for (int64_t t = 0; t < K; ++t) matches[2 * t + 1] = (uint32_t)candB[matches[2 * t + 1] - 1] + 1u; /* :406 */
+  free(a);
+  free(b);
+  free(b2);
+  free(idx2);
+  free(d1);
+  free(d2);
+  return K;
+}
+
 /* ------------------------------------------------------------------------------------------
  * A4 / B.2 whole  featureMatchingPairwise.m:43-63 + getMatches :103-120 (useMATLABFeatureMatch=0,
  * Matchingmethod='Exhaustive'): every (i<j), query = image i, train = image j, Unique=true.

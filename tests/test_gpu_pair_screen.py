@@ -145,3 +145,48 @@ def test_approximate_float_methods_match_the_oracle(aps, orc, nn):
             assert np.array_equal(gb[i][j], m.astype(np.float64))
     with pytest.raises(aps.ApsError):
         aps.featureMatchingPairwise(dict(inp, ApproxFloatNNMethod="pca2nn"), desc, len(desc), ctx=ctx)
+
+
+def test_subsetpdist2_above_the_subset_size(aps, orc):
+    """'subsetpdist2' when a train image has more rows than the subset (12000 in the reference, matchFeaturesScratch.m:151;
+    small numbers here): candB is `subset` DISTINCT rows in a pseudo-random order, the same for every pair with that
+    train image; the match lists equal the oracle's run on the same candB; images at or below the size use all rows."""
+    ctx = aps._lib.default_context()
+    desc, _ = aps.synth.make_config(5, n=6, kp=3000)
+    desc = [d[:c] for d, c in zip(desc, (3000, 900, 2600, 3000, 1500, 2999))]
+    subset = 1500
+    plan = aps.PairwisePlan(ctx, [d.shape[0] for d in desc], 64, False)
+    plan.set_method("subsetpdist2", subset=subset, seed=7)
+    plan.upload(desc)
+    plan.prepare()
+    pp, rows, met = plan.match(1.5, 0.75)
+    tables = {}
+    for j, d in enumerate(desc):
+        if d.shape[0] > subset:
+            t = plan.subset_table(j)
+            assert t.shape == (subset,) and len(set(t.tolist())) == subset and t.min() >= 0 and t.max() < d.shape[0]
+            assert not np.array_equal(t, np.arange(subset))          # a permutation prefix, not the first rows
+            tables[j] = t
+        else:
+            with pytest.raises(aps.ApsError):
+                plan.subset_table(j)
+    assert sorted(tables) == [0, 2, 3, 5]
+    plan2 = aps.PairwisePlan(ctx, [d.shape[0] for d in desc], 64, False)     # another seed, another subset
+    plan2.set_method("subsetpdist2", subset=subset, seed=8)
+    plan2.upload(desc)
+    plan2.prepare()
+    assert not np.array_equal(plan2.subset_table(0), tables[0])
+    plan2.close()
+    n, total = len(desc), 0
+    for j in range(n):
+        for i in range(j):
+            c = i + j * n
+            g, gm = rows[pp[c]:pp[c + 1]], met[pp[c]:pp[c + 1]]
+            if j in tables:
+                m, d = orc.match_features_subset(desc[i], desc[j], tables[j], 1.5, 0.75)
+            else:
+                m, d = orc.match_features_method(desc[i], desc[j], 1.5, 0.75, "subsetpdist2")
+            assert np.array_equal(g, m) and np.array_equal(gm, d), (i, j)
+            total += len(m)
+    assert total > 300
+    plan.close()
