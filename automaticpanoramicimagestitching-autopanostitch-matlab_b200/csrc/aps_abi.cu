@@ -1019,6 +1019,22 @@ extern "C" int aps_feature_matching_global_dev(aps_ctx* c, const void* d_pooled,
 
 // ------------------------------------------------------------------------------------------------
 // matchFeaturesScratch / featureMatchingPairwise
+// One image pair of a pairwise pass; results are appended to the host vectors in the order of the pair list.
+struct PairRef {
+  int i, j;
+  size_t ordinal;      // position in the full pair list (cell order)
+  int64_t qbase = -1;  // 'pca2nn': first row of the pair's projected query rows in the batch buffers (else: the image's rows)
+};
+// 'pca2nn': the rows one pass of the pairwise pipeline reads when they are NOT the set's own -- the query rows of a batch
+// projected with the train images' bases, and the projected train set
+struct PcaViews {
+  const float* q_xn; const float* q_sq; const float* q_invn; const void* q_xh; int64_t qN;
+  const float* t_xn; const float* t_sq; const void* t_xh; int64_t tN;
+  const float2* bounds;
+  const int32_t* flags;
+  int D;   // components kept (<= 48)
+};
+
 struct PairwiseSets {
   // per-image views: raw (un-normalised) and normalised (matchFeaturesScratch.m:105-110 is a
   // per-PAIR decision: normalise both iff max|A|>2 or max|B|>2)
@@ -1040,6 +1056,13 @@ struct PairwiseSets {
   DevBuf<float> tv_xn[2], tv_sq[2], tv_colbias[2], tv_ones;   // [0] un-normalised view, [1] normalised view
   DevBuf<uint16_t> tv_xh[2];
   DevBuf<int64_t> d_tstart, d_tcount;
+  // 'pca2nn' (aps_pca.cu): per view [0] un-normalised / [1] normalised: basis of every image and the projected,
+  // normalised train rows [F x P] with their fp16 operands [F x 64]
+  int pcaP = 0;
+  DevBuf<float> pca_mu[2], pca_coeff[2], pca_txn[2], pca_tsq[2], pca_tinvn[2];
+  DevBuf<uint16_t> pca_txh[2];
+  DevBuf<float2> pca_bounds[2];
+  DevBuf<int32_t> pca_flags[2];
   bool subsets() const { return !voff.empty(); }
   int64_t toff(int j) const { return (subsets() && voff[j] >= 0) ? voff[j] : off[j]; }
   int64_t tcnt(int j, const int64_t* counts) const { return (subsets() && voff[j] >= 0) ? vcnt : counts[j]; }
@@ -1256,6 +1279,110 @@ static int pairwise_build_train_view(aps_ctx* c, PairwiseSets& ps, const int64_t
   return APS_OK;
 }
 
+// 'pca2nn' (matchFeaturesScratch.m:130-141, 442-573): per view, the PCA basis of every image (it is the TRAIN image's basis
+// that a pair uses, :476-483), the projected + re-normalised (:486-487) train rows and their fp16 operands.  D <= 48: no
+// PCA (:477), the rows are only re-normalised -- expressed as the identity basis so that one code path serves both.
+__global__ void k_identity_basis(int n, int D, float* __restrict__ mu, float* __restrict__ coeff) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)n * D) mu[i] = 0.f;
+  if (i < (int64_t)n * D * D) {
+    const int64_t e = i % ((int64_t)D * D);
+    coeff[i] = (e / D == e % D) ? 1.f : 0.f;
+  }
+}
+static int pairwise_build_pca(aps_ctx* c, PairwiseSets& ps, const int64_t* counts, int n, int D) {
+  cudaStream_t s = c->stream;
+  const int64_t F = ps.off[n];
+  if (F == 0) return APS_OK;
+  const int P = D > aps_pca_components() ? aps_pca_components() : D;
+  ps.pcaP = P;
+  for (int w = 0; w < 2; ++w) {
+    const FloatSet& S = w ? ps.normset : ps.rawset;
+    if (S.N == 0 || !S.raw.p) continue;
+    const float* X = S.xn.p ? S.xn.p : S.raw.p;
+    APS_TRY(ps.pca_mu[w].alloc((size_t)n * D, s));
+    APS_TRY(ps.pca_coeff[w].alloc((size_t)n * D * P, s));
+    if (D > aps_pca_components()) {
+      DevBuf<double> scratch;
+      APS_TRY(scratch.alloc((size_t)2 * n * D * D, s));
+      APS_TRY(aps_k_pca_basis(s, X, ps.d_img_off.p, n, D, P, ps.pca_mu[w].p, ps.pca_coeff[w].p, scratch.p));
+    } else {
+      k_identity_basis<<<(unsigned)aps_ceil_div((int64_t)n * D * D, 256), 256, 0, s>>>(n, D, ps.pca_mu[w].p, ps.pca_coeff[w].p);
+      APS_LAUNCHED();
+    }
+    std::vector<aps_proj_seg> segs;
+    for (int j = 0; j < n; ++j)
+      if (counts[j] > 0) segs.push_back(aps_proj_seg{ps.off[j], ps.off[j], (int32_t)counts[j], j});
+    APS_TRY(ps.pca_txn[w].alloc((size_t)F * P, s));
+    APS_TRY(ps.pca_tsq[w].alloc((size_t)F, s));
+    APS_TRY(ps.pca_tinvn[w].alloc((size_t)F, s));
+    APS_TRY(ps.pca_txh[w].alloc((size_t)F * 64, s));
+    APS_TRY(ps.pca_bounds[w].alloc((size_t)n, s));
+    APS_TRY(ps.pca_flags[w].alloc(8, s));
+    static const int32_t init[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    APS_CUDA(cudaMemcpyAsync(ps.pca_flags[w].p, init, sizeof init, cudaMemcpyHostToDevice, s));
+    APS_TRY(aps_k_pca_project(s, X, D, P, segs, ps.pca_mu[w].p, ps.pca_coeff[w].p, ps.pca_txn[w].p));
+    APS_TRY(aps_k_prepare_norm(s, ps.pca_txn[w].p, F, P, APS_NORM_PAIRWISE, ps.pca_txn[w].p, ps.pca_tsq[w].p,
+                               ps.pca_tinvn[w].p, ps.pca_flags[w].p, 1));
+    APS_TRY(aps_k_prepare_operands_f16(s, ps.pca_txn[w].p, F, P, 64, ps.pca_txh[w].p));
+    std::vector<int64_t> st((size_t)n * 2);
+    for (int j = 0; j < n; ++j) {
+      st[j] = ps.off[j];
+      st[(size_t)n + j] = counts[j];
+    }
+    DevBuf<int64_t> d_st;
+    APS_TRY(d_st.alloc(st.size(), s));
+    APS_CUDA(cudaMemcpyAsync(d_st.p, st.data(), st.size() * 8, cudaMemcpyHostToDevice, s));
+    APS_CUDA(cudaStreamSynchronize(s));
+    APS_TRY(aps_k_image_sq_bounds(s, ps.pca_tsq[w].p, d_st.p, d_st.p + n, n, ps.pca_bounds[w].p));
+  }
+  return APS_OK;
+}
+
+// one batch of pairs in 'pca2nn' mode: project the query rows with their train images' bases, re-normalise, screen, match
+static int pairwise_screen_stage(aps_ctx* c, PairwiseSets& ps, std::vector<PairRef>& pairs, const int64_t* counts, int D,
+                                 bool norm, double match_threshold, double max_ratio, const PcaViews* pv = nullptr);
+static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRef>& pairs, const int64_t* counts, int D,
+                          int dtype, bool norm, bool tensor, int dist_metric, double match_threshold, double max_ratio,
+                          std::vector<int32_t>& out_count, std::vector<std::vector<uint32_t>>& out_rows,
+                          std::vector<std::vector<double>>& out_metric, const PcaViews* pv = nullptr);
+static int pairwise_pca_batch(aps_ctx* c, PairwiseSets& ps, std::vector<PairRef> batch, const int64_t* counts, int D,
+                              bool norm, bool tensor, double match_threshold, double max_ratio,
+                              std::vector<int32_t>& cnt, std::vector<std::vector<uint32_t>>& prow,
+                              std::vector<std::vector<double>>& pmet) {
+  cudaStream_t s = c->stream;
+  const int w = norm ? 1 : 0, P = ps.pcaP;
+  const FloatSet& S = norm ? ps.normset : ps.rawset;
+  const float* X = S.xn.p ? S.xn.p : S.raw.p;
+  std::vector<aps_proj_seg> segs;
+  int64_t E = 0;
+  for (PairRef& pr : batch) {
+    pr.qbase = E;
+    segs.push_back(aps_proj_seg{ps.off[pr.i], E, (int32_t)counts[pr.i], pr.j});
+    E += counts[pr.i];
+  }
+  if (E == 0) return APS_OK;
+  DevBuf<float> qxn, qsq, qinvn;
+  DevBuf<uint16_t> qxh;
+  APS_TRY(qxn.alloc((size_t)E * P, s));
+  APS_TRY(qsq.alloc((size_t)E, s));
+  APS_TRY(qinvn.alloc((size_t)E, s));
+  APS_TRY(aps_k_pca_project(s, X, D, P, segs, ps.pca_mu[w].p, ps.pca_coeff[w].p, qxn.p));
+  APS_TRY(aps_k_prepare_norm(s, qxn.p, E, P, APS_NORM_PAIRWISE, qxn.p, qsq.p, qinvn.p, ps.pca_flags[w].p, 1));
+  PcaViews pv;
+  pv.q_xn = qxn.p; pv.q_sq = qsq.p; pv.q_invn = qinvn.p; pv.q_xh = nullptr; pv.qN = E;
+  pv.t_xn = ps.pca_txn[w].p; pv.t_sq = ps.pca_tsq[w].p; pv.t_xh = ps.pca_txh[w].p; pv.tN = ps.off.back();
+  pv.bounds = ps.pca_bounds[w].p; pv.flags = ps.pca_flags[w].p; pv.D = P;
+  if (tensor) {
+    APS_TRY(qxh.alloc((size_t)E * 64, s));
+    APS_TRY(aps_k_prepare_operands_f16(s, qxn.p, E, P, 64, qxh.p));
+    pv.q_xh = qxh.p;
+    if (c->pairwise_screen) APS_TRY(pairwise_screen_stage(c, ps, batch, counts, D, norm, match_threshold, max_ratio, &pv));
+  }
+  return pairwise_batch(c, ps, batch, counts, D, APS_F32, norm, tensor, /*metric*/ 3, match_threshold, max_ratio, cnt, prow,
+                        pmet, &pv);
+}
+
 static int pairwise_prepare(aps_ctx* c, PairwiseSets& ps, const void* const* desc, const int64_t* counts, int n,
                             int D, int dtype, int layout, bool tensor) {
   APS_TRY(pairwise_alloc(c, ps, counts, n, D, dtype));
@@ -1414,26 +1541,23 @@ __global__ void k_gather_pairs(const uint32_t* __restrict__ src_m, const double*
 
 // One batch of pairs (all using the same descriptor view) through the batched pipeline; results are
 // appended to the host vectors in the order of `pairs`.
-struct PairRef {
-  int i, j;
-  size_t ordinal;  // position in the full pair list (cell order)
-};
 
 static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRef>& pairs, const int64_t* counts, int D,
                           int dtype, bool norm, bool tensor, int dist_metric, double match_threshold, double max_ratio,
                           std::vector<int32_t>& out_count, std::vector<std::vector<uint32_t>>& out_rows,
-                          std::vector<std::vector<double>>& out_metric) {
+                          std::vector<std::vector<double>>& out_metric, const PcaViews* pv) {
   const int np = (int)pairs.size();
   if (np == 0) return APS_OK;
   cudaStream_t s = c->stream;
+  if (pv) D = pv->D;
   std::vector<int64_t> eoff(np + 1, 0), boff(np + 1, 0);
   std::vector<int32_t> qoff(np), toff(np), tcnt(np);
   for (int p = 0; p < np; ++p) {
     eoff[p + 1] = eoff[p] + counts[pairs[p].i];
-    boff[p + 1] = boff[p] + ps.tcnt(pairs[p].j, counts);
-    qoff[p] = (int32_t)ps.off[pairs[p].i];
-    toff[p] = (int32_t)ps.toff(pairs[p].j);       // the train image's rows, or its subset view ('subsetpdist2')
-    tcnt[p] = (int32_t)ps.tcnt(pairs[p].j, counts);
+    boff[p + 1] = boff[p] + (pv ? counts[pairs[p].j] : ps.tcnt(pairs[p].j, counts));
+    qoff[p] = (int32_t)(pairs[p].qbase >= 0 ? pairs[p].qbase : ps.off[pairs[p].i]);
+    toff[p] = (int32_t)(pv ? ps.off[pairs[p].j] : ps.toff(pairs[p].j));   // the train image's rows, or its subset view
+    tcnt[p] = (int32_t)(pv ? counts[pairs[p].j] : ps.tcnt(pairs[p].j, counts));
   }
   const int64_t E = eoff[np], B = boff[np];
   DevBuf<int64_t> d_eoff, d_boff;
@@ -1466,7 +1590,7 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   aps_pair_tables pt;
   memset(&pt, 0, sizeof pt);
   pt.eoff = d_eoff.p; pt.qoff = d_qoff.p; pt.toff = d_toff.p; pt.tcnt = d_tcnt.p; pt.boff = d_boff.p; pt.npairs = np;
-  if (dtype == APS_F32 && ps.subsets()) {
+  if (dtype == APS_F32 && ps.subsets() && !pv) {
     pt.vmap = ps.vmap.p;
     pt.vfirst = ps.Freal;
   }
@@ -1478,9 +1602,18 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
                                       keys.p, winners.p, d_count.p, matches.p, metric.p));
   } else {
     FloatSet& S = norm ? ps.normset : ps.rawset;
-    const FloatSide side = S.side();
-    const TrainView tv = train_view(ps, norm);
-    const int bias_mode = norm ? 0 : 1;
+    FloatSide side = S.side();
+    TrainView tv = train_view(ps, norm);
+    int bias_mode = norm ? 0 : 1;
+    const int32_t* flags_dev = S.flags.p;
+    const void* q_xh = norm ? (const void*)ps.xh_norm.p : (const void*)ps.xh_raw.p;
+    if (pv) {   // 'pca2nn': projected, normalised rows on both sides; cosine scores (scale 1, no bias)
+      side.xn = pv->q_xn; side.sq = pv->q_sq; side.invn = pv->q_invn; side.N = pv->qN;
+      tv.xn = pv->t_xn; tv.sq = pv->t_sq; tv.xh = pv->t_xh; tv.N = pv->tN; tv.ones = ps.ones.p; tv.colbias = ps.ones.p;
+      bias_mode = 0;
+      flags_dev = pv->flags;
+      q_xh = pv->q_xh;
+    }
     c->stats[0] += E;
     if (tensor) {
       c->stats[2] = 2;
@@ -1521,7 +1654,7 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       aps_tc_problem tp;
       // fp16 operand rows (built for the screen; |x| <= 2 in this path) when present: 4x smaller operand-rounding
       // term in the proof's eps than bf16, so far fewer rows end in the exact fallback
-      const void* xh = norm ? (const void*)ps.xh_norm.p : (const void*)ps.xh_raw.p;
+      const void* xh = q_xh;
       tp.Qb = xh ? (const __nv_bfloat16*)xh : side.xb;
       tp.Tb = xh ? (const __nv_bfloat16*)tv.xh : side.xb_t;
       tp.operand_fp16 = xh ? 1 : 0;
@@ -1550,7 +1683,7 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
       ptr_.tile_mode = KCP == 3 ? aps_k_knn_tc_tile_mode_segment() : 0;
       ptr_.operand_fp16 = tp.operand_fp16;
       APS_TRY(aps_k_rerank(s, side.xn, side.sq, side.invn, tv.xn, tv.sq, D, dist_metric, 0, E, 0, nlist, KCP, cidx.p,
-                           cscore.p, S.flags.p, bias_mode, S.flags.p, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &ptr_));
+                           cscore.p, flags_dev, bias_mode, flags_dev, 2, 0, i2.p, dd.p, fb.p, fb.p + E, &ptr_));
       APS_TRY(aps_k_pair_exact2(s, side.xn, side.sq, tv.xn, tv.sq, D, dist_metric, pt, fb.p, fb.p + E, E, i2.p, dd.p));
       APS_CUDA(cudaMemcpyAsync(c->h_flags + 33, fb.p + E, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     } else {
@@ -1602,24 +1735,25 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
 // with fp16 operands; pairs in which no query row can pass the ratio / threshold test are dropped from the list
 // (their cell is empty: zero matches), the others go on to the exact pipeline.
 static int pairwise_screen_stage(aps_ctx* c, PairwiseSets& ps, std::vector<PairRef>& pairs, const int64_t* counts, int D,
-                                 bool norm, double match_threshold, double max_ratio) {
+                                 bool norm, double match_threshold, double max_ratio, const PcaViews* pv) {
   const int np = (int)pairs.size();
   if (np == 0) return APS_OK;
   cudaStream_t s = c->stream;
+  if (pv) D = pv->D;
   const int Dp = (D + 63) / 64 * 64;
   FloatSet& S = norm ? ps.normset : ps.rawset;
-  const void* xh = norm ? (const void*)ps.xh_norm.p : (const void*)ps.xh_raw.p;
-  const float2* bounds = norm ? ps.bounds_norm.p : ps.bounds_raw.p;
+  const void* xh = pv ? pv->q_xh : (norm ? (const void*)ps.xh_norm.p : (const void*)ps.xh_raw.p);
+  const float2* bounds = pv ? pv->bounds : (norm ? ps.bounds_norm.p : ps.bounds_raw.p);
   if (!xh || !bounds) return APS_OK;
   std::vector<int32_t> tab((size_t)np * 5);
   std::vector<int64_t> off2((size_t)(np + 1) * 2, 0);
   int32_t *qoff = tab.data(), *qcnt = qoff + np, *toff = qcnt + np, *tcnt = toff + np, *timg = tcnt + np;
   int64_t *eoff = off2.data(), *uoff = eoff + (np + 1);
   for (int p = 0; p < np; ++p) {
-    qoff[p] = (int32_t)ps.off[pairs[p].i];
+    qoff[p] = (int32_t)(pairs[p].qbase >= 0 ? pairs[p].qbase : ps.off[pairs[p].i]);
     qcnt[p] = (int32_t)counts[pairs[p].i];
-    toff[p] = (int32_t)ps.toff(pairs[p].j);
-    tcnt[p] = (int32_t)ps.tcnt(pairs[p].j, counts);
+    toff[p] = (int32_t)(pv ? ps.off[pairs[p].j] : ps.toff(pairs[p].j));
+    tcnt[p] = (int32_t)(pv ? counts[pairs[p].j] : ps.tcnt(pairs[p].j, counts));
     timg[p] = pairs[p].j;
     eoff[p + 1] = eoff[p] + counts[pairs[p].i];
     uoff[p + 1] = uoff[p] + (counts[pairs[p].i] + 255) / 256;
@@ -1646,14 +1780,15 @@ static int pairwise_screen_stage(aps_ctx* c, PairwiseSets& ps, std::vector<PairR
     APS_CUDA(cudaEventRecord(ev0, s));
   }
   const TrainView tv = train_view(ps, norm);
-  APS_TRY(aps_k_pair_screen(s, c->sm_count, xh, S.N, tv.xh, tv.N, Dp, t, d_units.p, U, scr.p));
+  APS_TRY(aps_k_pair_screen(s, c->sm_count, xh, pv ? pv->qN : S.N, pv ? pv->t_xh : tv.xh, pv ? pv->tN : tv.N, Dp, t,
+                            d_units.p, U, scr.p));
   if (c->timing) {
     APS_CUDA(cudaEventRecord(ev1, s));
     c->tc_events.push_back(ev0);
     c->tc_events.push_back(ev1);
   }
-  APS_TRY(aps_k_pair_screen_decide(s, scr.p, S.sq.p, t, bounds, S.flags.p, Dp, max_ratio * max_ratio, match_threshold,
-                                   d_surv.p));
+  APS_TRY(aps_k_pair_screen_decide(s, scr.p, pv ? pv->q_sq : S.sq.p, t, bounds, pv ? pv->flags : S.flags.p, Dp,
+                                   max_ratio * max_ratio, match_threshold, d_surv.p));
   std::vector<int32_t> surv((size_t)np);
   APS_CUDA(cudaMemcpyAsync(surv.data(), d_surv.p, (size_t)np * 4, cudaMemcpyDeviceToHost, s));
   APS_CUDA(cudaStreamSynchronize(s));   // also covers the pageable host tables above
@@ -1741,6 +1876,8 @@ extern "C" int aps_pplan_prepare(aps_pplan* p) {
   if (p->dtype == APS_F32)
     APS_TRY(pairwise_build_train_view(p->c, p->ps, p->counts.data(), p->n, p->D, p->tensor,
                                       p->method == APS_METHOD_APPROX_SUBSETPDIST2 ? p->subset : 0, p->seed));
+  if (p->dtype == APS_F32 && p->method == APS_METHOD_APPROX_PCA2NN)
+    APS_TRY(pairwise_build_pca(p->c, p->ps, p->counts.data(), p->n, p->D));
   p->prepared = true;
   return APS_OK;
 }
@@ -1758,7 +1895,7 @@ extern "C" int aps_pplan_subset_table(aps_pplan* p, int image, int32_t* out) {
 
 extern "C" int aps_pplan_set_method(aps_pplan* p, int method, int64_t subset, uint64_t seed) {
   if (!p) APS_FAIL(APS_ERR_ARGS, "", "plan is NULL");
-  if (method < APS_METHOD_EXHAUSTIVE || method > APS_METHOD_APPROX_KDTREE)
+  if (method < APS_METHOD_EXHAUSTIVE || method > APS_METHOD_APPROX_PCA2NN)
     APS_FAIL(APS_ERR_METHOD, "", "Select a approximate method");   // matchFeaturesScratch.m:156-157
   if (subset < 1) APS_FAIL(APS_ERR_ARGS, "", "subset must be positive");
   p->method = method;
@@ -1776,6 +1913,7 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
   *out = nullptr;
   // float descriptors: 1 = (a2 + b2) - 2 G of nearest2SSDExhaustive; 2 = Euclidean search squared afterwards ('kdtree'
   // = exact KD-tree search, :142-148; 'subsetpdist2', :149-155, whose candidate subset is ALL of B while N2 <= subset)
+  const bool pca = p->dtype == APS_F32 && p->method == APS_METHOD_APPROX_PCA2NN;
   const int metric = (p->dtype == APS_F32 && p->method != APS_METHOD_EXHAUSTIVE) ? 2 : 1;
 
   if (pair_stride < 1 || pair_first < 0 || pair_first >= pair_stride) APS_FAIL(APS_ERR_ARGS, "", "bad pair share");
@@ -1814,7 +1952,7 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
       (norm ? mine_norm : mine_raw).push_back(pr);
     }
     c->pair_stats[0] = c->pair_stats[1] = c->pair_stats[2] = c->pair_stats[3] = 0;
-    if (tensor && c->pairwise_screen) {
+    if (tensor && c->pairwise_screen && !pca) {
       rc = pairwise_screen_stage(c, ps, mine_raw, counts, D, false, match_threshold, max_ratio);
       if (rc == APS_OK) rc = pairwise_screen_stage(c, ps, mine_norm, counts, D, true, match_threshold, max_ratio);
     }
@@ -1830,8 +1968,11 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
         int64_t e = 0;
         while (b < grp.size() && (b == a || e + counts[grp[b].i] <= ENTRY_BUDGET)) e += counts[grp[b++].i];
         std::vector<PairRef> batch(grp.begin() + a, grp.begin() + b);
-        rc = pairwise_batch(c, ps, batch, counts, D, dtype, g == 1, tensor, metric, match_threshold, max_ratio, cnt, prow,
-                            pmet);
+        if (pca)   // projection with the train image's basis is a per-PAIR operation: screen and match batch by batch
+          rc = pairwise_pca_batch(c, ps, batch, counts, D, g == 1, tensor, match_threshold, max_ratio, cnt, prow, pmet);
+        else
+          rc = pairwise_batch(c, ps, batch, counts, D, dtype, g == 1, tensor, metric, match_threshold, max_ratio, cnt, prow,
+                              pmet);
         a = b;
       }
     }

@@ -237,6 +237,17 @@ int aps_k_pair_screen_decide(cudaStream_t s, const uint32_t* scr, const float* s
                              const float2* img_bounds, const int32_t* flags, int Dp, double r2, double mt,
                              int32_t* survivors);
 
+// aps_pca.cu : 'pca2nn' front end (mean, covariance, Jacobi eigenvectors per image; table-driven projections)
+struct aps_proj_seg {   // rows [src, src + cnt) of X projected with the basis of image `basis` into rows [dst, dst + cnt)
+  int64_t src, dst;
+  int32_t cnt, basis;
+};
+int aps_pca_components();
+int aps_k_pca_basis(cudaStream_t s, const float* X, const int64_t* d_img_off, int n, int D, int P, float* mu, float* coeff,
+                    double* scratch /* 2 * n * D * D */);
+int aps_k_pca_project(cudaStream_t s, const float* X, int D, int P, const std::vector<aps_proj_seg>& segs, const float* mu,
+                      const float* coeff, float* out);
+
 // K3 aps_rerank.cu : exact FP32 re-rank of the candidates + completeness proof.
 //   approx distance of a score: alpha[row] + beta[row]*score ; row proven iff
 //   (worst retained approx distance over segments) - eps_bound > exact k-th distance.

@@ -49,6 +49,14 @@ __device__ __forceinline__ float l2sq_seq(const float* __restrict__ a, const flo
   return s;
 }
 
+// metric 3 ('pca2nn', matchFeaturesScratch.m:536-573 doBlock): cosine similarity of the projected, normalised rows,
+// G = A*B.' restated as a sequential float32 dot; the caller ranks by -sim and reports fl(2 - fl(2 sim)).
+__device__ __forceinline__ float dot_seq(const float* __restrict__ a, const float* __restrict__ b, int D) {
+  float g = 0.f;
+  for (int d = 0; d < D; ++d) g = __fadd_rn(g, __fmul_rn(a[d], b[d]));
+  return g;
+}
+
 // error bound of the approximate distance; flags: [0] operands exact in bf16, [1] bits of max|sq-1|,
 // [2] bits of max sq.  See DESIGN.md "Exactness of the tensor-core search".
 // operand_kind: 0 bf16 (flags[0] = rows exact in bf16), 1 fp16 never exact, 2 fp16 (flags[0] = rows exact in fp16)

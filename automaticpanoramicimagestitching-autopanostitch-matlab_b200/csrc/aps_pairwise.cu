@@ -50,8 +50,10 @@ __global__ void __launch_bounds__(256) k_pair_exact2(const float* __restrict__ X
     int j0 = -1, j1 = -1;
     for (int j = lane; j < tn; j += 32) {
       const float* b = XT + (t0 + j) * D;
-      const float d = METRIC == 0 ? l2sq_flann(a, b, D)
-                      : (METRIC == 2 ? __fsqrt_rn(l2sq_seq(a, b, D)) : ssd_seq(a, b, D, a2, sqT[t0 + j]));
+      const float d = METRIC == 0   ? l2sq_flann(a, b, D)
+                      : METRIC == 2 ? __fsqrt_rn(l2sq_seq(a, b, D))
+                      : METRIC == 3 ? -dot_seq(a, b, D)
+                                    : ssd_seq(a, b, D, a2, sqT[t0 + j]);
       if (d < d0) { d1 = d0; j1 = j0; d0 = d; j0 = j; }
       else if (d < d1) { d1 = d; j1 = j; }
     }
@@ -67,7 +69,10 @@ __global__ void __launch_bounds__(256) k_pair_exact2(const float* __restrict__ X
       const bool found = bj != 0x7fffffff;
       if (lane == 0) {
         idx[e * 2 + c] = found ? (uint32_t)(bj + 1) : 0u;
-        dist[e * 2 + c] = found ? (METRIC == 2 ? __fmul_rn(bd, bd) : bd) : CUDART_INF_F;
+        dist[e * 2 + c] = found ? (METRIC == 2   ? __fmul_rn(bd, bd)
+                                   : METRIC == 3 ? __fsub_rn(2.0f, __fmul_rn(2.0f, -bd))
+                                                 : bd)
+                                : CUDART_INF_F;
       }
       if (found && j0 == bj) { d0 = d1; j0 = j1; d1 = CUDART_INF_F; j1 = -1; }  // pop the winner
     }
@@ -232,6 +237,8 @@ int aps_k_pair_exact2(cudaStream_t s, const float* X, const float* sq, const flo
     k_pair_exact2<0><<<grid, 256, 0, s>>>(X, sq, XT, sqT, D, pt, rows, nrows_dev, n_entries, idx, dist);
   else if (metric == 2)
     k_pair_exact2<2><<<grid, 256, 0, s>>>(X, sq, XT, sqT, D, pt, rows, nrows_dev, n_entries, idx, dist);
+  else if (metric == 3)
+    k_pair_exact2<3><<<grid, 256, 0, s>>>(X, sq, XT, sqT, D, pt, rows, nrows_dev, n_entries, idx, dist);
   else
     k_pair_exact2<1><<<grid, 256, 0, s>>>(X, sq, XT, sqT, D, pt, rows, nrows_dev, n_entries, idx, dist);
   APS_LAUNCHED();

@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
     if (metric == 2) {      // Euclidean search ('kdtree' / 'subsetpdist2'): rank by r = sqrt(s), ties -> lower index
       ds = l2sq_seq(a, b, D);
       d = __fsqrt_rn(ds);
+    } else if (metric == 3) {   // 'pca2nn': [sim1, id1] = max(G, [], 2): rank by similarity (descending), first index on ties
+      const float sim = dot_seq(a, b, D);
+      d = -sim;
+      ds = __fsub_rn(2.0f, __fmul_rn(2.0f, sim));   // d1Block = single(2 - 2*sim1), :568-570
     } else {
       d = (metric == 0) ? l2sq_flann(a, b, D) : ssd_seq(a, b, D, a2, sqT[ci]);
       ds = d;
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
   const int nvalid = __popc(__ballot_sync(0xffffffffu, need) & segmask);
   if (need && rank < k) {
     idx[orow * k + rank] = (uint32_t)((int64_t)ci - t0 + 1);
-    dist[orow * k + rank] = (metric == 2) ? __fmul_rn(d, d) : d;   // :146-147, :153-154: dBest = d.^2
+    dist[orow * k + rank] = (metric == 2) ? __fmul_rn(d, d) : (metric == 3 ? ds : d);   // :146-147, :153-154: dBest = d.^2
   }
   if (row_ok && sl >= nvalid && sl < k) {  // fewer than k neighbours exist: flann_knn.cpp:216-219
     idx[orow * k + sl] = 0u;
@@ -208,7 +212,10 @@ __global__ void __launch_bounds__(256) k_rerank(const float* __restrict__ Q, con
           for (int64_t col = c_lo + sl; col < c_hi; col += G) {
             if ((uint32_t)col == segskip[2 * z] || (uint32_t)col == segskip[2 * z + 1]) continue;
             const float* b = T + col * D;
-            const float dd = (metric == 0) ? l2sq_flann(a, b, D) : (metric == 2 ? l2sq_seq(a, b, D) : ssd_seq(a, b, D, a2, sqT[col]));
+            const float dd = (metric == 0)   ? l2sq_flann(a, b, D)
+                             : (metric == 2) ? l2sq_seq(a, b, D)
+                             : (metric == 3) ? __fsub_rn(2.0f, __fmul_rn(2.0f, dot_seq(a, b, D)))
+                                             : ssd_seq(a, b, D, a2, sqT[col]);
             if (!(dd == dd)) bad = true;
             dmin = fminf(dmin, dd);
           }

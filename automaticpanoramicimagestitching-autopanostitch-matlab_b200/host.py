@@ -186,13 +186,14 @@ class ApsSemanticsWarning(UserWarning):
     """The call was served with semantics that differ from what the reference's defaults select."""
 
 
-APS_METHOD = {"exhaustive": 0, "subsetpdist2": 1, "kdtree": 2}
+APS_METHOD = {"exhaustive": 0, "subsetpdist2": 1, "kdtree": 2, "pca2nn": 3}
 
 
 def _resolve_method(input, method):
     """(Matchingmethod, ApproxFloatNNMethod) -> aps_method (include/apsmatch.h), following matchFeaturesScratch.m:116-163.
     PP/inputs.m:47-49 defaults: useMATLABFeatureMatch=1 (MathWorks matchFeatures, closed source), 'Approximate',
-    'subsetpdist2'.  Nothing here may change results silently: what is not built raises or warns."""
+    'subsetpdist2'.  Nothing here may change results silently: the closed-source branch warns; all three
+    ApproxFloatNNMethod values are built (include/apsmatch.h, aps_method)."""
     import warnings
 
     accept = bool(int(_field(input, "apsAcceptScratchSemantics", 0)))
@@ -203,15 +204,8 @@ def _resolve_method(input, method):
     if method == "exhaustive":
         return APS_METHOD["exhaustive"]
     nn = str(_field(input, "ApproxFloatNNMethod", "pca2nn")).lower()     # parser default, matchFeaturesScratch.m:75
-    if nn in ("subsetpdist2", "kdtree"):
+    if nn in ("subsetpdist2", "kdtree", "pca2nn"):
         return APS_METHOD[nn]
-    if nn == "pca2nn":
-        if not accept:
-            raise ApsError(9, "apsmatch:method", "ApproxFloatNNMethod 'pca2nn' (PCA-48 + cosine GEMM, "
-                           "matchFeaturesScratch.m:130-141) is not built; use 'subsetpdist2' (the inputs.m default), "
-                           "'kdtree' or 'Exhaustive', or set input.apsAcceptScratchSemantics=1 to run the exact search instead")
-        warnings.warn("ApproxFloatNNMethod 'pca2nn' is served by the exhaustive search", ApsSemanticsWarning, stacklevel=3)
-        return APS_METHOD["exhaustive"]
     raise ValueError("Select a approximate method")                      # :156-157
 
 
@@ -241,9 +235,9 @@ def featureMatchingPairwise(input, allDescriptors, numImg, ctx=None, return_metr
     input.useMATLABFeatureMatch=1 (the reference default, PP/inputs.m:47) selects MathWorks' closed-source
     matchFeatures there; here it is served by the matchFeaturesScratch semantics and an ApsSemanticsWarning
     says so (silence it with input.apsAcceptScratchSemantics=1).  Matchingmethod='Approximate' follows
-    input.ApproxFloatNNMethod: 'subsetpdist2' (the inputs.m default) and 'kdtree' are built (Euclidean searches,
-    include/apsmatch.h aps_method); 'pca2nn' raises.  Binary descriptors always run the exhaustive Hamming search, as the
-    reference does (matchFeaturesScratch.m:611).
+    input.ApproxFloatNNMethod: 'subsetpdist2' (the inputs.m default), 'kdtree' (Euclidean searches) and 'pca2nn' (PCA-48
+    + cosine similarity), include/apsmatch.h aps_method.  Binary descriptors always run the exhaustive Hamming search, as
+    the reference does (matchFeaturesScratch.m:611).
     shard=(first, stride): compute only every stride-th pair of the column-major pair list (one share
     per GPU rank); cells of other shares come back empty and are merged by `merge_pairwise_shards`.
     csr=True returns the compacted lists as they leave the C ABI: (pair_ptr [n*n+1], rows [M x 2] uint32, metric [M])."""
@@ -334,8 +328,8 @@ def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRat
     """[matches, matchMetric] = matchFeaturesScratch(F1, F2, 'Method','Exhaustive', ...)  (:1-215)
 
     matches: [K x 2] uint32 (1-based rows of F1 / F2); matchMetric: [K x 1] (SSD, or percent Hamming).
-    Method='Approximate' with float descriptors: ApproxFloatNNMethod 'subsetpdist2' / 'kdtree' (Euclidean searches,
-    :142-155) are built for Unique=true; 'pca2nn' (the parser default, :75) raises.  Binary: exhaustive (:611)."""
+    Method='Approximate' with float descriptors: ApproxFloatNNMethod 'pca2nn' (the parser default, :75), 'subsetpdist2',
+    'kdtree' (:128-163), built for Unique=true.  Binary: exhaustive (:611)."""
     ctx = ctx or default_context()
     if str(Method).lower() not in ("exhaustive", "approximate"):
         raise ValueError(f"Unknown Method: {Method}")  # :164-165
@@ -375,8 +369,6 @@ def matchFeaturesScratch(F1, F2, Method="Exhaustive", MatchThreshold=3.5, MaxRat
         nn = str(ApproxFloatNNMethod).lower()
         if nn not in ("pca2nn", "kdtree", "subsetpdist2"):
             raise ValueError("Select a approximate method")  # :156-157
-        if nn == "pca2nn":
-            raise ApsError(9, "apsmatch:method", "ApproxFloatNNMethod 'pca2nn' is not built (matchFeaturesScratch.m:130-141)")
         if not Unique:
             raise ApsError(9, "apsmatch:method", "approximate float matching is built for Unique=true only")
         A = np.asarray(A, np.float32)

@@ -290,8 +290,14 @@ int aps_pplan_prepare(aps_pplan* p);
  *                                    image instead of one per call; aps_pplan_subset_table returns it (0-based rows of B)
  *   APS_METHOD_APPROX_KDTREE         knnsearch(createns(B,'kdtree'), A, 'K', 2): an EXACT Euclidean search, squared (:142-148)
  * Both approximate modes are served by the exact search with the Euclidean metric: distance = fl(sqrt(s))^2 with
- * s = sum((a-b).^2) in sequential float32, ranking by fl(sqrt(s)), ties -> lower index.  'pca2nn' is not built. */
-enum aps_method { APS_METHOD_EXHAUSTIVE = 0, APS_METHOD_APPROX_SUBSETPDIST2 = 1, APS_METHOD_APPROX_KDTREE = 2 };
+ * s = sum((a-b).^2) in sequential float32, ranking by fl(sqrt(s)), ties -> lower index.
+ *   APS_METHOD_APPROX_PCA2NN         nearest2ApproxFloatFast (:442-573): D > 48 -> PCA of the TRAIN image (mean, 48 leading
+ *                                    components), both images projected, rows re-normalised, cosine similarity G = A*B',
+ *                                    best = first maximum, second = maximum of the rest, d = 2 - 2 sim.  MathWorks' pca is
+ *                                    closed source; restated with a fixed float64 covariance + cyclic Jacobi (csrc/aps_pca.cu)
+ *                                    -- the similarities depend only on the 48-dimensional subspace, not on the basis. */
+enum aps_method { APS_METHOD_EXHAUSTIVE = 0, APS_METHOD_APPROX_SUBSETPDIST2 = 1, APS_METHOD_APPROX_KDTREE = 2,
+                  APS_METHOD_APPROX_PCA2NN = 3 };
 int aps_pplan_set_method(aps_pplan* p, int method, int64_t subset, uint64_t seed);   /* before prepare() */
 int aps_pplan_subset_table(aps_pplan* p, int image, int32_t* out /* [subset] */);   /* after prepare() */
 int aps_pplan_match(aps_pplan* p, double match_threshold, double max_ratio, int pair_first, int pair_stride,

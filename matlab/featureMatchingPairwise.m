@@ -2,7 +2,7 @@ function matches = featureMatchingPairwise(input, allDescriptors, numImg)
     %FEATUREMATCHINGPAIRWISE  Drop-in replacement of PP/featureMatching/featureMatchingPairwise.m.
     %   Runs getMatches' matchFeaturesScratch branch (Unique = true) for every image pair i<j on the GPU in one call.
     %   input.Matchingmethod 'Exhaustive', or 'Approximate' with input.ApproxFloatNNMethod 'subsetpdist2' (the
-    %   inputs.m default) / 'kdtree' -- both Euclidean searches, matchFeaturesScratch.m:142-155; 'pca2nn' is not built.
+    %   inputs.m default) / 'kdtree' (Euclidean searches, matchFeaturesScratch.m:142-155) / 'pca2nn' (PCA-48 + cosine, :130-141).
     %   (The MathWorks matchFeatures branch, input.useMATLABFeatureMatch = 1, is closed source; with this file on the
     %   path the scratch semantics are used and a warning says so.)
     arguments
@@ -16,7 +16,7 @@ function matches = featureMatchingPairwise(input, allDescriptors, numImg)
         warning('apsmatch:semantics', ['input.useMATLABFeatureMatch = 1 selects MathWorks matchFeatures in the ' ...
             'reference; this GPU path runs the matchFeaturesScratch semantics (featureMatchingPairwise.m:108-117).']);
     end
-    method = 0;                                          % aps_method: 0 exhaustive, 1 subsetpdist2, 2 kdtree
+    method = 0;                                          % aps_method: 0 exhaustive, 1 subsetpdist2, 2 kdtree, 3 pca2nn
     if isfield(input, 'Matchingmethod') && strcmpi(input.Matchingmethod, 'Approximate')
         nn = 'pca2nn';                                   % parser default, matchFeaturesScratch.m:75
         if isfield(input, 'ApproxFloatNNMethod'); nn = lower(char(input.ApproxFloatNNMethod)); end
@@ -26,10 +26,7 @@ function matches = featureMatchingPairwise(input, allDescriptors, numImg)
             case 'kdtree'
                 method = 2;
             case 'pca2nn'
-                if ~accept
-                    error('apsmatch:method', ['ApproxFloatNNMethod pca2nn is not built; use subsetpdist2, kdtree or ' ...
-                        'Exhaustive (or input.apsAcceptScratchSemantics = 1 to run the exact search instead).']);
-                end
+                method = 3;
             otherwise
                 error('Select a approximate method');
         end

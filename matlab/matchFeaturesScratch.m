@@ -9,7 +9,7 @@ function [matches, matchMetric] = matchFeaturesScratch(F1, F2, varargin)
     %   aps_matchFeatures_mex; this file only parses the options and decides the descriptor kind (lines 237-292).
     %   'Approximate': binary descriptors run the exhaustive search (the reference's own branch is the exhaustive OMP MEX,
     %   line 611; the LSH options are accepted and ignored as there); float descriptors follow 'ApproxFloatNNMethod':
-    %   'subsetpdist2' and 'kdtree' (Euclidean searches, lines 142-155) are built, 'pca2nn' (the parser default) errors.
+    %   'pca2nn' (the parser default, PCA-48 + cosine, lines 130-141), 'subsetpdist2' and 'kdtree' (Euclidean searches, 142-155).
     opt = struct('Method', 'Exhaustive', 'MatchThreshold', 3.5, 'MaxRatio', 0.6, 'Unique', true, 'ApproxFloatNNMethod', 'pca2nn');
     accepted = {'ApproxNumTables', 'ApproxBitsPerKey', 'ApproxProbes', 'ApproxKDBucketSize', ...
                 'ApproxKDTreeLeafSize', 'Approx.NumTables', 'Approx.BitsPerKey', 'Approx.Probes'};
@@ -57,7 +57,7 @@ function [matches, matchMetric] = matchFeaturesScratch(F1, F2, varargin)
             case 'kdtree'
                 nnMethod = 2;
             case 'pca2nn'
-                error('apsmatch:method', 'ApproxFloatNNMethod pca2nn is not built; use subsetpdist2 or kdtree.');
+                nnMethod = 3;
             otherwise
                 error('Select a approximate method');
         end

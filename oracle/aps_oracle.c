@@ -711,6 +711,154 @@ int64_t orc_match_features_subset(const float* A, int64_t N1, const float* B, in
 }
 
 /* ------------------------------------------------------------------------------------------
+ * A10 'pca2nn'  matchFeaturesScratch.m:130-141 -> nearest2ApproxFloatFast :442-534 + doBlock :536-573.
+ *   D > 48: muB = mean(B,1); coeff = pca(B - muB, 'NumComponents', 48); B = (B-muB)*coeff; A = (A-muB)*coeff  (:476-483)
+ *   rows re-normalised, x ./ (sqrt(sum(x.^2,2)) + eps) (:486-487); G = A*B.'; [sim1,id1] = max(G,[],2); mask; sim2 = max;
+ *   d = single(2 - 2*sim) (:560-570).  The blocking / parfor (:493-531) does not change any value.
+ *   MathWorks' pca (SVD of the centred data) is closed source: parity unpinned.  G and the row norms depend only on
+ *   the SUBSPACE of the 48 leading components (not on the basis inside it, nor on component signs), so any exact
+ *   eigen-solver gives the same result up to rounding; restated with ONE fixed arithmetic, which csrc/aps_pca.cu repeats
+ *   operation by operation: mean float32 sequential; covariance float64 sequential over the rows ((x - mu) formed in
+ *   float32); cyclic Jacobi, ORC_PCA_SWEEPS sweeps, rotations (p,q), p<q; eigenvalues descending, ties -> lower index;
+ *   coeff = single(V(:, order)), min(48, N2-1) columns (pca returns at most N-1), the rest zero; projection
+ *   y_c = sum_d fl(fl(x_d - mu_d) * coeff[d][c]) sequential float32; similarity = sequential float32 dot.
+ * ---------------------------------------------------------------------------------------- */
+#define ORC_PCA_SWEEPS 12
+#define ORC_PCA_COMPONENTS 48
+static void orc_pca_basis(const float* B, int64_t N2, int D, int P, float* mu, float* coeff /* [D][P] */) {
+  double* A = (double*)calloc((size_t)D * D, sizeof(double));
+  double* V = (double*)calloc((size_t)D * D, sizeof(double)); /* V[k][p] */
+  for (int d = 0; d < D; ++d) {
+    float s = 0.0f;
+    for (int64_t r = 0; r < N2; ++r) s = s + B[r * D + d];
+    mu[d] = N2 > 0 ? s / (float)N2 : 0.0f;
+  }
+  for (int a = 0; a < D; ++a)
+    for (int b = a; b < D; ++b) {
+      double s = 0.0;
+      for (int64_t r = 0; r < N2; ++r) {
+        const double xa = (double)(float)(B[r * D + a] - mu[a]), xb = (double)(float)(B[r * D + b] - mu[b]);
+        s = s + xa * xb;
+      }
+      A[a * D + b] = s;
+      A[b * D + a] = s;
+    }
+  for (int k = 0; k < D; ++k) V[k * D + k] = 1.0;
+  for (int sweep = 0; sweep < ORC_PCA_SWEEPS; ++sweep)
+    for (int p = 0; p < D - 1; ++p)
+      for (int q = p + 1; q < D; ++q) {
+        const double apq = A[p * D + q];
+        if (apq == 0.0) continue;
+        const double app = A[p * D + p], aqq = A[q * D + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        const double c = 1.0 / sqrt(t * t + 1.0);
+        const double s = t * c;
+        for (int k = 0; k < D; ++k) {
+          const double akp = A[k * D + p], akq = A[k * D + q];
+          A[k * D + p] = c * akp - s * akq;
+          A[k * D + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < D; ++k) {
+          const double apk = A[p * D + k], aqk = A[q * D + k];
+          A[p * D + k] = c * apk - s * aqk;
+          A[q * D + k] = s * apk + c * aqk;
+          const double vkp = V[k * D + p], vkq = V[k * D + q];
+          V[k * D + p] = c * vkp - s * vkq;
+          V[k * D + q] = s * vkp + c * vkq;
+        }
+      }
+  int* order = (int*)malloc((size_t)D * sizeof(int));
+  for (int k = 0; k < D; ++k) {
+    int r = 0;
+    for (int i = 0; i < D; ++i) r += (A[i * D + i] > A[k * D + k]) || (A[i * D + i] == A[k * D + k] && i < k);
+    order[r] = k;
+  }
+  const int Pj = (int)(N2 - 1 < P ? (N2 > 0 ? N2 - 1 : 0) : P);
+  for (int d = 0; d < D; ++d)
+    for (int c = 0; c < P; ++c) coeff[d * P + c] = c < Pj ? (float)V[d * D + order[c]] : 0.0f;
+  free(order);
+  free(A);
+  free(V);
+}
+static void orc_pca_project(const float* X, int64_t N, int D, int P, const float* mu, const float* coeff, float* Y) {
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < N; ++r)
+    for (int c = 0; c < P; ++c) {
+      float y = 0.0f;
+      for (int d = 0; d < D; ++d) {
+        const float e = X[r * D + d] - mu[d];
+        y = y + e * coeff[d * P + c];
+      }
+      Y[r * P + c] = y;
+    }
+}
+/* 2-NN by cosine similarity of rows that are already projected and normalised */
+void orc_nearest2_cosine(const float* A, int64_t N1, const float* B, int64_t N2, int P, uint32_t* idx2, float* d1, float* d2) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < N1; ++i) {
+    float s1 = -INFINITY, s2 = -INFINITY;
+    uint32_t i1 = 0;
+    for (int64_t j = 0; j < N2; ++j) {
+      float g = 0.0f;
+      for (int c = 0; c < P; ++c) g = g + A[i * P + c] * B[j * P + c];
+      if (g > s1) {
+        s2 = s1;
+        s1 = g;
+        i1 = (uint32_t)(j + 1);
+      } else if (g > s2) {
+        s2 = g;
+      }
+    }
+    idx2[i] = i1;
+    d1[i] = i1 ? 2.0f - 2.0f * s1 : INFINITY;
+    d2[i] = isinf(s2) ? INFINITY : 2.0f - 2.0f * s2;
+  }
+}
+int64_t orc_match_features_pca(const float* Ain, int64_t N1, const float* Bin, int64_t N2, int D, double matchThreshold,
+                               double maxRatio, int unique, uint32_t* matches, double* metric) {
+  if (N1 == 0 || N2 == 0) return 0;
+  float* a = (float*)malloc((size_t)N1 * D * sizeof(float));
+  float* b = (float*)malloc((size_t)N2 * D * sizeof(float));
+  memcpy(a, Ain, (size_t)N1 * D * sizeof(float));
+  memcpy(b, Bin, (size_t)N2 * D * sizeof(float));
+  if (orc_needs_normalization(a, N1 * D, b, N2 * D)) { /* :105-110, before the method switch */
+    orc_normalize_rows_pairwise(a, N1, D);
+    orc_normalize_rows_pairwise(b, N2, D);
+  }
+  const int P = D > ORC_PCA_COMPONENTS ? ORC_PCA_COMPONENTS : D;
+  float* ap = a;
+  float* bp = b;
+  if (D > ORC_PCA_COMPONENTS) { /* :477 */
+    float* mu = (float*)malloc((size_t)D * sizeof(float));
+    float* coeff = (float*)malloc((size_t)D * P * sizeof(float));
+    orc_pca_basis(b, N2, D, P, mu, coeff);
+    ap = (float*)malloc((size_t)N1 * P * sizeof(float));
+    bp = (float*)malloc((size_t)N2 * P * sizeof(float));
+    orc_pca_project(a, N1, D, P, mu, coeff, ap);
+    orc_pca_project(b, N2, D, P, mu, coeff, bp);
+    free(mu);
+    free(coeff);
+  }
+  orc_normalize_rows_pairwise(ap, N1, P); /* :486-487 */
+  orc_normalize_rows_pairwise(bp, N2, P);
+  uint32_t* idx2 = (uint32_t*)malloc((size_t)N1 * sizeof(uint32_t));
+  float* d1 = (float*)malloc((size_t)N1 * sizeof(float));
+  float* d2 = (float*)malloc((size_t)N1 * sizeof(float));
+  orc_nearest2_cosine(ap, N1, bp, N2, P, idx2, d1, d2);
+  const int64_t K = orc_filter_unique(idx2, d1, d2, N1, N2, 0, 0, matchThreshold, maxRatio, unique, matches, metric);
+  if (ap != a) free(ap);
+  if (bp != b) free(bp);
+  free(a);
+  free(b);
+  free(idx2);
+  free(d1);
+  free(d2);
+  return K;
+}
+
+/* ------------------------------------------------------------------------------------------
  * A4 / B.2 whole  featureMatchingPairwise.m:43-63 + getMatches :103-120 (useMATLABFeatureMatch=0,
  * Matchingmethod='Exhaustive'): every (i<j), query = image i, train = image j, Unique=true.
  *   desc pooled row-major; CSR output like orc_global_scatter (pair cell (i,j) i<j), rows =

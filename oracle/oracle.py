@@ -70,6 +70,9 @@ def lib():
         L.orc_match_features_subset.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_int, _i32p, C.c_int64, C.c_double,
                                                 C.c_double, C.c_int, _u32p, _f64p]
         L.orc_match_features_subset.restype = C.c_int64
+        L.orc_match_features_pca.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int,
+                                             _u32p, _f64p]
+        L.orc_match_features_pca.restype = C.c_int64
         L.orc_nearest2_euclid.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_int, _u32p, _f32p, _f32p]
         L.orc_feature_matching_pairwise.argtypes = [C.c_void_p, C.c_int, _i64p, C.c_int, C.c_int, C.c_double,
                                                     C.c_double, _i64p, _u32p, _f64p]
@@ -236,6 +239,17 @@ def match_features_method(A, B, match_threshold, max_ratio, method, unique=True)
     K = lib().orc_match_features_method(A.ctypes.data, N1, B.ctypes.data, N2, A.shape[1], int(is_binary),
                                         METHODS[method], float(match_threshold), float(max_ratio), int(unique),
                                         m.reshape(-1), met)
+    return m[:K].copy(), met[:K].copy()
+
+
+def match_features_pca(A, B, match_threshold, max_ratio, unique=True):
+    """matchFeaturesScratch(A,B,'Method','Approximate','ApproxFloatNNMethod','pca2nn',...) for float descriptors."""
+    A, B = _f32(A), _f32(B)
+    N1 = A.shape[0]
+    m = np.zeros((max(N1, 1), 2), np.uint32)
+    met = np.zeros(max(N1, 1), np.float64)
+    K = lib().orc_match_features_pca(A, N1, B, B.shape[0], A.shape[1], float(match_threshold), float(max_ratio),
+                                     int(unique), m.reshape(-1), met)
     return m[:K].copy(), met[:K].copy()
 
 

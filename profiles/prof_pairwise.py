@@ -1,5 +1,5 @@
 """Small driver used under ncu: the staged pairwise pipeline on one GPU (C5 family).
-usage: python profiles/prof_pairwise.py [n_images=300] [kp=4096] [reps=1]"""
+usage: python profiles/prof_pairwise.py [n_images=300] [kp=4096] [reps=1] [exhaustive|subsetpdist2|kdtree|pca2nn]"""
 import os
 import sys
 import time
@@ -11,9 +11,11 @@ pkg = ge.load_package()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 kp = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+method = sys.argv[4] if len(sys.argv) > 4 else "exhaustive"
 desc, c = pkg.synth.make_config(5, n=n, kp=kp)
 ctx = pkg.Context(0)
 plan = pkg.PairwisePlan(ctx, [d.shape[0] for d in desc], desc[0].shape[1], False)
+plan.set_method(method)
 plan.upload(desc)
 for _ in range(reps):
     ctx.synchronize()

@@ -143,8 +143,8 @@ def test_approximate_float_methods_match_the_oracle(aps, orc, nn):
         for i in range(j):
             m, _ = orc.match_features(orb[i], orb[j], 40.0, 0.7)
             assert np.array_equal(gb[i][j], m.astype(np.float64))
-    with pytest.raises(aps.ApsError):
-        aps.featureMatchingPairwise(dict(inp, ApproxFloatNNMethod="pca2nn"), desc, len(desc), ctx=ctx)
+    with pytest.raises(ValueError):
+        aps.featureMatchingPairwise(dict(inp, ApproxFloatNNMethod="lsh"), desc, len(desc), ctx=ctx)
 
 
 def test_subsetpdist2_above_the_subset_size(aps, orc):
@@ -190,3 +190,39 @@ def test_subsetpdist2_above_the_subset_size(aps, orc):
             total += len(m)
     assert total > 300
     plan.close()
+
+
+def test_pca2nn_matches_the_oracle(aps, orc):
+    """ApproxFloatNNMethod 'pca2nn' (matchFeaturesScratch.m:442-573): PCA basis of the train image (mean, float64
+    covariance, cyclic Jacobi -- csrc/aps_pca.cu repeats the oracle's arithmetic operation by operation), both images
+    projected on 48 components, rows re-normalised, cosine 2-NN, d = 2 - 2 sim.  Match lists and metrics equal the
+    oracle's bit for bit; D <= 48 skips the PCA (:477)."""
+    ctx = aps._lib.default_context()
+    inp = {"Matchingmethod": "Approximate", "ApproxFloatNNMethod": "pca2nn", "Matchingthreshold": 1.5, "Ratiothreshold": 0.7,
+           "useMATLABFeatureMatch": 0}
+    sets = [aps.synth.make_config(5, n=6, kp=1500)[0],               # KAZE-64
+            aps.synth.make_config(1, n=4, kp=1200)[0],               # integer SIFT-128: front end normalises first
+            [d[:, :40].copy() for d in aps.synth.make_config(5, n=4, kp=900)[0]]]   # D = 40: no PCA
+    for si, desc in enumerate(sets):
+        for screen in (True, False):
+            ctx.set_pairwise_screen(screen)
+            try:
+                got, met = aps.featureMatchingPairwise(inp, desc, len(desc), ctx=ctx, return_metric=True)
+            finally:
+                ctx.set_pairwise_screen(True)
+            total = 0
+            for j in range(len(desc)):
+                for i in range(j):
+                    if desc[i].shape[0] == 0 or desc[j].shape[0] == 0:
+                        assert got[i][j].shape[0] == 0
+                        continue
+                    m, d = orc.match_features_pca(desc[i], desc[j], 1.5, 0.7)
+                    assert got[i][j].shape == (len(m), 2) and np.array_equal(got[i][j], m.astype(np.float64)), (si, screen, i, j)
+                    if len(m):
+                        assert np.array_equal(np.asarray(met[i][j]), d), (si, screen, i, j)
+                    total += len(m)
+            assert total > 200, (si, total)
+    A, B = sets[0][0], sets[0][1]
+    m, d = aps.matchFeaturesScratch(A, B, Method="Approximate", MatchThreshold=1.5, MaxRatio=0.7, ctx=ctx)   # parser default = pca2nn
+    om, od = orc.match_features_pca(A, B, 1.5, 0.7)
+    assert np.array_equal(m, om) and np.array_equal(d, od)

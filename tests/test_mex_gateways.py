@@ -146,3 +146,9 @@ def test_gateway_batched_global_and_pairwise_match_the_oracle(tmp_path):
     outs = _run_gate("gate_batched", [(0, d) for d in kz], [1, 1.5, 0.6], tmp_path)
     ref = oracle.feature_matching_pairwise(kz, 1.5, 0.6)
     _cells_equal(outs, ref["cells"] if isinstance(ref, dict) else ref, len(kz))
+    # 'Approximate': aps_method 1 'subsetpdist2' (the inputs.m default) and 3 'pca2nn' through the same gateway
+    for method, fn in ((1, lambda a, b: oracle.match_features_method(a, b, 1.5, 0.6, "subsetpdist2")),
+                       (3, lambda a, b: oracle.match_features_pca(a, b, 1.5, 0.6))):
+        outs = _run_gate("gate_batched", [(0, d) for d in kz], [1, 1.5, 0.6, method], tmp_path)
+        cells = {(i, j): fn(kz[i], kz[j])[0] for j in range(len(kz)) for i in range(j)}
+        _cells_equal(outs, cells, len(kz))

@@ -231,7 +231,7 @@ def test_euclidean_modes_kdtree_subsetpdist2(orc):
 
 def test_host_method_resolution(aps):
     """Matchingmethod / ApproxFloatNNMethod / useMATLABFeatureMatch of PP/inputs.m:47-49: built modes resolve silently,
-    the closed-source branch warns, 'pca2nn' raises unless acknowledged (no GPU needed: pure host logic)."""
+    the closed-source branch warns, an unknown method raises (no GPU needed: pure host logic)."""
     import warnings
 
     from importlib import import_module
@@ -244,11 +244,40 @@ def test_host_method_resolution(aps):
         assert host._resolve_method({}, "exhaustive") == 0
     with pytest.warns(host.ApsSemanticsWarning):
         host._resolve_method({"useMATLABFeatureMatch": 1, "ApproxFloatNNMethod": "subsetpdist2"}, "approximate")
-    with pytest.raises(aps.ApsError):
-        host._resolve_method({"ApproxFloatNNMethod": "pca2nn"}, "approximate")
-    with pytest.raises(aps.ApsError):
-        host._resolve_method({}, "approximate")                          # parser default is pca2nn (:75)
-    with pytest.warns(host.ApsSemanticsWarning):
-        assert host._resolve_method({"ApproxFloatNNMethod": "pca2nn", "apsAcceptScratchSemantics": 1}, "approximate") == 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert host._resolve_method({"ApproxFloatNNMethod": "pca2nn"}, "approximate") == 3
+        assert host._resolve_method({}, "approximate") == 3               # parser default is pca2nn (:75)
     with pytest.raises(ValueError):
         host._resolve_method({"ApproxFloatNNMethod": "lsh"}, "approximate")
+
+
+def test_pca2nn_restatement_against_lapack(orc):
+    """'pca2nn' (matchFeaturesScratch.m:442-573): the oracle's fixed-arithmetic PCA (float64 covariance + cyclic Jacobi)
+    against an independent numpy / LAPACK restatement (eigh of the centred scatter matrix): the similarities depend only
+    on the 48-dimensional subspace, so nearest / second-nearest distances agree to rounding and the indices agree wherever
+    the two best similarities are not within that rounding."""
+    rng = np.random.default_rng(48)
+    for N1, N2, D in ((200, 500, 64), (150, 300, 128)):
+        A = rng.standard_normal((N1, D)).astype(np.float32)
+        B = np.vstack([A[:60] + rng.normal(0, 0.03, (60, D)).astype(np.float32), rng.standard_normal((N2 - 60, D)).astype(np.float32)])
+        A /= np.linalg.norm(A, axis=1, keepdims=True)
+        B /= np.linalg.norm(B, axis=1, keepdims=True)
+        m, d = orc.match_features_pca(A, B, 1.5, 0.8)
+        mu = B.mean(0, dtype=np.float64)
+        Bc = B.astype(np.float64) - mu
+        w, v = np.linalg.eigh(Bc.T @ Bc)
+        coeff = v[:, ::-1][:, :48]
+        Ap, Bp = (A - mu) @ coeff, Bc @ coeff
+        Ap /= np.linalg.norm(Ap, axis=1, keepdims=True)
+        Bp /= np.linalg.norm(Bp, axis=1, keepdims=True)
+        G = Ap @ Bp.T
+        srt = np.sort(G, axis=1)
+        i1 = G.argmax(1)
+        d1, d2 = 2 - 2 * srt[:, -1], 2 - 2 * srt[:, -2]
+        keep = (d1 <= 0.64 * d2) & (d1 <= 1.5)
+        assert len(m) >= 50
+        q = m[:, 0] - 1
+        assert keep[q].all() or (np.abs(d1[q] - 0.64 * d2[q]) < 1e-4).any()
+        assert np.array_equal(i1[q] + 1, m[:, 1])
+        assert np.allclose(d, d1[q], rtol=0, atol=2e-5)
