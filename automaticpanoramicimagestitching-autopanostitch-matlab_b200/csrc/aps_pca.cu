@@ -4,8 +4,8 @@
 //     muB = mean(B,1);  coeff = pca(B - muB, 'NumComponents', 48);  B = (B - muB)*coeff;  A = (A - muB)*coeff;
 // (only when D > 48).  MathWorks' pca is closed source (SVD of the centred data); what matters downstream is the
 // SUBSPACE of the leading components -- A'B'^T and the row norms do not depend on the basis chosen inside it, nor on the
-// sign of a component (negating a column of coeff negates the projected component exactly).  Restated here and in the
-// oracle with ONE fixed arithmetic so that both produce the same bits:
+// sign of a component (negating a column of coeff negates the projected component exactly).  Restated here with ONE fixed
+// arithmetic, the same as the oracle's, so that both produce the same bits:
 //   mean        float32, sequential over the rows
 //   covariance  C = sum_r (x_r - mu)(x_r - mu)^T in float64, sequential over the rows (x - mu formed in float32)
 //   eigenvectors cyclic-by-row Jacobi in float64, PCA_SWEEPS sweeps, rotations in the order (p, q), p < q; every
