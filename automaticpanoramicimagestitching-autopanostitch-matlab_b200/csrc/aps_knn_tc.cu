@@ -479,53 +479,51 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
             }
             // PRE = false (short units, e.g. one image pair: the lists never leave their filling phase, the
             // pre-filter would reject almost nothing) goes straight to the scaled scores
-            if (!PRE || partial || DUMP || fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) > thr_pre) {
-              float gm[4];
+            const bool gate_all = !PRE || partial || DUMP;
+            if (gate_all || fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) > thr_pre) {
+              // group-gated slow path: only the 8-column groups whose raw maximum can hold a candidate are scaled and
+              // searched (in the middle of a sweep that is usually one group of the chunk, not four)
+              bool inserted = false;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                const float4 s0 = lds_f32x4(cscale + (c * 32 + 8 * g) * 4);
-                const float4 s1 = lds_f32x4(cscale + (c * 32 + 8 * g + 4) * 4);
-                if (BIAS) {
-                  const float4 b0 = lds_f32x4(cscale + (TN + c * 32 + 8 * g) * 4);
-                  const float4 b1 = lds_f32x4(cscale + (TN + c * 32 + 8 * g + 4) * 4);
-                  cur[8 * g + 0] = fmaf(cur[8 * g + 0], s0.x, b0.x); cur[8 * g + 1] = fmaf(cur[8 * g + 1], s0.y, b0.y);
-                  cur[8 * g + 2] = fmaf(cur[8 * g + 2], s0.z, b0.z); cur[8 * g + 3] = fmaf(cur[8 * g + 3], s0.w, b0.w);
-                  cur[8 * g + 4] = fmaf(cur[8 * g + 4], s1.x, b1.x); cur[8 * g + 5] = fmaf(cur[8 * g + 5], s1.y, b1.y);
-                  cur[8 * g + 6] = fmaf(cur[8 * g + 6], s1.z, b1.z); cur[8 * g + 7] = fmaf(cur[8 * g + 7], s1.w, b1.w);
-                } else {
-                  cur[8 * g + 0] *= s0.x; cur[8 * g + 1] *= s0.y; cur[8 * g + 2] *= s0.z; cur[8 * g + 3] *= s0.w;
-                  cur[8 * g + 4] *= s1.x; cur[8 * g + 5] *= s1.y; cur[8 * g + 6] *= s1.z; cur[8 * g + 7] *= s1.w;
-                }
-              }
-              if (partial || DUMP) {  // first / last tile of the searched range: mask foreign columns
+                if (gate_all || rm[g] > thr_pre) {
+                  const float4 s0 = lds_f32x4(cscale + (c * 32 + 8 * g) * 4);
+                  const float4 s1 = lds_f32x4(cscale + (c * 32 + 8 * g + 4) * 4);
+                  if (BIAS) {
+                    const float4 b0 = lds_f32x4(cscale + (TN + c * 32 + 8 * g) * 4);
+                    const float4 b1 = lds_f32x4(cscale + (TN + c * 32 + 8 * g + 4) * 4);
+                    cur[8 * g + 0] = fmaf(cur[8 * g + 0], s0.x, b0.x); cur[8 * g + 1] = fmaf(cur[8 * g + 1], s0.y, b0.y);
+                    cur[8 * g + 2] = fmaf(cur[8 * g + 2], s0.z, b0.z); cur[8 * g + 3] = fmaf(cur[8 * g + 3], s0.w, b0.w);
+                    cur[8 * g + 4] = fmaf(cur[8 * g + 4], s1.x, b1.x); cur[8 * g + 5] = fmaf(cur[8 * g + 5], s1.y, b1.y);
+                    cur[8 * g + 6] = fmaf(cur[8 * g + 6], s1.z, b1.z); cur[8 * g + 7] = fmaf(cur[8 * g + 7], s1.w, b1.w);
+                  } else {
+                    cur[8 * g + 0] *= s0.x; cur[8 * g + 1] *= s0.y; cur[8 * g + 2] *= s0.z; cur[8 * g + 3] *= s0.w;
+                    cur[8 * g + 4] *= s1.x; cur[8 * g + 5] *= s1.y; cur[8 * g + 6] *= s1.z; cur[8 * g + 7] *= s1.w;
+                  }
+                  if (partial || DUMP) {  // first / last tile of the searched range: mask foreign columns
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int64_t col = col0 + c * 32 + j;
-                  const bool ok = col >= x.t0 && col < x.t1;
-                  if (DUMP && ok && qrow < P.q1) P.dump[(qrow - P.q0) * (P.t1 - P.t0) + (col - P.t0)] = cur[j];
-                  if (!ok) cur[j] = -CUDART_INF_F;
-                }
-              }
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
-                m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
-                m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
-                gm[g] = fmaxf(m, cur[8 * g + 7]);
-              }
-              if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) > theta) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                    for (int j = 0; j < 8; ++j) {
+                      const int64_t col = col0 + c * 32 + 8 * g + j;
+                      const bool ok = col >= x.t0 && col < x.t1;
+                      if (DUMP && ok && qrow < P.q1) P.dump[(qrow - P.q0) * (P.t1 - P.t0) + (col - P.t0)] = cur[8 * g + j];
+                      if (!ok) cur[8 * g + j] = -CUDART_INF_F;
+                    }
+                  }
+                  float gm = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
+                  gm = fmaxf(fmaxf(gm, cur[8 * g + 3]), cur[8 * g + 4]);
+                  gm = fmaxf(fmaxf(gm, cur[8 * g + 5]), cur[8 * g + 6]);
+                  gm = fmaxf(gm, cur[8 * g + 7]);
                   // branch-free replace-min of the group's maximum; loops only if the same 8 columns hold
                   // a second candidate
-                  while (gm[g] > theta) {
+                  while (gm > theta) {
+                    inserted = true;
                     int js = 7;
 #pragma unroll
-                    for (int j = 6; j >= 0; --j) js = (cur[8 * g + j] == gm[g]) ? j : js;
+                    for (int j = 6; j >= 0; --j) js = (cur[8 * g + j] == gm) ? j : js;
                     sts_u32(si + minpos * SLOT_STRIDE, (uint32_t)(col0 + c * 32 + 8 * g + js));
                     // the 3 low mantissa bits of a retained score hold its slot number: one FMNMX tree yields the
                     // new minimum AND its slot (the 7-ulp truncation is covered by the re-rank's eps)
-                    const float key = __uint_as_float((__float_as_uint(gm[g]) & ~7u) | (uint32_t)minpos);
+                    const float key = __uint_as_float((__float_as_uint(gm) & ~7u) | (uint32_t)minpos);
 #pragma unroll
                     for (int i = 0; i < KCT; ++i) bv[i] = (i == minpos) ? key : bv[i];
                     if constexpr (KCT == 8) {
@@ -542,14 +540,14 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
                     minpos = (int)(__float_as_uint(theta) & 7u);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) cur[8 * g + j] = (j == js) ? -CUDART_INF_F : cur[8 * g + j];
-                    float m = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
-                    m = fmaxf(fmaxf(m, cur[8 * g + 3]), cur[8 * g + 4]);
-                    m = fmaxf(fmaxf(m, cur[8 * g + 5]), cur[8 * g + 6]);
-                    gm[g] = fmaxf(m, cur[8 * g + 7]);
+                    gm = fmaxf(fmaxf(cur[8 * g], cur[8 * g + 1]), cur[8 * g + 2]);
+                    gm = fmaxf(fmaxf(gm, cur[8 * g + 3]), cur[8 * g + 4]);
+                    gm = fmaxf(fmaxf(gm, cur[8 * g + 5]), cur[8 * g + 6]);
+                    gm = fmaxf(gm, cur[8 * g + 7]);
                   }
                 }
-                if (PRE) thr_pre = pre_threshold(theta);
               }
+              if (PRE && inserted) thr_pre = pre_threshold(theta);
             }
             if (CS == 1 && c + 1 < CG / 32) tmem_wait_ld(nxt);
           }
