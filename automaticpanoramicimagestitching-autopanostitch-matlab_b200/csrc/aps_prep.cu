@@ -73,12 +73,16 @@ int aps_k_transpose_out_u32f32(cudaStream_t s, const uint32_t* idx_rm, const flo
 // img_off != nullptr: blockIdx.y = image, rows [img_off[y], img_off[y+1]) with its own flag words flags + 8*y (the
 // per-image magnitude test of the pairwise path in ONE launch)
 constexpr int PN_WARPS = 4;   // warps per block; shared memory = PN_WARPS * 32 * (D+1) * 4 bytes
-__global__ void __launch_bounds__(32 * PN_WARPS) k_prepare_norm(const float* __restrict__ raw, int64_t F, int D,
+// DT = compile-time descriptor length (64, 128: the index arithmetic of the coalesced phases becomes shifts; it was 40 %
+// of the instructions with a run-time D) or 0 = generic.
+template <int DT>
+__global__ void __launch_bounds__(32 * PN_WARPS) k_prepare_norm(const float* __restrict__ raw, int64_t F, int Drt,
                                                                 int norm_mode, float* __restrict__ xn,
                                                                 float* __restrict__ sq, float* __restrict__ invn,
                                                                 int32_t* __restrict__ flags,
                                                                 const int64_t* __restrict__ img_off, int fp16) {
   extern __shared__ float tile_all[];
+  const int D = DT ? DT : Drt;
   const int ld = D + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* tile = tile_all + (size_t)warp * 32 * ld;
@@ -208,12 +212,13 @@ static int prepare_norm_launch(cudaStream_t s, const float* raw, int64_t F, int6
     aps_set_error(APS_ERR_DIM, "", "descriptor dimension %d too large", D);
     return APS_ERR_DIM;
   }
-  APS_CUDA(cudaFuncSetAttribute(k_prepare_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = D == 128 ? k_prepare_norm<128> : (D == 64 ? k_prepare_norm<64> : k_prepare_norm<0>);
+  APS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t gx = aps_ceil_div(rows_per_y, (int64_t)PN_WARPS * 32);
   const int64_t cap = aps_ceil_div((int64_t)148 * 8, (int64_t)ny);   // a few CTAs per SM; warps loop over the rest
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)(gx < 1 ? 1 : gx), ny);
-  k_prepare_norm<<<grid, 32 * PN_WARPS, smem, s>>>(raw, F, D, norm_mode, xn, sq, invn, flags, img_off, fp16);
+  kern<<<grid, 32 * PN_WARPS, smem, s>>>(raw, F, D, norm_mode, xn, sq, invn, flags, img_off, fp16);
   APS_LAUNCHED();
   return APS_OK;
 }
