@@ -109,6 +109,21 @@ static __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 8 columns (one column group of the selection epilogue, re-read on the rare candidate path)
+static __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+static __device__ __forceinline__ void tmem_wait_ld8(float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
 // The wait names the destination registers as in/out operands so the compiler cannot schedule a use of
 // them above the wait (tcgen05.ld is asynchronous).
 static __device__ __forceinline__ void tmem_wait_ld(float (&v)[32]) {

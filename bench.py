@@ -636,11 +636,18 @@ def run_ours_pairwise(args, rank, world, local_rank, pkg, ctx, stream, cfg, torc
         if not args.no_cpu_baseline:
             oracle = _oracle_all_cores()
             dt, pairs, sel, ref = cpu_sample_pairwise(oracle, desc, 24)
-            line["cpu_baseline"] = {"value": pairs / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-                                    "sample": f"{len(sel)} image pairs ({pairs:.3e} descriptor pairs, {dt:.1f} s): "
-                                              f"matchFeaturesScratch exhaustive + unique of the oracle, scaled linearly"}
+            if world == 1:
+                line["cpu_baseline"] = {"value": pairs / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                                        "sample": f"{len(sel)} image pairs ({pairs:.3e} descriptor pairs, {dt:.1f} s): "
+                                                  f"matchFeaturesScratch exhaustive + unique of the oracle, scaled linearly"}
             same = all(np.array_equal(cells[i][j], m.astype(np.float64)) for (i, j), (m, _) in zip(sel, ref))
             line["parity_check"] = ("ok" if same else "MISMATCH") + f": {len(sel)} sampled image pairs == oracle match lists"
+        rp = os.path.join(ROOT, "profiles", f"r2_bench_{cfg}_1gpu.json")
+        if world > 1 and os.path.exists(rp):   # strong-scaling context: this workload on ONE GPU (recorded run of this bench)
+            one = json.load(open(rp))
+            line["strong_scaling"] = {"one_gpu_ms_per_step_recorded": one["ms_per_step"],
+                                      "speedup": one["ms_per_step"] / ms_per_step,
+                                      "source": f"profiles/r2_bench_{cfg}_1gpu.json"}
         print(json.dumps(line), flush=True)
     plan.close()
     for p in host_ptrs:

@@ -23,6 +23,7 @@ for what in "$@"; do
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pair_screen$ -c 1 --metrics sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor_subpipe_hmma.sum,sm__mem_tensor_reads.sum,sm__mem_tensor_writes.sum,sm__inst_executed_pipe_tmem.sum -o gpurun_out/prof_screen2 -f python profiles/prof_pairwise.py 120 4096 1 > gpurun_out/ncu_screen2.log 2>&1; echo "screen rc=$?"
              timeout 600 ncu --set full --clock-control none -k regex:'k_prepare_norm|k_prepare_operands|k_rerank|k_global_filter|k_rank_per_image|k_scatter_rows|k_gather_train' -s 7 -c 7 -o gpurun_out/prof_aux2 -f python profiles/prof_step.py 20 8192 3 2 > gpurun_out/ncu_aux2.log 2>&1; echo "aux rc=$?"
              timeout 600 ncu --set full --clock-control none -k regex:k_knn_hamming -c 1 -o gpurun_out/prof_ham -f python profiles/prof_step.py 20 8192 1 4 > gpurun_out/ncu_ham.log 2>&1; echo "ham rc=$?";;
+    ncu_tc6) timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_knn_tc.*int.6, .int.1" -c 1 --metrics sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor_subpipe_hmma.sum,sm__mem_tensor_reads.sum,sm__mem_tensor_writes.sum,sm__inst_executed_pipe_tmem.sum -o gpurun_out/prof_tc6 -f python profiles/prof_step.py 20 8192 2 2 > gpurun_out/ncu_tc6.log 2>&1; echo "tc6 rc=$?";;
     ncu_tc)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_knn_tc -s 2 -c 1 \
                --metrics sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor_subpipe_hmma.sum,sm__mem_tensor_reads.sum,sm__mem_tensor_writes.sum,sm__inst_executed_pipe_tmem.sum \
                -o gpurun_out/prof_tc -f python profiles/prof_step.py 20 8192 2 2 > gpurun_out/ncu_tc.log 2>&1; echo "ncu_tc rc=$?"; tail -3 gpurun_out/ncu_tc.log;;
