@@ -193,37 +193,62 @@ __global__ void __launch_bounds__(TJ) k_knn_exact(const float* __restrict__ Q, c
   }
 }
 
-// merges the `ns` partial ascending lists of every row (ties -> lower index), one thread per row
+// merges the `ns` (<= 128) partial ascending lists of every row (ties -> lower index): one WARP per row, lane l owns
+// the lists l, l+32, l+64, l+96; per output rank a shuffle arg-min over the lanes' best heads
 __global__ void k_knn_exact_merge(const int32_t* __restrict__ rows, const int32_t* __restrict__ nrows_dev, int64_t q0,
                                   int64_t nq, int k, int nsplit, int64_t split_cap, const uint32_t* __restrict__ pidx,
                                   const float* __restrict__ pdist, int64_t out_row0, uint32_t* __restrict__ idx,
                                   float* __restrict__ dist) {
   const int64_t total = rows ? (int64_t)(*nrows_dev) : nq;
   if (!(nsplit > 1 && total <= split_cap)) return;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= total) return;  // warp-uniform
   const int64_t row = rows ? (int64_t)rows[i] : q0 + i;
-  unsigned char head[128];  // nsplit <= 128, k <= APS_MAX_K
-  for (int s = 0; s < nsplit; ++s) head[s] = 0;
+  int head[4] = {0, 0, 0, 0};
   for (int c = 0; c < k; ++c) {
-    float bd = CUDART_INF_F;
-    uint32_t bi = 0;
-    int bs = -1;
-    for (int s = 0; s < nsplit; ++s) {
-      if (head[s] >= k) continue;
-      const int64_t o = (i * nsplit + s) * k + head[s];
-      const uint32_t ci = pidx[o];
-      if (ci == 0u) continue;
-      const float cd = pdist[o];
-      if (bs < 0 || cd < bd || (cd == bd && ci < bi)) {
-        bd = cd;
-        bi = ci;
-        bs = s;
+    float bd = CUDART_INF_F;  // every stored candidate has a finite distance: +inf == "no head left"
+    uint32_t bi = 0xffffffffu;
+    int bq = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sp = lane + 32 * q;
+      if (sp < nsplit && head[q] < k) {
+        const int64_t o = (i * nsplit + sp) * k + head[q];
+        const uint32_t ci = pidx[o];
+        if (ci != 0u) {
+          const float cd = pdist[o];
+          if (cd < bd || (cd == bd && ci < bi)) {
+            bd = cd;
+            bi = ci;
+            bq = q;
+          }
+        }
       }
     }
-    if (bs >= 0) head[bs]++;
-    idx[(row - out_row0) * k + c] = bi;
-    dist[(row - out_row0) * k + c] = bs >= 0 ? bd : CUDART_INF_F;
+    float wd = bd;
+    uint32_t wi = bi;
+    int wl = lane;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, wd, off);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, wi, off);
+      const int ol = __shfl_xor_sync(0xffffffffu, wl, off);
+      if (od < wd || (od == wd && oi < wi)) {
+        wd = od;
+        wi = oi;
+        wl = ol;
+      }
+    }
+    const bool found = wi != 0xffffffffu;
+    if (found && lane == wl) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) head[q] += (q == bq) ? 1 : 0;
+    }
+    if (lane == 0) {
+      idx[(row - out_row0) * k + c] = found ? wi : 0u;
+      dist[(row - out_row0) * k + c] = found ? wd : CUDART_INF_F;
+    }
   }
 }
 
@@ -268,7 +293,7 @@ int aps_k_knn_exact(cudaStream_t s, const float* Q, const float* sqQ, const int3
   }
   APS_LAUNCHED();
   if (nsplit > 1) {
-    k_knn_exact_merge<<<(unsigned)aps_ceil_div(aps_min64(nq, split_cap), 128), 128, 0, s>>>(
+    k_knn_exact_merge<<<(unsigned)aps_ceil_div(aps_min64(nq, split_cap), 4), 128, 0, s>>>(
         rows, nrows_dev, q0, nq, k, nsplit, split_cap, pidx.p, pdist.p, out_row0, idx, dist);
     APS_LAUNCHED();
   }

@@ -450,6 +450,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         };
         float thr_pre = PRE ? pre_threshold(theta) : 0.f;
         float va[32], vb[32];
+        bool slot_released = false;  // (warp-uniform)
         if constexpr (PRE && CS == 1 && !DUMP) {
           // ---- long sweeps: straight-line scan of the whole tile, candidates re-read from TMEM ----
           // (1) the 16 group maxima of the row's 128 raw accumulators (FMNMX3 trees, no branch, no per-column constant);
@@ -461,6 +462,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           //     at run time, instead of one per (chunk, group): the scan stays in the instruction cache fully unrolled.
           // The lists are the ones the per-chunk loop below builds: same order of columns, same exact test against
           // theta; only the conservative raw gate is evaluated once per tile instead of once per chunk.
+#ifndef APS_TC_NOEPI   // (measurement aid: -DAPS_TC_NOEPI leaves the accumulators unread = the TMA + MMA floor)
           float rm[16];
           tmem_ld32(taddr, va);
           tmem_wait_ld(va);
@@ -488,66 +490,85 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
             for (int g = 0; g < 16; ++g) pend |= (rm[g] > thr_pre) ? (1u << g) : 0u;
             if (partial) pend = 0xffffu;
             uint32_t uni = __reduce_or_sync(0xffffffffu, pend);
-            while (uni) {
-              const int g = __ffs((int)uni) - 1;
-              uni &= uni - 1;
-              float v[8];
-              __syncwarp();
-              tmem_ld8(taddr + 8 * g, v);
-              tmem_wait_ld8(v);
-              if ((pend >> g) & 1u) {
-                const float4 s0 = lds_f32x4(cscale + (8 * g) * 4);
-                const float4 s1 = lds_f32x4(cscale + (8 * g + 4) * 4);
-                if (BIAS) {
-                  const float4 b0 = lds_f32x4(cscale + (TN + 8 * g) * 4);
-                  const float4 b1 = lds_f32x4(cscale + (TN + 8 * g + 4) * 4);
-                  v[0] = fmaf(v[0], s0.x, b0.x); v[1] = fmaf(v[1], s0.y, b0.y);
-                  v[2] = fmaf(v[2], s0.z, b0.z); v[3] = fmaf(v[3], s0.w, b0.w);
-                  v[4] = fmaf(v[4], s1.x, b1.x); v[5] = fmaf(v[5], s1.y, b1.y);
-                  v[6] = fmaf(v[6], s1.z, b1.z); v[7] = fmaf(v[7], s1.w, b1.w);
-                } else {
-                  v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
-                  v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-                }
-                if (partial) {  // first / last tile of the searched range: foreign columns can never be selected
+            // one flagged group of this lane: scale, mask, insert (inlined once per stash position below)
+            auto search_group = [&](float(&v)[8], const int g) {
+              const float4 s0 = lds_f32x4(cscale + (8 * g) * 4);
+              const float4 s1 = lds_f32x4(cscale + (8 * g + 4) * 4);
+              if (BIAS) {
+                const float4 b0 = lds_f32x4(cscale + (TN + 8 * g) * 4);
+                const float4 b1 = lds_f32x4(cscale + (TN + 8 * g + 4) * 4);
+                v[0] = fmaf(v[0], s0.x, b0.x); v[1] = fmaf(v[1], s0.y, b0.y);
+                v[2] = fmaf(v[2], s0.z, b0.z); v[3] = fmaf(v[3], s0.w, b0.w);
+                v[4] = fmaf(v[4], s1.x, b1.x); v[5] = fmaf(v[5], s1.y, b1.y);
+                v[6] = fmaf(v[6], s1.z, b1.z); v[7] = fmaf(v[7], s1.w, b1.w);
+              } else {
+                v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+                v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+              }
+              if (partial) {  // first / last tile of the searched range: foreign columns can never be selected
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const int64_t col = col0 + 8 * g + j;
-                    if (col < x.t0 || col >= x.t1) v[j] = -CUDART_INF_F;
-                  }
+                for (int j = 0; j < 8; ++j) {
+                  const int64_t col = col0 + 8 * g + j;
+                  if (col < x.t0 || col >= x.t1) v[j] = -CUDART_INF_F;
                 }
-                float gm = fmaxf(fmaxf(v[0], v[1]), v[2]);
+              }
+              float gm = fmaxf(fmaxf(v[0], v[1]), v[2]);
+              gm = fmaxf(fmaxf(gm, v[3]), v[4]);
+              gm = fmaxf(fmaxf(gm, v[5]), v[6]);
+              gm = fmaxf(gm, v[7]);
+              while (gm > theta) {  // loops only if the same 8 columns hold a second candidate
+                int js = 7;
+#pragma unroll
+                for (int j = 6; j >= 0; --j) js = (v[j] == gm) ? j : js;
+                sts_u32(si + minpos * SLOT_STRIDE, (uint32_t)(col0 + 8 * g + js));
+                const float key = __uint_as_float((__float_as_uint(gm) & ~7u) | (uint32_t)minpos);
+#pragma unroll
+                for (int i = 0; i < KCT; ++i) bv[i] = (i == minpos) ? key : bv[i];
+                if constexpr (KCT == 8) {
+                  float m01 = fminf(fminf(bv[0], bv[1]), bv[2]);
+                  float m23 = fminf(fminf(bv[3], bv[4]), bv[5]);
+                  theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
+                } else if constexpr (KCT == 6) {
+                  theta = fminf(fminf(fminf(bv[0], bv[1]), bv[2]), fminf(fminf(bv[3], bv[4]), bv[5]));
+                } else {
+                  theta = fminf(fminf(bv[0], bv[1]), fminf(bv[2], bv[3]));
+                }
+                minpos = (int)(__float_as_uint(theta) & 7u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = (j == js) ? -CUDART_INF_F : v[j];
+                gm = fmaxf(fmaxf(v[0], v[1]), v[2]);
                 gm = fmaxf(fmaxf(gm, v[3]), v[4]);
                 gm = fmaxf(fmaxf(gm, v[5]), v[6]);
                 gm = fmaxf(gm, v[7]);
-                while (gm > theta) {  // loops only if the same 8 columns hold a second candidate
-                  int js = 7;
-#pragma unroll
-                  for (int j = 6; j >= 0; --j) js = (v[j] == gm) ? j : js;
-                  sts_u32(si + minpos * SLOT_STRIDE, (uint32_t)(col0 + 8 * g + js));
-                  const float key = __uint_as_float((__float_as_uint(gm) & ~7u) | (uint32_t)minpos);
-#pragma unroll
-                  for (int i = 0; i < KCT; ++i) bv[i] = (i == minpos) ? key : bv[i];
-                  if constexpr (KCT == 8) {
-                    float m01 = fminf(fminf(bv[0], bv[1]), bv[2]);
-                    float m23 = fminf(fminf(bv[3], bv[4]), bv[5]);
-                    theta = fminf(fminf(m01, m23), fminf(bv[6], bv[7]));
-                  } else if constexpr (KCT == 6) {
-                    theta = fminf(fminf(fminf(bv[0], bv[1]), bv[2]), fminf(fminf(bv[3], bv[4]), bv[5]));
-                  } else {
-                    theta = fminf(fminf(bv[0], bv[1]), fminf(bv[2], bv[3]));
-                  }
-                  minpos = (int)(__float_as_uint(theta) & 7u);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = (j == js) ? -CUDART_INF_F : v[j];
-                  gm = fmaxf(fmaxf(v[0], v[1]), v[2]);
-                  gm = fmaxf(fmaxf(gm, v[3]), v[4]);
-                  gm = fmaxf(fmaxf(gm, v[5]), v[6]);
-                  gm = fmaxf(gm, v[7]);
-                }
               }
+            };
+            // Rounds of up to four flagged groups: their accumulators are copied out of TMEM first and, once nothing is
+            // left to read, the slot goes back to the tensor pipe BEFORE the insertions run -- a tile with candidates
+            // (the slow 40 %) no longer holds up the MMAs of the tile after next.
+            while (uni) {
+              int gq[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                gq[q] = uni ? __ffs((int)uni) - 1 : 31;  // 31: no group (bit 31 of pend is never set)
+                uni &= uni - 1;
+              }
+              float vs[32];
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) tmem_ld8(taddr + 8 * (gq[q] & 15), *reinterpret_cast<float(*)[8]>(vs + 8 * q));
+              tmem_wait_ld(vs);
+              if (uni == 0u) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);
+                slot_released = true;
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if ((pend >> gq[q]) & 1u) search_group(*reinterpret_cast<float(*)[8]>(vs + 8 * q), gq[q]);
             }
           }
+#endif
         } else {
         if (CS == 1) {  // two warps per sub-partition: double-buffer the TMEM loads
           tmem_ld32(taddr, va);
@@ -655,7 +676,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&bars->acc_empty[slot]);
+          if (!slot_released) mbar_arrive(&bars->acc_empty[slot]);
           mbar_arrive(&bars->cs_empty[cs]);
         }
       }

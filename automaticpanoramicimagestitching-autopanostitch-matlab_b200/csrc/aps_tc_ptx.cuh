@@ -2,6 +2,7 @@
 // mbarrier pipelines, TMA (cp.async.bulk.tensor) loads, tcgen05.mma / commit / ld, shared-memory matrix
 // descriptors and the host-side tensor-map encoder.  Everything is static / inline: one copy per translation unit.
 #pragma once
+#include <cstdio>
 #include <cuda.h>
 #include <math_constants.h>
 
@@ -42,6 +43,9 @@ constexpr uint32_t kSuspendHintNs = 20000;
 static __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
+#ifdef APS_TC_WATCHDOG
+  uint32_t spins = 0;
+#endif
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -50,6 +54,12 @@ static __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "=r"(done)
         : "r"(addr), "r"(parity), "r"(kSuspendHintNs)
         : "memory");
+#ifdef APS_TC_WATCHDOG   // debugging aid: name the barrier a deadlocked role is parked on, then trap
+    if (!done && ++spins > (1u << 16)) {
+      printf("mbar watchdog: block %d thread %d barrier smem+0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, addr, parity);
+      __trap();
+    }
+#endif
   } while (!done);
 }
 // producer / MMA-issuer flavour: back off between probes so the spinning lane does not steal issue
