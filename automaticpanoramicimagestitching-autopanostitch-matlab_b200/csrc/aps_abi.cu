@@ -75,6 +75,7 @@ extern "C" void aps_ctx_destroy(aps_ctx* c) {
   for (cudaEvent_t e : c->tc_events) cudaEventDestroy(e);
   if (c->d_scratch_flags) cudaFree(c->d_scratch_flags);
   if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }

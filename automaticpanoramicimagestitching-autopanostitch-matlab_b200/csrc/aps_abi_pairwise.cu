@@ -1,6 +1,8 @@
 // aps_abi_pairwise.cu -- the pairwise half of the extern "C" surface (include/apsmatch.h): matchFeaturesScratch for one
 // pair, featureMatchingPairwise in one call, and the staged pairwise pipeline aps_pplan_* (screen stage, exact stage,
 // subset views of 'subsetpdist2', PCA views of 'pca2nn').  No CPU compute path: without a CUDA device every entry fails.
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <limits>
 #include <new>
@@ -696,8 +698,12 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
   std::vector<int64_t> outoff(np + 1, 0);
   for (int p = 0; p < np; ++p) outoff[p + 1] = outoff[p] + hc[p];
   const int64_t M = outoff[np];
-  std::vector<uint32_t> hrows((size_t)M * 2);
-  std::vector<double> hmet((size_t)M);
+  // rows and metric of the batch land in ONE pinned staging area (a pageable destination is copied through the
+  // driver's bounce buffers at a fraction of the PCIe rate) and are split per pair from there
+  uint8_t* stage = M > 0 ? (uint8_t*)aps_ctx_stage(c, (size_t)M * 16) : nullptr;
+  if (M > 0 && !stage) APS_FAIL(APS_ERR_ALLOC, "", "out of pinned host memory (%lld match rows)", (long long)M);
+  const uint32_t* hrows = (const uint32_t*)stage;
+  const double* hmet = (const double*)(stage + (size_t)M * 8);
   if (M > 0) {
     DevBuf<uint32_t> rows;
     DevBuf<double> met;
@@ -708,15 +714,16 @@ static int pairwise_batch(aps_ctx* c, PairwiseSets& ps, const std::vector<PairRe
     APS_CUDA(cudaMemcpyAsync(d_outoff.p, outoff.data(), (np + 1) * 8, cudaMemcpyHostToDevice, s));
     k_gather_pairs<<<(unsigned)np, 128, 0, s>>>(matches.p, metric.p, d_eoff.p, d_outoff.p, rows.p, met.p);
     APS_LAUNCHED();
-    APS_CUDA(cudaMemcpyAsync(hrows.data(), rows.p, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
-    APS_CUDA(cudaMemcpyAsync(hmet.data(), met.p, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+    APS_CUDA(cudaMemcpyAsync(stage, rows.p, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
+    APS_CUDA(cudaMemcpyAsync(stage + (size_t)M * 8, met.p, (size_t)M * 8, cudaMemcpyDeviceToHost, s));
     APS_CUDA(cudaStreamSynchronize(s));
   }
   for (int p = 0; p < np; ++p) {
     const size_t o = pairs[p].ordinal;
     out_count[o] = hc[p];
-    out_rows[o].assign(hrows.begin() + 2 * outoff[p], hrows.begin() + 2 * outoff[p + 1]);
-    out_metric[o].assign(hmet.begin() + outoff[p], hmet.begin() + outoff[p + 1]);
+    if (hc[p] == 0) continue;
+    out_rows[o].assign(hrows + 2 * outoff[p], hrows + 2 * outoff[p + 1]);
+    out_metric[o].assign(hmet + outoff[p], hmet + outoff[p + 1]);
   }
   return APS_OK;
 }
@@ -942,10 +949,14 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
       (norm ? mine_norm : mine_raw).push_back(pr);
     }
     c->pair_stats[0] = c->pair_stats[1] = c->pair_stats[2] = c->pair_stats[3] = 0;
+    const bool dbg_t = getenv("APS_TIMING") != nullptr;
+    auto dbg_now = [&]() { cudaStreamSynchronize(c->stream); return std::chrono::steady_clock::now(); };
+    auto dbg_t0 = dbg_t ? dbg_now() : std::chrono::steady_clock::time_point();
     if (tensor && c->pairwise_screen && !pca) {
       rc = pairwise_screen_stage(c, ps, mine_raw, counts, D, false, match_threshold, max_ratio);
       if (rc == APS_OK) rc = pairwise_screen_stage(c, ps, mine_norm, counts, D, true, match_threshold, max_ratio);
     }
+    auto dbg_t1 = dbg_t ? dbg_now() : dbg_t0;
     std::vector<int32_t> cnt(NP, 0);
     std::vector<std::vector<uint32_t>> prow(NP);
     std::vector<std::vector<double>> pmet(NP);
@@ -966,6 +977,7 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
         a = b;
       }
     }
+    auto dbg_t2 = dbg_t ? dbg_now() : dbg_t0;
     if (rc == APS_OK) {
       size_t o = 0;
       for (int j = 0; j < n; ++j)
@@ -979,9 +991,16 @@ extern "C" int aps_pplan_match(aps_pplan* p, double match_threshold, double max_
       m->rows.reserve((size_t)m->total * 2);
       m->metric.reserve((size_t)m->total);
       for (size_t q = 0; q < NP; ++q) {
+        if (prow[q].empty()) continue;
         m->rows.insert(m->rows.end(), prow[q].begin(), prow[q].end());
         m->metric.insert(m->metric.end(), pmet[q].begin(), pmet[q].end());
       }
+    }
+    if (dbg_t) {
+      auto dbg_t3 = dbg_now();
+      auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      fprintf(stderr, "aps_pplan_match: screen %.2f ms, batches %.2f ms, assemble %.2f ms\n", ms(dbg_t0, dbg_t1), ms(dbg_t1, dbg_t2),
+              ms(dbg_t2, dbg_t3));
     }
   }
   if (rc != APS_OK) {

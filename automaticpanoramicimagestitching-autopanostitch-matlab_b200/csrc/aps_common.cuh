@@ -53,7 +53,20 @@ struct aps_ctx {
   std::vector<cudaEvent_t> tc_events;  // pairs (start, stop) of tcgen05 kernel launches
   int32_t* d_scratch_flags = nullptr;  // small persistent device scratch (64 ints)
   int32_t* h_flags = nullptr;          // pinned mirror
+  void* h_stage = nullptr;             // grow-only pinned staging area for result downloads (aps_ctx_stage)
+  size_t h_stage_bytes = 0;
 };
+// pinned host staging of at least `bytes` (contents undefined); nullptr on allocation failure
+inline void* aps_ctx_stage(aps_ctx* c, size_t bytes) {
+  if (bytes <= c->h_stage_bytes) return c->h_stage;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->h_stage = nullptr;
+  c->h_stage_bytes = 0;
+  const size_t want = bytes + bytes / 4 + 4096;
+  if (cudaMallocHost(&c->h_stage, want) != cudaSuccess) { c->h_stage = nullptr; (void)cudaGetLastError(); return nullptr; }
+  c->h_stage_bytes = want;
+  return c->h_stage;
+}
 
 // Stream-ordered device buffer (cudaMallocAsync pool: repeated calls re-use the same memory).
 template <class T>

@@ -30,10 +30,17 @@ __device__ __forceinline__ float l2sq_flann(const float* __restrict__ a, const f
   return result;
 }
 
+// The sequential helpers below read both rows with 128-bit loads when the rows allow it (length a multiple of four,
+// 16-byte aligned -- every row of a cudaMalloc'ed [rows x D] matrix then): a lane that owns a train row otherwise
+// issues four times the load instructions and touches each 32-byte sector eight times.  The ORDER of the float
+// operations is the scalar loop's: same bits.
+__device__ __forceinline__ bool rows_vec4(const float* a, const float* b, int D) {
+  return ((D & 3) == 0) && ((((uintptr_t)a | (uintptr_t)b) & 15u) == 0);
+}
+__device__ __forceinline__ float dot_seq(const float* __restrict__ a, const float* __restrict__ b, int D);
 __device__ __forceinline__ float ssd_seq(const float* __restrict__ a, const float* __restrict__ b, int D, float a2,
                                          float b2) {
-  float g = 0.f;
-  for (int d = 0; d < D; ++d) g = __fadd_rn(g, __fmul_rn(a[d], b[d]));
+  const float g = dot_seq(a, b, D);
   return __fsub_rn(__fadd_rn(a2, b2), __fmul_rn(2.0f, g));
 }
 
@@ -42,6 +49,20 @@ __device__ __forceinline__ float ssd_seq(const float* __restrict__ a, const floa
 // the caller ranks by sqrt_rn(s) and reports fmul_rn(r, r).
 __device__ __forceinline__ float l2sq_seq(const float* __restrict__ a, const float* __restrict__ b, int D) {
   float s = 0.f;
+  if (rows_vec4(a, b, D)) {
+    for (int d = 0; d < D; d += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(a + d), y = *reinterpret_cast<const float4*>(b + d);
+      float e = __fsub_rn(x.x, y.x);
+      s = __fadd_rn(s, __fmul_rn(e, e));
+      e = __fsub_rn(x.y, y.y);
+      s = __fadd_rn(s, __fmul_rn(e, e));
+      e = __fsub_rn(x.z, y.z);
+      s = __fadd_rn(s, __fmul_rn(e, e));
+      e = __fsub_rn(x.w, y.w);
+      s = __fadd_rn(s, __fmul_rn(e, e));
+    }
+    return s;
+  }
   for (int d = 0; d < D; ++d) {
     const float e = __fsub_rn(a[d], b[d]);
     s = __fadd_rn(s, __fmul_rn(e, e));
@@ -53,6 +74,16 @@ __device__ __forceinline__ float l2sq_seq(const float* __restrict__ a, const flo
 // G = A*B.' restated as a sequential float32 dot; the caller ranks by -sim and reports fl(2 - fl(2 sim)).
 __device__ __forceinline__ float dot_seq(const float* __restrict__ a, const float* __restrict__ b, int D) {
   float g = 0.f;
+  if (rows_vec4(a, b, D)) {
+    for (int d = 0; d < D; d += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(a + d), y = *reinterpret_cast<const float4*>(b + d);
+      g = __fadd_rn(g, __fmul_rn(x.x, y.x));
+      g = __fadd_rn(g, __fmul_rn(x.y, y.y));
+      g = __fadd_rn(g, __fmul_rn(x.z, y.z));
+      g = __fadd_rn(g, __fmul_rn(x.w, y.w));
+    }
+    return g;
+  }
   for (int d = 0; d < D; ++d) g = __fadd_rn(g, __fmul_rn(a[d], b[d]));
   return g;
 }
