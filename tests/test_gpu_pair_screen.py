@@ -226,3 +226,24 @@ def test_pca2nn_matches_the_oracle(aps, orc):
     m, d = aps.matchFeaturesScratch(A, B, Method="Approximate", MatchThreshold=1.5, MaxRatio=0.7, ctx=ctx)   # parser default = pca2nn
     om, od = orc.match_features_pca(A, B, 1.5, 0.7)
     assert np.array_equal(m, om) and np.array_equal(d, od)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D", [30, 61, 36])
+def test_descriptor_lengths_not_a_multiple_of_four(aps, orc, D):
+    """The sequential exact-distance helpers (aps_exact_math.cuh) read rows with 128-bit loads only when the row length
+    is a multiple of four and the rows are 16-byte aligned; D = 30 / 61 take the scalar loop, D = 36 the vector loop with a
+    padded operand length (Dp = 64).  Exhaustive and Euclidean ('subsetpdist2') modes against the oracle, matches and
+    metric bit for bit."""
+    rng = np.random.default_rng(900 + D)
+    A = rng.standard_normal((1500, D)).astype(np.float32)
+    B = rng.standard_normal((1700, D)).astype(np.float32)
+    B[:400] = A[200:600] + 0.01 * rng.standard_normal((400, D)).astype(np.float32)
+    B[400:420] = A[700:720]                                   # exact duplicates: ties
+    m, met = aps.matchFeaturesScratch(A, B, MatchThreshold=1.5, MaxRatio=0.7)
+    om, omet = orc.match_features(A, B, 1.5, 0.7)
+    assert len(om) > 300 and np.array_equal(m, om) and np.array_equal(met, omet), D
+    m, met = aps.matchFeaturesScratch(A, B, Method="Approximate", ApproxFloatNNMethod="subsetpdist2", MatchThreshold=1.5,
+                                      MaxRatio=0.7)
+    om, omet = orc.match_features_method(A, B, 1.5, 0.7, "subsetpdist2")
+    assert len(om) > 300 and np.array_equal(m, om) and np.array_equal(met, omet), D
