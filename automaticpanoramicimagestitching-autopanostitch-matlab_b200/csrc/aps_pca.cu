@@ -111,14 +111,18 @@ struct ProjSeg {   // rows [src, src + cnt) of X projected with the basis of ima
   int32_t cnt, basis;
 };
 
-// block = PR_ROWS rows x P components (P <= 64): the (x - mu) rows and the basis staged in shared memory
-constexpr int PR_ROWS = 32;
+// block = PR_ROWS rows x P components (P <= 64): the (x - mu) rows and the basis staged in shared memory.  Thread =
+// (component, row group): the component's basis column is read once per four dimensions and used for eight rows held in
+// registers, the rows come as broadcast 128-bit loads -- 0.4 shared-memory loads per multiply-add instead of 2 (the
+// first version was bound by the load/store pipe: 182 ms for the 44850 projections of C5).  Every y is still the
+// sequential float32 sum over d of the oracle.
+constexpr int PR_ROWS = 128;
 __global__ void __launch_bounds__(256) k_pca_project(const float* __restrict__ X, int D, int P,
                                                      const ProjSeg* __restrict__ segs,
                                                      const int64_t* __restrict__ blk_off, int nseg,
                                                      const float* __restrict__ mu, const float* __restrict__ coeff,
                                                      float* __restrict__ out) {
-  extern __shared__ float smf[];
+  extern __shared__ __align__(16) float smf[];
   float* cf = smf;               // [D][P]
   float* xs = cf + D * P;        // [PR_ROWS][D]  (x - mu)
   // segment of this block: last s with blk_off[s] <= blockIdx.x
@@ -137,12 +141,37 @@ __global__ void __launch_bounds__(256) k_pca_project(const float* __restrict__ X
     xs[i] = (row0 + r < sg.cnt) ? __fsub_rn(X[(sg.src + row0 + r) * D + d], mj[d]) : 0.f;
   }
   __syncthreads();
-  const int cidx = threadIdx.x % 64;
+  const int cidx = threadIdx.x % 64, rg = threadIdx.x / 64;
   if (cidx >= P) return;
-  for (int r = threadIdx.x / 64; r < PR_ROWS && row0 + r < sg.cnt; r += 4) {
-    float y = 0.f;
-    for (int d = 0; d < D; ++d) y = __fadd_rn(y, __fmul_rn(xs[r * D + d], cf[d * P + cidx]));
-    out[(sg.dst + row0 + r) * P + cidx] = y;
+  const bool vec = ((D & 3) == 0) && (((D * P) & 3) == 0);
+  for (int c0 = 0; c0 < PR_ROWS && row0 + c0 < sg.cnt; c0 += 32) {
+    float y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y[k] = 0.f;
+    if (vec) {
+      for (int d = 0; d < D; d += 4) {
+        const float b0 = cf[d * P + cidx], b1 = cf[(d + 1) * P + cidx], b2 = cf[(d + 2) * P + cidx], b3 = cf[(d + 3) * P + cidx];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 x = *reinterpret_cast<const float4*>(xs + (c0 + rg + 4 * k) * D + d);
+          y[k] = __fadd_rn(y[k], __fmul_rn(x.x, b0));
+          y[k] = __fadd_rn(y[k], __fmul_rn(x.y, b1));
+          y[k] = __fadd_rn(y[k], __fmul_rn(x.z, b2));
+          y[k] = __fadd_rn(y[k], __fmul_rn(x.w, b3));
+        }
+      }
+    } else {
+      for (int d = 0; d < D; ++d) {
+        const float bb = cf[d * P + cidx];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = __fadd_rn(y[k], __fmul_rn(xs[(c0 + rg + 4 * k) * D + d], bb));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t r = row0 + c0 + rg + 4 * k;
+      if (r < sg.cnt) out[(sg.dst + r) * P + cidx] = y[k];
+    }
   }
 }
 

@@ -212,7 +212,7 @@ static int prepare_norm_launch(cudaStream_t s, const float* raw, int64_t F, int6
     aps_set_error(APS_ERR_DIM, "", "descriptor dimension %d too large", D);
     return APS_ERR_DIM;
   }
-  auto kern = D == 128 ? k_prepare_norm<128> : (D == 64 ? k_prepare_norm<64> : k_prepare_norm<0>);
+  auto kern = D == 128 ? k_prepare_norm<128> : (D == 64 ? k_prepare_norm<64> : (D == 48 ? k_prepare_norm<48> : k_prepare_norm<0>));
   APS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t gx = aps_ceil_div(rows_per_y, (int64_t)PN_WARPS * 32);
   const int64_t cap = aps_ceil_div((int64_t)148 * 8, (int64_t)ny);   // a few CTAs per SM; warps loop over the rest
