@@ -21,15 +21,19 @@
 //   warps 1-2: one single-thread tcgen05.mma issuer per row block (warp 1 also owns the TMEM allocation);
 //              independent issuers remove head-of-line blocking between the two epilogue groups
 //   warps 3-6: epilogue group 0 = row block 0, warps 7-10: group 1 = row block 1 (thread == query row,
-//              tcgen05.ld 32x32b from the warp's TMEM lane quadrant).  Per 32-column chunk:
-//              (1) raw pre-filter: FMNMX3 tree over the 32 accumulators, one compare with a per-tile
-//                  threshold derived from the row's K'-th best (theta) and the tile's (min,max) column
-//                  scale / bias (aps_k_tile_bounds; the train view is sorted by scale so the bounds are
-//                  tight) -- a chunk that cannot hold a candidate costs ~31 instructions;
-//              (2) otherwise score = acc*scale (+bias) with the constants read as broadcast LDS.128,
-//                  exact group maxima, and a branch-free replace-min for the groups that hold a
-//                  candidate: scores in registers as packed keys (value bits & ~7 | slot), train-row
-//                  indices in shared memory.
+//              tcgen05.ld 32x32b from the warp's TMEM lane quadrant).  Long sweeps (PRE), per 128-column tile:
+//              (1) straight-line scan: all four tcgen05.ld .x32 in flight, 16 FMNMX3 trees = the maxima of the 16
+//                  8-column groups of RAW accumulators, against a per-tile threshold derived from the row's K'-th
+//                  best (theta) and the tile's (min,max) column scale / bias (aps_k_tile_bounds; the train view
+//                  is sorted by scale so the bounds are tight) -- no per-column constant, no multiply;
+//              (2) ONE warp vote; no lane flagged a group -> next tile (~270 instructions per tile and warp);
+//              (3) otherwise the union of the flagged groups is RE-READ from TMEM (tcgen05.ld .x8, rounds of four)
+//                  by the converged warp, the slot is handed back to the tensor pipe, and the flagged lanes scale
+//                  (broadcast LDS.128 of the constants), search and replace-min: scores in registers as packed
+//                  keys (value bits & ~7 | slot), train-row indices in shared memory.  One run-time-indexed copy
+//                  of the insertion code.
+//              Short sweeps (!PRE: the lists never leave their filling phase) keep the per-chunk loop: scale every
+//              32-column chunk, group maxima, branch-free replace-min for the groups that hold a candidate.
 // TMEM: 4 accumulator slots of 128 columns = slot(tile parity, row block): the tensor pipe fills the
 // slots of tile t+1 while both groups drain tile t.  Pipelines (all mbarrier based): B ring (4 x 32 KB),
 // A pair (single buffered per unit), accumulator slots, (scale,bias) ring.
@@ -37,23 +41,21 @@
 // balanced either by cutting its units into <= 4 equal column segments or by cutting its tile steps into
 // one equal share per CTA (make_schedule), each piece filling its own candidate list of the row.
 //
-// What bounds it (round 1 measurements, C2 = 163840^2 pairs, D = 128, same box, profiles/r1_ncu_history.txt):
-//   * selection skipped (accumulators never read): TMA + MMA alone 3.99 ms = 1723 TFLOP/s -- the floor of
-//     this tiling;
-//   * epilogue that reads every accumulator (tcgen05.ld) and runs 63 ALU instructions per chunk but never
-//     selects: 4.80 ms = 1432 TFLOP/s -- so the TMEM read path is NOT the limiter;
-//   * full kernel: 6.1 ms = 1120-1130 TFLOP/s (83-84 % of the measured sustained bf16 peak) with 8 candidates per
-//     list, 5.75 ms = 1194 TFLOP/s (89 %) with 6 (operands exact in bf16, e.g. integer SIFT).  The epilogue
-//     is issue/latency bound: two epilogue warps per scheduler at IPC 0.43 ('wait' 31 % of the samples);
-//     2.25e9 epilogue warp instructions per launch = per tile 73 + 2 x 63 on the fast path, and 0.95e9
-//     in the candidate path, which 19 % of the chunks enter (K'(1 + ln(F/K')) ~ 87 insertions per row are
-//     inherent to a streaming top-K').  acc_full waits are 13 % of the samples: the first tiles of a unit
-//     are epilogue-bound (lists filling), the last ones MMA-bound.
-//   * not kept: two lists per row on column halves with 16 epilogue warps (6.89 ms: twice the
-//     insertions), a fully unrolled chunk loop (6.81 ms: instruction cache), fp16 accumulators (rounding
-//     breaks the completeness proof on SIFT-like data: median d8-d4 gap 0.016);
-//   * earlier designs: one row block per unit, epilogue split by columns, single MMA issuer: 8.23 ms;
-//     fully unrolled register-resident sorted top-K: 348 KB of SASS, 69 % instruction-fetch stalls, 109 ms.
+// What bounds it (C2 = 163840^2 pairs, D = 128; profiles/r2_ncu_history.txt, profiles/r2_ncu_k_knn_tc.txt):
+//   * accumulators never read (-DAPS_TC_NOEPI): TMA + MMA alone 3.39 ms = 2027 TFLOP/s -- the floor of this tiling
+//     (85 % of nominal; the same with the A operand in TMEM: shared-memory bandwidth is not the limiter);
+//   * full kernel 4.71-4.87 ms = 1410-1460 TFLOP/s = 0.88-0.90 of the measured cuBLAS bf16 burst figure (round 1:
+//     5.79 ms; per-chunk group-gated version: 5.32 ms); C3 (F = 1e6, long sweeps) 1635 TFLOP/s = 1.01 of it.
+//     What is left at C2 is the VARIANCE of the epilogue: a tile with insertions (39 % of them) takes ~4x the cycles
+//     of one without, and two accumulator slots per row block cannot average that out: the epilogue warps wait for
+//     acc_full 22 % of their time while the issuers spin on acc_empty.  K'(1 + ln(F/K')) ~ 67 insertions per row are
+//     inherent to a streaming top-K';
+//   * not kept: A operand in TMEM with three slots (5.34 ms); separate scan / insert warps with setmaxnreg
+//     (5.13 ms: the per-tile hand-off costs more than it frees); two lists per row on column halves with 16
+//     epilogue warps (twice the insertions); fp16 accumulators (rounding breaks the completeness proof on
+//     SIFT-like data: median d8-d4 gap 0.016);
+//   * earlier designs: one row block per unit, epilogue split by columns, single MMA issuer: 8.23 ms; fully unrolled
+//     register-resident sorted top-K: 348 KB of SASS, 69 % instruction-fetch stalls, 109 ms.
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2*D per (query, train) pair.  HBM traffic is
 // negligible (operands stream from L2: every concurrently running CTA walks the same B tiles).
