@@ -117,7 +117,7 @@ struct ProjSeg {   // rows [src, src + cnt) of X projected with the basis of ima
 // first version was bound by the load/store pipe: 182 ms for the 44850 projections of C5).  Every y is still the
 // sequential float32 sum over d of the oracle.
 constexpr int PR_ROWS = 128;
-__global__ void __launch_bounds__(256) k_pca_project(const float* __restrict__ X, int D, int P,
+__global__ void __launch_bounds__(256) k_pca_project(const float* __restrict__ X, int D, int P,  // (4 * P threads)
                                                      const ProjSeg* __restrict__ segs,
                                                      const int64_t* __restrict__ blk_off, int nseg,
                                                      const float* __restrict__ mu, const float* __restrict__ coeff,
@@ -135,15 +135,30 @@ __global__ void __launch_bounds__(256) k_pca_project(const float* __restrict__ X
   const int64_t row0 = ((int64_t)blockIdx.x - blk_off[lo]) * PR_ROWS;
   const float* cj = coeff + (int64_t)sg.basis * D * P;
   const float* mj = mu + (int64_t)sg.basis * D;
+  const bool vec = ((D & 3) == 0) && (((D * P) & 3) == 0);
   for (int i = threadIdx.x; i < D * P; i += blockDim.x) cf[i] = cj[i];
-  for (int i = threadIdx.x; i < PR_ROWS * D; i += blockDim.x) {
-    const int r = i / D, d = i - r * D;
-    xs[i] = (row0 + r < sg.cnt) ? __fsub_rn(X[(sg.src + row0 + r) * D + d], mj[d]) : 0.f;
+  if (vec) {   // rows of X are 16-byte aligned then (cudaMalloc'ed [rows x D] matrix)
+    const int d4 = D >> 2;
+    for (int i = threadIdx.x; i < PR_ROWS * d4; i += blockDim.x) {
+      const int r = i / d4, d = (i - r * d4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < sg.cnt) {
+        const float4 x = *reinterpret_cast<const float4*>(X + (sg.src + row0 + r) * D + d);
+        const float4 m = *reinterpret_cast<const float4*>(mj + d);
+        v = make_float4(__fsub_rn(x.x, m.x), __fsub_rn(x.y, m.y), __fsub_rn(x.z, m.z), __fsub_rn(x.w, m.w));
+      }
+      *reinterpret_cast<float4*>(xs + r * D + d) = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < PR_ROWS * D; i += blockDim.x) {
+      const int r = i / D, d = i - r * D;
+      xs[i] = (row0 + r < sg.cnt) ? __fsub_rn(X[(sg.src + row0 + r) * D + d], mj[d]) : 0.f;
+    }
   }
   __syncthreads();
-  const int cidx = threadIdx.x % 64, rg = threadIdx.x / 64;
-  if (cidx >= P) return;
-  const bool vec = ((D & 3) == 0) && (((D * P) & 3) == 0);
+  // thread = (component, row group): with P = 48 components the block is launched with 4 * 48 = 192 threads, all busy
+  const int cidx = threadIdx.x % P, rg = threadIdx.x / P;
+  if (rg >= 4) return;
   for (int c0 = 0; c0 < PR_ROWS && row0 + c0 < sg.cnt; c0 += 32) {
     float y[8];
 #pragma unroll
@@ -221,7 +236,7 @@ int aps_k_pca_project(cudaStream_t s, const float* X, int D, int P, const std::v
   APS_CUDA(cudaStreamSynchronize(s));   // pageable host tables
   const size_t smem = ((size_t)D * P + (size_t)PR_ROWS * D) * sizeof(float);
   APS_CUDA(cudaFuncSetAttribute(k_pca_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pca_project<<<(unsigned)boff.back(), 256, smem, s>>>(X, D, P, d_seg.p, d_boff.p, (int)segs.size(), mu, coeff, out);
+  k_pca_project<<<(unsigned)boff.back(), 4 * P, smem, s>>>(X, D, P, d_seg.p, d_boff.p, (int)segs.size(), mu, coeff, out);
   APS_LAUNCHED();   // d_seg / d_boff are released in stream order
   return APS_OK;
 }
